@@ -1,0 +1,80 @@
+"""ctypes binding of libgens_b200.so -- the only door from Python into the CUDA kernels.
+
+There is no CPU fallback: if the shared library is missing or a call fails this raises.
+torch is used only for device memory and the current stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libgens_b200.so")
+ABI_VERSION = 1
+DIV_TRUE, DIV_RECIP = 0, 1
+
+_lib = None
+
+_vp, _i, _ll, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+
+_SIGNATURES = {
+    "gens_abi_version": ([], _i),
+    "gens_error_string": ([_i], ctypes.c_char_p),
+    "gens_nchw4_to_nhwc4": ([_vp, _vp, _i, _i, _i, _vp], _i),
+    "gens_volume_agg_fwd": ([_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _i, _i, _vp, _vp, _vp], _i),
+    "gens_volume_project_debug": ([_i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp], _i),
+    "gens_volume_agg_bwd": ([_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _i, _vp, _vp, _vp], _i),
+}
+
+
+def exported_symbols():
+    """Names every build of the library must export (mirrors include/gens_b200.h)."""
+    return list(_SIGNATURES)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m gens_b200.build` "
+                "(gens_b200 has no CPU or PyTorch fallback)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (argtypes, restype) in _SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the .so is stale
+            fn.argtypes = argtypes
+            fn.restype = restype
+        got = handle.gens_abi_version()
+        if got != ABI_VERSION:
+            raise RuntimeError(f"libgens_b200.so ABI {got} != expected {ABI_VERSION}; rebuild")
+        _lib = handle
+    return _lib
+
+
+def check(code: int, what: str):
+    if code != 0:
+        msg = lib().gens_error_string(code)
+        raise RuntimeError(f"{what} failed ({code}): {msg.decode() if msg else '?'}")
+
+
+def ptr(t: torch.Tensor):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("gens_b200 kernels need CUDA tensors (no CPU fallback); got a "
+                               f"{t.device} tensor")
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()

@@ -1,0 +1,157 @@
+"""Parity of K1 (fused volume aggregation) through the C ABI, on the B200."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from gens_b200 import _lib
+from gens_b200.synthetic import make_scene
+from gens_b200.volume import Volume, agg_mean_var_scale, stage_cameras, to_channels_last4
+from oracle import c_oracle, torch_oracle
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+# fp32 tolerance of north_star: max rel err 1e-4 (+ an absolute floor for cancelling variances)
+RTOL, ATOL = 1e-4, 1e-6
+
+
+def _project_debug(intrs, c2ws, scale, d, hw, div_mode):
+    w2c, k = stage_cameras(intrs, c2ws, scale)
+    grid = torch.linspace(-1, 1, d, device=DEV)
+    nv = intrs.shape[0]
+    ix0 = torch.empty((nv, d, d, d), dtype=torch.int32, device=DEV)
+    iy0 = torch.empty_like(ix0)
+    valid = torch.empty((nv, d, d, d), dtype=torch.uint8, device=DEV)
+    _lib.check(_lib.lib().gens_volume_project_debug(nv, hw[0], hw[1], _lib.ptr(w2c), _lib.ptr(k), _lib.ptr(grid), d,
+                                                    div_mode, _lib.ptr(ix0), _lib.ptr(iy0), _lib.ptr(valid),
+                                                    _lib.stream_ptr()), "project_debug")
+    return ix0.cpu().numpy(), iy0.cpu().numpy(), valid.cpu().numpy()
+
+
+def test_golden_fixture_bit_exact_vs_reference_cpu(cuda_lib, golden_dir):
+    """div_mode TRUE reproduces the reference's CPU run: masks and indices bit-exact, values 1e-4."""
+    g = np.load(f"{golden_dir}/volume_agg.npz")
+    intrs = torch.from_numpy(g["intrs"])
+    c2ws = torch.from_numpy(g["c2ws"])
+    # camera prologue on the CPU, exactly the golden run's matrices, then moved over
+    for i, d in enumerate(g["dims"]):
+        d = int(d)
+        feat = torch.from_numpy(g[f"feat{i}"]).to(DEV)
+        h, w = feat.shape[-2:]
+        k = intrs.clone()
+        k[:, :2] *= 0.5 ** i
+        w2c = torch.inverse(c2ws)
+        vol = torch.empty((8, d, d, d), device=DEV)
+        msk = torch.empty((d, d, d), device=DEV)
+        grid = torch.linspace(-1, 1, d)
+        _lib.check(_lib.lib().gens_volume_agg_fwd(
+            _lib.ptr(to_channels_last4(feat)), 3, h, w, _lib.ptr(w2c.to(DEV)), _lib.ptr(k.to(DEV)),
+            _lib.ptr(grid.to(DEV)), d, 0, d, 0, d ** 3, 1, _lib.DIV_TRUE, _lib.ptr(vol), _lib.ptr(msk),
+            _lib.stream_ptr()), "agg")
+        assert np.array_equal(msk.cpu().numpy(), g[f"mask{i}"])
+        ref = g[f"volume{i}"]
+        assert np.all(np.abs(vol.cpu().numpy() - ref) <= ATOL + RTOL * np.abs(ref))
+        # projection stage
+        ix0 = torch.empty((3, d, d, d), dtype=torch.int32, device=DEV)
+        iy0 = torch.empty_like(ix0)
+        valid = torch.empty((3, d, d, d), dtype=torch.uint8, device=DEV)
+        _lib.check(_lib.lib().gens_volume_project_debug(
+            3, h, w, _lib.ptr(w2c.to(DEV)), _lib.ptr(k.to(DEV)), _lib.ptr(grid.to(DEV)), d, _lib.DIV_TRUE,
+            _lib.ptr(ix0), _lib.ptr(iy0), _lib.ptr(valid), _lib.stream_ptr()), "dbg")
+        vm = g[f"viewmask{i}"]
+        assert np.array_equal(valid.cpu().numpy(), vm)
+        rix, riy = torch_oracle.corner_indices(torch.from_numpy(g[f"grid{i}"]), (h, w))
+        sel = vm.astype(bool)
+        assert np.array_equal(ix0.cpu().numpy()[sel], rix.numpy().reshape(vm.shape)[sel])
+        assert np.array_equal(iy0.cpu().numpy()[sel], riy.numpy().reshape(vm.shape)[sel])
+
+
+@pytest.mark.parametrize("nv,hw,dims", [(3, (240, 320), [64, 32, 16, 8, 4]), (5, (96, 128), [48, 20, 12, 6, 3])])
+def test_matches_c_oracle(cuda_lib, nv, hw, dims):
+    """Seeded synthetic scenes (config 1 shape + a ragged one with D % 4 != 0): CUDA == C oracle."""
+    sc = make_scene(hw[0], hw[1], nv, seed=3)
+    for div_mode in (_lib.DIV_TRUE, _lib.DIV_RECIP):
+        for i, d in enumerate(dims):
+            w2c, k = stage_cameras(sc.intrs, sc.c2ws, i)
+            grid = torch.linspace(-1, 1, d)
+            ovol, omsk, oix, oiy, ovm = c_oracle.volume_agg(sc.features[i].numpy(), w2c.numpy(), k.numpy(),
+                                                            grid.numpy(), div_mode=div_mode, debug=True)
+            feat = sc.features[i].to(DEV)
+            vol = torch.empty((8, d, d, d), device=DEV)
+            msk = torch.empty((d, d, d), device=DEV)
+            h, w = feat.shape[-2:]
+            _lib.check(_lib.lib().gens_volume_agg_fwd(
+                _lib.ptr(to_channels_last4(feat)), nv, h, w, _lib.ptr(w2c.to(DEV)), _lib.ptr(k.to(DEV)),
+                _lib.ptr(grid.to(DEV)), d, 0, d, 0, d ** 3, 1, div_mode, _lib.ptr(vol), _lib.ptr(msk),
+                _lib.stream_ptr()), "agg")
+            assert np.array_equal(msk.cpu().numpy(), omsk), (div_mode, d)
+            assert np.all(np.abs(vol.cpu().numpy() - ovol) <= ATOL + RTOL * np.abs(ovol)), (div_mode, d)
+            ix0 = torch.empty((nv, d, d, d), dtype=torch.int32, device=DEV)
+            iy0 = torch.empty_like(ix0)
+            valid = torch.empty((nv, d, d, d), dtype=torch.uint8, device=DEV)
+            _lib.check(_lib.lib().gens_volume_project_debug(
+                nv, h, w, _lib.ptr(w2c.to(DEV)), _lib.ptr(k.to(DEV)), _lib.ptr(grid.to(DEV)), d, div_mode,
+                _lib.ptr(ix0), _lib.ptr(iy0), _lib.ptr(valid), _lib.stream_ptr()), "dbg")
+            assert np.array_equal(valid.cpu().numpy(), ovm)
+            assert np.array_equal(ix0.cpu().numpy(), oix) and np.array_equal(iy0.cpu().numpy(), oiy)
+
+
+def test_public_api_matches_aten_ops_on_gpu(cuda_lib):
+    """Volume.agg_mean_var (default DIV_RECIP) vs the same ATen op sequence the reference would run on
+    this GPU: visibility masks bit-exact, volumes within tolerance."""
+    sc = make_scene(240, 320, 3, seed=1).to(DEV)
+    dims = [64, 32, 16, 8, 4]
+    vols, masks = Volume(volume_dims=dims).agg_mean_var(sc.features, sc.intrs, sc.c2ws)
+    rvols, rmasks = torch_oracle.agg_mean_var(sc.features, sc.intrs, sc.c2ws, dims)
+    for i in range(5):
+        assert vols[i].shape == rvols[i].shape and masks[i].shape == rmasks[i].shape
+        assert torch.equal(masks[i], rmasks[i]), f"scale {i}: {(masks[i] != rmasks[i]).sum().item()} mask flips"
+        assert torch.all((vols[i] - rvols[i]).abs() <= ATOL + RTOL * rvols[i].abs())
+
+
+def test_full_size_properties(cuda_lib):
+    """BASELINE config 2 sizes (480x640, 3 views, 256..16): slab builds are bit-identical to the full
+    build; mask == (count of valid views > 1); invalid voxels are exactly zero."""
+    sc = make_scene(480, 640, 3, seed=0).to(DEV)
+    dims = [256, 128, 64, 32, 16]
+    vols, masks = Volume(volume_dims=dims).agg_mean_var(sc.features, sc.intrs, sc.c2ws)
+    for i, d in enumerate(dims):
+        parts = [agg_mean_var_scale(sc.features[i], sc.intrs, sc.c2ws, i, d, 1, (a, a + d // 8))
+                 for a in range(0, d, d // 8)]
+        assert torch.equal(torch.cat([p[0] for p in parts], 2), vols[i])
+        assert torch.equal(torch.cat([p[1] for p in parts], 2), masks[i])
+        _, _, valid = _project_debug(sc.intrs, sc.c2ws, i, d, sc.features[i].shape[-2:], _lib.DIV_RECIP)
+        cnt = valid.sum(0)
+        assert np.array_equal(masks[i][0, 0].cpu().numpy(), (cnt > 1).astype(np.float32))
+        dead = torch.from_numpy(cnt == 0).to(DEV)
+        assert vols[i][0][:, dead].abs().max().item() == 0.0
+        fill = masks[i].mean().item()
+        assert 0.15 < fill < 0.6, fill
+    # largest scale against the ATen op sequence on the same device (64^3 sub-sample to bound memory)
+    rvol, rmask = torch_oracle.agg_mean_var_scale(sc.features[2], sc.intrs, sc.c2ws, 2, 64)
+    assert torch.equal(rmask, masks[2])
+    assert torch.all((vols[2] - rvol).abs() <= ATOL + RTOL * rvol.abs())
+
+
+def test_backward_matches_autograd_of_aten_ops(cuda_lib):
+    sc = make_scene(96, 128, 3, seed=5).to(DEV)
+    d = 32
+    feat = sc.features[0].clone().requires_grad_(True)
+    vol, _ = agg_mean_var_scale(feat, sc.intrs, sc.c2ws, 0, d)
+    gout = torch.randn_like(vol)
+    (gfeat,) = torch.autograd.grad(vol, feat, gout)
+    feat2 = sc.features[0].clone().requires_grad_(True)
+    rvol, _ = torch_oracle.agg_mean_var_scale(feat2, sc.intrs, sc.c2ws, 0, d)
+    (rg,) = torch.autograd.grad(rvol, feat2, gout)
+    scale = rg.abs().max().item()
+    assert torch.all((gfeat - rg).abs() <= 1e-5 * scale + 1e-4 * rg.abs())
+
+
+def test_rejects_cpu_tensors_and_bad_channels(cuda_lib):
+    sc = make_scene(96, 128, 3, seed=0)
+    with pytest.raises(RuntimeError):
+        Volume(volume_dims=[8]).agg_mean_var(sc.features, sc.intrs, sc.c2ws)
+    with pytest.raises(RuntimeError):
+        to_channels_last4(torch.zeros(1, 3, 4, 4, device=DEV))
