@@ -19,13 +19,26 @@ _lib = None
 
 _vp, _i, _ll, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
 
+class VolumeScale(ctypes.Structure):
+    """Mirror of gens_volume_scale_t (include/gens_b200.h)."""
+    _fields_ = [
+        ("feat_padded", _vp), ("H", _i), ("W", _i), ("D", _i), ("a0", _i), ("a1", _i), ("a_base", _i),
+        ("channel_stride", _ll), ("k_row_scale", _f), ("grid", _vp), ("volume", _vp), ("mask_volume", _vp),
+    ]
+
+
 _SIGNATURES = {
     "gens_abi_version": ([], _i),
     "gens_error_string": ([_i], ctypes.c_char_p),
-    "gens_nchw4_to_nhwc4": ([_vp, _vp, _i, _i, _i, _vp], _i),
-    "gens_volume_agg_fwd": ([_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _i, _i, _vp, _vp, _vp], _i),
-    "gens_volume_project_debug": ([_i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp], _i),
-    "gens_volume_agg_bwd": ([_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _i, _vp, _vp, _vp], _i),
+    "gens_pack_feature_maps": ([_vp, _vp, _i, _i, _i, _vp], _i),
+    "gens_pack_feature_maps_multi": ([_vp, _vp, _vp, _vp, _i, _i, _vp], _i),
+    "gens_unpack_feature_grads": ([_vp, _vp, _i, _i, _i, _vp], _i),
+    "gens_volume_agg_fwd_multi": ([ctypes.POINTER(VolumeScale), _i, _i, _vp, _vp, _i, _i, _vp], _i),
+    "gens_volume_agg_fwd": ([_vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _i, _i, _i, _ll, _i, _i, _vp, _vp, _vp], _i),
+    "gens_volume_project_debug": ([_i, _i, _i, _vp, _vp, _f, _vp, _i, _i, _vp, _vp, _vp, _vp], _i),
+    "gens_volume_agg_bwd": ([_vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _i, _i, _i, _ll, _i, _vp, _vp, _vp], _i),
+    "gens_debug_set_variant": ([_i], _i),
+    "gens_selftest_division": ([_i, ctypes.c_ulonglong, _vp, _vp], _i),
 }
 
 

@@ -2,61 +2,90 @@
 //
 // Replaces one scale of Volume.agg_mean_var (reference models/modules/volume.py:21-58), which
 // runs ~320 ATen ops and >= 15 full (nv,.,D^3) temporaries per scale, with ONE launch that
-// reads each feature map once (through L2) and writes the 8+1 output channels once.
+// reads each feature map once (through L1/L2) and writes the 8+1 output channels once.
 //
-// Mapping: one thread owns VEC consecutive voxels along the fastest tensor dim (world z), so
-// each of the 9 channel planes is written with one coalesced 16-byte streaming store per
-// thread (512 B per warp per plane).  Camera matrices live in shared memory; the x/y part
-// of the k-ascending projection chain is shared by the VEC voxels of a thread.  Feature
-// maps are channels-last (nv,H,W,4): one bilinear corner = one 16-byte read-only load, and
-// neighbouring voxels hit neighbouring pixels so the gathers are served by L1/L2.
+// Data layout.  Feature maps are re-packed once per call to channels-last with one zero
+// row/column of padding, (nv, H+1, W+1, 4): a bilinear corner is a single 16-byte read-only
+// load and the +1 corners of any valid sample exist in memory, so the four gathers are
+// unconditional.  Outputs are the reference's NCDHW planes, written with coalesced
+// streaming stores.
 //
-// Arithmetic is the reference's, step for step (see oracle/gens_oracle.c for the CPU
-// restatement it is tested against): two-stage projection, IEEE division, the two-moment
-// variance E[x^2]-E[x]^2 (NOT Welford: parity with the reference's cancellation behaviour
-// is the contract), every rounding spelled with _rn intrinsics.
+// Mapping (packed kernel, D % 128 == 0).  A warp owns 32 CONSECUTIVE voxels along the fastest
+// tensor dim (world z); a thread owns four voxels 32 apart.  Consecutive voxels project
+// about one pixel apart, so a warp-wide gather touches 4-5 cache lines instead of the 16 a
+// "4 consecutive voxels per thread" layout would; every store instruction is one full
+// 128-byte line.  The kernel is bound by instruction issue and L1 gather bandwidth, not HBM
+// (see DESIGN.md), so the arithmetic runs on Blackwell's packed fp32x2 pipe: two voxels per
+// FFMA2 in the projection, two channels per FFMA2 in the bilinear accumulation.
+//
+// Arithmetic is the reference's, rounding for rounding (oracle/gens_oracle.c is the CPU
+// restatement it is tested against bit-for-bit): two-stage projection as k-ascending fma
+// chains, IEEE division, two-moment variance E[x^2]-E[x]^2 (NOT Welford -- parity with the
+// reference's cancellation behaviour is the contract).
 #include "common.cuh"
+#include "f32x2.cuh"
 
 namespace {
 
-struct Cam {
+struct __align__(16) Cam {
     float w2c[16];
     float k[12];
+    int affine;  // w2c row 3 == (0,0,0,1), K == [[fx,0,cx,0],[0,fy,cy,0],[0,0,1,0]]
+    int pad[3];
 };
 
+struct Extent {
+    float hx, hy, inv_hx, inv_hy;
+};
+
+// Stage the per-view matrices in shared memory.  `k_row_scale` = 0.5^scale multiplies rows 0-1 of
+// the intrinsics exactly as the reference's `intrs_stage[:, :2] *= 0.5**i` (volume.py:25); a
+// power-of-two factor, so the product is exact and bit-identical to the torch op.
+__device__ __forceinline__ void load_cams(Cam* s_cam, const float* w2c, const float* intrs, float k_row_scale,
+                                          int nv) {
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthreads = blockDim.x * blockDim.y;
+    for (int i = tid; i < nv * 32; i += nthreads) {
+        const int v = i >> 5, j = i & 31;
+        if (j < 16) s_cam[v].w2c[j] = w2c[v * 16 + j];
+        else if (j < 28) s_cam[v].k[j - 16] = __fmul_rn(intrs[v * 16 + (j - 16)], j < 24 ? k_row_scale : 1.0f);
+    }
+    __syncthreads();
+    if (tid < nv) {
+        const float* w = s_cam[tid].w2c;
+        const float* k = s_cam[tid].k;
+        s_cam[tid].affine = w[12] == 0.f && w[13] == 0.f && w[14] == 0.f && w[15] == 1.f && k[1] == 0.f &&
+                            k[3] == 0.f && k[4] == 0.f && k[7] == 0.f && k[8] == 0.f && k[9] == 0.f &&
+                            k[10] == 1.f && k[11] == 0.f;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// scalar path (any D): one voxel per thread.  Also the parity view of the projection stage.
+// ------------------------------------------------------------------------------------------
 struct Proj {
     float ix, iy;
     bool valid;
 };
 
 template <bool RECIP>
-__device__ __forceinline__ float div_scalar(float a, float b, float inv_b) {
-    return RECIP ? __fmul_rn(a, inv_b) : __fdiv_rn(a, b);
-}
-
-// Finish the projection of one voxel given the x/y partial sums of the camera transform.
-template <bool RECIP>
-__device__ __forceinline__ Proj project_finish(const Cam& cam, const float pre[4], float z, float hx,
-                                                float hy, float inv_hx, float inv_hy, int W, int H) {
+__device__ __forceinline__ Proj project_scalar(const Cam& cam, float X, float Y, float Z, const Extent& e) {
     float c[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        float t = __fmaf_rn(cam.w2c[4 * r + 2], z, pre[r]);
-        c[r] = __fmaf_rn(cam.w2c[4 * r + 3], 1.0f, t);
-    }
+    for (int r = 0; r < 4; ++r) c[r] = row_dot4(cam.w2c + 4 * r, X, Y, Z, 1.0f);
     float img[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) img[r] = row_dot4(cam.k + 4 * r, c[0], c[1], c[2], c[3]);
-    float den = __fadd_rn(img[2], 1e-8f);
-    float x = __fdiv_rn(img[0], den);
-    float y = __fdiv_rn(img[1], den);
-    float nx = __fsub_rn(div_scalar<RECIP>(x, hx, inv_hx), 1.0f);
-    float ny = __fsub_rn(div_scalar<RECIP>(y, hy, inv_hy), 1.0f);
+    const float den = __fadd_rn(img[2], 1e-8f);
+    const float x = __fdiv_rn(img[0], den), y = __fdiv_rn(img[1], den);
+    const float nx = __fsub_rn(RECIP ? __fmul_rn(x, e.inv_hx) : __fdiv_rn(x, e.hx), 1.0f);
+    const float ny = __fsub_rn(RECIP ? __fmul_rn(y, e.inv_hy) : __fdiv_rn(y, e.hy), 1.0f);
     Proj p;
     p.valid = (fabsf(nx) <= 1.0f) && (fabsf(ny) <= 1.0f) && (img[2] > 0.0f);
-    // ATen grid_sampler_unnormalize, align_corners=True
-    p.ix = __fmul_rn(__fmul_rn(__fadd_rn(nx, 1.0f), 0.5f), (float)(W - 1));
-    p.iy = __fmul_rn(__fmul_rn(__fadd_rn(ny, 1.0f), 0.5f), (float)(H - 1));
+    // ATen grid_sampler_unnormalize (align_corners=True): ((n+1)*0.5)*(size-1) == (n+1)*((size-1)/2)
+    // bit for bit, the halving being exact.
+    p.ix = __fmul_rn(__fadd_rn(nx, 1.0f), e.hx);
+    p.iy = __fmul_rn(__fadd_rn(ny, 1.0f), e.hy);
     return p;
 }
 
@@ -65,11 +94,11 @@ struct Footprint {
     float w_nw, w_ne, w_sw, w_se;
 };
 
+// Valid samples have ix in [0, W-1], so ix - floor(ix) is exact and 1 - frac == (floor+1) - ix.
 __device__ __forceinline__ Footprint footprint(float ix, float iy) {
-    float fx0 = floorf(ix), fy0 = floorf(iy);
-    float fx1 = __fadd_rn(fx0, 1.0f), fy1 = __fadd_rn(fy0, 1.0f);
-    float ax = __fsub_rn(fx1, ix), bx = __fsub_rn(ix, fx0);
-    float ay = __fsub_rn(fy1, iy), by = __fsub_rn(iy, fy0);
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const float bx = __fsub_rn(ix, fx0), by = __fsub_rn(iy, fy0);
+    const float ax = __fsub_rn(1.0f, bx), ay = __fsub_rn(1.0f, by);
     Footprint f;
     f.x0 = (int)fx0;
     f.y0 = (int)fy0;
@@ -87,175 +116,292 @@ __device__ __forceinline__ void fma4(float4& acc, const float4 v, float w) {
     acc.w = __fmaf_rn(v.w, w, acc.w);
 }
 
-// Bilinear sample with zeros padding from a channels-last (H,W,4) map: corners outside the
-// map contribute nothing (their weight is still computed from the un-clamped coordinate).
-__device__ __forceinline__ float4 sample4(const float4* __restrict__ map, int H, int W, const Footprint& f) {
-    const bool x0_in = (unsigned)f.x0 < (unsigned)W, x1_in = (unsigned)(f.x0 + 1) < (unsigned)W;
-    const bool y0_in = (unsigned)f.y0 < (unsigned)H, y1_in = (unsigned)(f.y0 + 1) < (unsigned)H;
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    const long long base = (long long)f.y0 * W + f.x0;
-    // issue all four loads before the first use
-    const float4 v_nw = (x0_in && y0_in) ? ldg4(map + base) : zero;
-    const float4 v_ne = (x1_in && y0_in) ? ldg4(map + base + 1) : zero;
-    const float4 v_sw = (x0_in && y1_in) ? ldg4(map + base + W) : zero;
-    const float4 v_se = (x1_in && y1_in) ? ldg4(map + base + W + 1) : zero;
-    float4 acc = zero;
-    if (x0_in && y0_in) fma4(acc, v_nw, f.w_nw);
-    if (x1_in && y0_in) fma4(acc, v_ne, f.w_ne);
-    if (x0_in && y1_in) fma4(acc, v_sw, f.w_sw);
-    if (x1_in && y1_in) fma4(acc, v_se, f.w_se);
+// Bilinear sample of a VALID footprint from the zero-padded channels-last map (pitch = W+1).
+__device__ __forceinline__ float4 sample_padded(const float4* __restrict__ map, int pitch, const Footprint& f) {
+    const float4* p = map + (f.y0 * pitch + f.x0);
+    const float4 v_nw = __ldg(p), v_ne = __ldg(p + 1), v_sw = __ldg(p + pitch), v_se = __ldg(p + pitch + 1);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    fma4(acc, v_nw, f.w_nw);
+    fma4(acc, v_ne, f.w_ne);
+    fma4(acc, v_sw, f.w_sw);
+    fma4(acc, v_se, f.w_se);
     return acc;
 }
 
-__device__ __forceinline__ void load_cams(Cam* s_cam, const float* w2c, const float* k_stage, int nv) {
-    for (int i = threadIdx.x; i < nv * 28; i += blockDim.x) {
-        int v = i / 28, j = i % 28;
-        float val = j < 16 ? w2c[v * 16 + j] : k_stage[v * 16 + (j - 16)];
-        (j < 16 ? s_cam[v].w2c[j] : s_cam[v].k[j - 16]) = val;
-    }
-    __syncthreads();
-}
-
-template <int VEC>
-__device__ __forceinline__ void store_vec(float* p, const float (&v)[VEC]) {
-    if constexpr (VEC == 4) {
-        __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
-    } else {
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) __stcs(p + j, v[j]);
-    }
-}
-
-template <int VEC, bool RECIP>
-__global__ void __launch_bounds__(256)
-volume_agg_fwd_kernel(const float4* __restrict__ feat, int nv, int H, int W, const float* __restrict__ w2c,
-                      const float* __restrict__ k_stage, const float* __restrict__ grid, int D, int a0,
-                      long long n_groups, long long out_off, long long channel_stride, int min_vis_view,
-                      float hx, float hy, float inv_hx, float inv_hy, float* __restrict__ volume,
-                      float* __restrict__ mask_volume) {
-    __shared__ Cam s_cam[GENS_MAX_VIEWS];
-    load_cams(s_cam, w2c, k_stage, nv);
-
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_groups) return;
-    const long long n0 = g * VEC;  // flat voxel offset inside the slab [a0, a1)
-    const int DD = D * D;
-    const int a = a0 + (int)(n0 / DD);
-    const int rem = (int)(n0 % DD);
-    const int b = rem / D, c0 = rem % D;
-
-    const float X = __ldg(grid + a), Y = __ldg(grid + b);
-    float Z[VEC];
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) Z[j] = __ldg(grid + c0 + j);
-
-    float4 s[VEC], q[VEC];
-    int cnt[VEC];
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        s[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        q[j] = s[j];
-        cnt[j] = 0;
-    }
-
-    const long long map_stride = (long long)H * W;
-    for (int v = 0; v < nv; ++v) {
-        const Cam& cam = s_cam[v];
-        float pre[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) pre[r] = __fmaf_rn(cam.w2c[4 * r + 1], Y, __fmul_rn(cam.w2c[4 * r], X));
-        Proj p[VEC];
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) p[j] = project_finish<RECIP>(cam, pre, Z[j], hx, hy, inv_hx, inv_hy, W, H);
-        const float4* map = feat + v * map_stride;
-        float4 f[VEC];
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            f[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p[j].valid) f[j] = sample4(map, H, W, footprint(p[j].ix, p[j].iy));
-        }
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            if (p[j].valid) {
-                cnt[j] += 1;
-                s[j].x = __fadd_rn(s[j].x, f[j].x);
-                s[j].y = __fadd_rn(s[j].y, f[j].y);
-                s[j].z = __fadd_rn(s[j].z, f[j].z);
-                s[j].w = __fadd_rn(s[j].w, f[j].w);
-                q[j].x = __fadd_rn(q[j].x, __fmul_rn(f[j].x, f[j].x));
-                q[j].y = __fadd_rn(q[j].y, __fmul_rn(f[j].y, f[j].y));
-                q[j].z = __fadd_rn(q[j].z, __fmul_rn(f[j].z, f[j].z));
-                q[j].w = __fadd_rn(q[j].w, __fmul_rn(f[j].w, f[j].w));
-            }
-        }
-    }
-
-    float out[9][VEC];
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        const float den = cnt[j] <= 0 ? 1e-8f : (float)cnt[j];
-        const float sv[4] = {s[j].x, s[j].y, s[j].z, s[j].w};
-        const float qv[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float mean = __fdiv_rn(sv[k], den);
-            out[k][j] = mean;
-            out[4 + k][j] = __fsub_rn(__fdiv_rn(qv[k], den), __fmul_rn(mean, mean));
-        }
-        out[8][j] = cnt[j] > min_vis_view ? 1.0f : 0.0f;
-    }
-    const long long o = out_off + n0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) store_vec<VEC>(volume + k * channel_stride + o, out[k]);
-    store_vec<VEC>(mask_volume + o, out[8]);
+// Exact s/n for the small integer n = number of valid views (Markstein: r = RN(1/n) is
+// precomputed, one residual correction gives the correctly rounded quotient).
+__device__ __forceinline__ f32x2 div_count2(f32x2 s, float n, float r) {
+    const f32x2 q = mul2(s, bc(r));
+    const f32x2 rem = fma2(bc(-n), q, s);
+    return fma2(rem, bc(r), q);
 }
 
 template <bool RECIP>
 __global__ void __launch_bounds__(256)
-volume_project_debug_kernel(int nv, int H, int W, const float* __restrict__ w2c, const float* __restrict__ k_stage,
-                            const float* __restrict__ grid, int D, float hx, float hy, float inv_hx, float inv_hy,
-                            int32_t* __restrict__ ix0, int32_t* __restrict__ iy0, uint8_t* __restrict__ valid) {
+volume_agg_scalar_kernel(const float4* __restrict__ feat, int nv, int H, int W, const float* __restrict__ w2c,
+                         const float* __restrict__ k_stage, float k_row_scale, const float* __restrict__ grid, int D, int a0,
+                         long long out_off, long long channel_stride, int min_vis_view, Extent e,
+                         float* __restrict__ volume, float* __restrict__ mask_volume) {
     __shared__ Cam s_cam[GENS_MAX_VIEWS];
-    load_cams(s_cam, w2c, k_stage, nv);
-    const long long D3 = (long long)D * D * D;
-    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= D3) return;
-    const int a = (int)(n / ((long long)D * D)), rem = (int)(n % ((long long)D * D));
-    const float X = grid[a], Y = grid[rem / D], Z = grid[rem % D];
+    load_cams(s_cam, w2c, k_stage, k_row_scale, nv);
+    const int c = blockIdx.x * 32 + threadIdx.x, b = blockIdx.y * 8 + threadIdx.y, a = a0 + blockIdx.z;
+    if (c >= D || b >= D) return;
+    const float X = __ldg(grid + a), Y = __ldg(grid + b), Z = __ldg(grid + c);
+    const int pitch = W + 1;
+    const long long map_stride = (long long)(H + 1) * pitch;
+
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    int cnt = 0;
     for (int v = 0; v < nv; ++v) {
-        const Cam& cam = s_cam[v];
-        float pre[4];
+        const Proj p = project_scalar<RECIP>(s_cam[v], X, Y, Z, e);
+        if (p.valid) {
+            const float4 f = sample_padded(feat + v * map_stride, pitch, footprint(p.ix, p.iy));
+            cnt += 1;
+            s.x = __fadd_rn(s.x, f.x); s.y = __fadd_rn(s.y, f.y);
+            s.z = __fadd_rn(s.z, f.z); s.w = __fadd_rn(s.w, f.w);
+            q.x = __fadd_rn(q.x, __fmul_rn(f.x, f.x)); q.y = __fadd_rn(q.y, __fmul_rn(f.y, f.y));
+            q.z = __fadd_rn(q.z, __fmul_rn(f.z, f.z)); q.w = __fadd_rn(q.w, __fmul_rn(f.w, f.w));
+        }
+    }
+    const float den = cnt <= 0 ? 1e-8f : (float)cnt;
+    const float sv[4] = {s.x, s.y, s.z, s.w}, qv[4] = {q.x, q.y, q.z, q.w};
+    const long long o = out_off + ((long long)blockIdx.z * D + b) * D + c;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) pre[r] = __fmaf_rn(cam.w2c[4 * r + 1], Y, __fmul_rn(cam.w2c[4 * r], X));
-        Proj p = project_finish<RECIP>(cam, pre, Z, hx, hy, inv_hx, inv_hy, W, H);
-        Footprint f = footprint(p.valid ? p.ix : 0.f, p.valid ? p.iy : 0.f);
+    for (int k = 0; k < 4; ++k) {
+        const float mean = __fdiv_rn(sv[k], den);
+        __stcs(volume + k * channel_stride + o, mean);
+        __stcs(volume + (4 + k) * channel_stride + o, __fsub_rn(__fdiv_rn(qv[k], den), __fmul_rn(mean, mean)));
+    }
+    __stcs(mask_volume + o, cnt > min_vis_view ? 1.0f : 0.0f);
+}
+
+template <bool RECIP>
+__global__ void __launch_bounds__(256)
+volume_project_debug_kernel(int nv, const float* __restrict__ w2c, const float* __restrict__ k_stage,
+                            float k_row_scale, const float* __restrict__ grid, int D, Extent e, int32_t* __restrict__ ix0,
+                            int32_t* __restrict__ iy0, uint8_t* __restrict__ valid) {
+    __shared__ Cam s_cam[GENS_MAX_VIEWS];
+    load_cams(s_cam, w2c, k_stage, k_row_scale, nv);
+    const int c = blockIdx.x * 32 + threadIdx.x, b = blockIdx.y * 8 + threadIdx.y, a = blockIdx.z;
+    if (c >= D || b >= D) return;
+    const long long D3 = (long long)D * D * D, n = ((long long)a * D + b) * D + c;
+    const float X = grid[a], Y = grid[b], Z = grid[c];
+    for (int v = 0; v < nv; ++v) {
+        const Proj p = project_scalar<RECIP>(s_cam[v], X, Y, Z, e);
+        const Footprint f = footprint(p.valid ? p.ix : 0.f, p.valid ? p.iy : 0.f);
         ix0[v * D3 + n] = p.valid ? f.x0 : 0;
         iy0[v * D3 + n] = p.valid ? f.y0 : 0;
         valid[v * D3 + n] = p.valid ? 1 : 0;
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// packed path (D % (64*PAIRS) == 0): PAIRS voxel pairs per thread, two voxels per FFMA2.
+// ------------------------------------------------------------------------------------------
+struct Proj2 {
+    f32x2 ix, iy;
+    bool valid_lo, valid_hi;
+};
+
+// Projection of a voxel pair sharing (X,Y); `pre[r]` = fma(w[r][1], Y, w[r][0]*X).
+template <bool RECIP, bool AFFINE>
+__device__ __forceinline__ Proj2 project_pair(const Cam& cam, const float (&pre)[4], f32x2 Z, const Extent& e) {
+    f32x2 img0, img1, depth;
+    if (AFFINE) {
+        // Same chain with the structural zeros/ones of a rigid pose and a pinhole K removed:
+        // fma(0, x, t) == t and fma(1, x, +-0) == x for finite x, so every surviving rounding
+        // is identical.
+        f32x2 c[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            c[r] = add2(fma2(bc(cam.w2c[4 * r + 2]), Z, bc(pre[r])), bc(cam.w2c[4 * r + 3]));
+        img0 = fma2(bc(cam.k[2]), c[2], mul2(bc(cam.k[0]), c[0]));
+        img1 = fma2(bc(cam.k[6]), c[2], mul2(bc(cam.k[5]), c[1]));
+        depth = c[2];
+    } else {
+        f32x2 c[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            c[r] = add2(fma2(bc(cam.w2c[4 * r + 2]), Z, bc(pre[r])), bc(cam.w2c[4 * r + 3]));
+        f32x2 img[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            f32x2 t = mul2(bc(cam.k[4 * r]), c[0]);
+            t = fma2(bc(cam.k[4 * r + 1]), c[1], t);
+            t = fma2(bc(cam.k[4 * r + 2]), c[2], t);
+            img[r] = fma2(bc(cam.k[4 * r + 3]), c[3], t);
+        }
+        img0 = img[0]; img1 = img[1]; depth = img[2];
+    }
+    const float d_lo = lo(depth), d_hi = hi(depth);
+    const f32x2 den = add2(depth, bc(1e-8f));
+    // depth <= 0 is invalid whatever x/y are; depth in (0, 2^100) puts den in [1e-8, 2^100], the
+    // range div2() is exact on.  Anything else (never, for real cameras) takes IEEE division.
+    const Recip2 rc = recip2(den);
+    f32x2 x = div2(img0, rc), y = div2(img1, rc);
+    if (__builtin_expect(d_lo >= 1e30f || d_hi >= 1e30f, 0)) {
+        x = pk(__fdiv_rn(lo(img0), lo(den)), __fdiv_rn(hi(img0), hi(den)));
+        y = pk(__fdiv_rn(lo(img1), lo(den)), __fdiv_rn(hi(img1), hi(den)));
+    }
+    f32x2 nx, ny;
+    if (RECIP) {
+        nx = add2(mul2_rounded(x, bc(e.inv_hx)), bc(-1.0f));
+        ny = add2(mul2_rounded(y, bc(e.inv_hy)), bc(-1.0f));
+    } else {
+        nx = add2(pk(__fdiv_rn(lo(x), e.hx), __fdiv_rn(hi(x), e.hx)), bc(-1.0f));
+        ny = add2(pk(__fdiv_rn(lo(y), e.hy), __fdiv_rn(hi(y), e.hy)), bc(-1.0f));
+    }
+    Proj2 p;
+    p.valid_lo = (fabsf(lo(nx)) <= 1.0f) && (fabsf(lo(ny)) <= 1.0f) && (d_lo > 0.0f);
+    p.valid_hi = (fabsf(hi(nx)) <= 1.0f) && (fabsf(hi(ny)) <= 1.0f) && (d_hi > 0.0f);
+    p.ix = mul2(add2(nx, bc(1.0f)), bc(e.hx));
+    p.iy = mul2(add2(ny, bc(1.0f)), bc(e.hy));
+    return p;
+}
+
+struct Acc {
+    f32x2 s_xy, s_zw, q_xy, q_zw;
+    int cnt;
+};
+
+struct Corner4 {
+    float4 nw, ne, sw, se;
+};
+
+__device__ __forceinline__ Corner4 gather4(const float4* __restrict__ map, int pitch, int x0, int y0) {
+    const float4* p = map + (y0 * pitch + x0);
+    Corner4 c;
+    c.nw = __ldg(p);
+    c.ne = __ldg(p + 1);
+    c.sw = __ldg(p + pitch);
+    c.se = __ldg(p + pitch + 1);
+    return c;
+}
+
+__device__ __forceinline__ void blend_accumulate(const Corner4& v, float w_nw, float w_ne, float w_sw, float w_se,
+                                                 Acc& a) {
+    f32x2 f_xy = mul2(pk(v.nw.x, v.nw.y), bc(w_nw));  // fma(v, w, 0) == v*w
+    f32x2 f_zw = mul2(pk(v.nw.z, v.nw.w), bc(w_nw));
+    f_xy = fma2(pk(v.ne.x, v.ne.y), bc(w_ne), f_xy);
+    f_zw = fma2(pk(v.ne.z, v.ne.w), bc(w_ne), f_zw);
+    f_xy = fma2(pk(v.sw.x, v.sw.y), bc(w_sw), f_xy);
+    f_zw = fma2(pk(v.sw.z, v.sw.w), bc(w_sw), f_zw);
+    f_xy = fma2(pk(v.se.x, v.se.y), bc(w_se), f_xy);
+    f_zw = fma2(pk(v.se.z, v.se.w), bc(w_se), f_zw);
+    a.cnt += 1;
+    a.s_xy = add2(a.s_xy, f_xy);
+    a.s_zw = add2(a.s_zw, f_zw);
+    a.q_xy = add2(a.q_xy, mul2_rounded(f_xy, f_xy));
+    a.q_zw = add2(a.q_zw, mul2_rounded(f_zw, f_zw));
+}
+
+// One view for all of a thread's voxel pairs.  GATHER = 0: both voxels of a pair issue their
+// four gathers before the first blend (8 loads in flight per thread); GATHER = 1: one voxel at a
+// time (4 in flight, 16 fewer live registers).
+template <int PAIRS, bool RECIP, bool AFFINE, int GATHER>
+__device__ __forceinline__ void accumulate_view(const Cam& cam, const float4* __restrict__ map, int pitch,
+                                                float X, float Y, const f32x2 (&Z)[PAIRS], const Extent& e,
+                                                Acc (&acc)[2 * PAIRS]) {
+    float pre[4];
+#pragma unroll
+    for (int r = 0; r < (AFFINE ? 3 : 4); ++r)
+        pre[r] = __fmaf_rn(cam.w2c[4 * r + 1], Y, __fmul_rn(cam.w2c[4 * r], X));
+#pragma unroll
+    for (int h = 0; h < PAIRS; ++h) {
+        const Proj2 p = project_pair<RECIP, AFFINE>(cam, pre, Z[h], e);
+        if (!(p.valid_lo || p.valid_hi)) continue;
+        const float fx_lo = floorf(lo(p.ix)), fx_hi = floorf(hi(p.ix));
+        const float fy_lo = floorf(lo(p.iy)), fy_hi = floorf(hi(p.iy));
+        const f32x2 bx = sub2(p.ix, pk(fx_lo, fx_hi)), by = sub2(p.iy, pk(fy_lo, fy_hi));
+        const f32x2 ax = sub2(bc(1.0f), bx), ay = sub2(bc(1.0f), by);
+        const f32x2 w_nw = mul2(ax, ay), w_ne = mul2(bx, ay), w_sw = mul2(ax, by), w_se = mul2(bx, by);
+        if (GATHER == 0) {
+            Corner4 v_lo, v_hi;
+            if (p.valid_lo) v_lo = gather4(map, pitch, (int)fx_lo, (int)fy_lo);
+            if (p.valid_hi) v_hi = gather4(map, pitch, (int)fx_hi, (int)fy_hi);
+            if (p.valid_lo) blend_accumulate(v_lo, lo(w_nw), lo(w_ne), lo(w_sw), lo(w_se), acc[2 * h]);
+            if (p.valid_hi) blend_accumulate(v_hi, hi(w_nw), hi(w_ne), hi(w_sw), hi(w_se), acc[2 * h + 1]);
+        } else {
+            if (p.valid_lo)
+                blend_accumulate(gather4(map, pitch, (int)fx_lo, (int)fy_lo), lo(w_nw), lo(w_ne), lo(w_sw), lo(w_se),
+                                 acc[2 * h]);
+            if (p.valid_hi)
+                blend_accumulate(gather4(map, pitch, (int)fx_hi, (int)fy_hi), hi(w_nw), hi(w_ne), hi(w_sw), hi(w_se),
+                                 acc[2 * h + 1]);
+        }
+    }
+}
+
+template <int PAIRS, bool RECIP, int MIN_BLOCKS, int GATHER>
+__global__ void __launch_bounds__(256, MIN_BLOCKS)
+volume_agg_packed_kernel(const float4* __restrict__ feat, int nv, int H, int W, const float* __restrict__ w2c,
+                         const float* __restrict__ k_stage, float k_row_scale, const float* __restrict__ grid, int D, int a0,
+                         long long out_off, long long channel_stride, int min_vis_view, Extent e,
+                         float* __restrict__ volume, float* __restrict__ mask_volume) {
+    __shared__ Cam s_cam[GENS_MAX_VIEWS];
+    load_cams(s_cam, w2c, k_stage, k_row_scale, nv);
+    const int c0 = blockIdx.x * (64 * PAIRS) + threadIdx.x, b = blockIdx.y * 8 + threadIdx.y, a = a0 + blockIdx.z;
+    if (b >= D) return;
+    const float X = __ldg(grid + a), Y = __ldg(grid + b);
+    f32x2 Z[PAIRS];
+#pragma unroll
+    for (int h = 0; h < PAIRS; ++h) Z[h] = pk(__ldg(grid + c0 + 64 * h), __ldg(grid + c0 + 64 * h + 32));
+    const int pitch = W + 1;
+    const long long map_stride = (long long)(H + 1) * pitch;
+
+    Acc acc[2 * PAIRS];
+#pragma unroll
+    for (int j = 0; j < 2 * PAIRS; ++j) {
+        acc[j].s_xy = acc[j].s_zw = acc[j].q_xy = acc[j].q_zw = bc(0.0f);
+        acc[j].cnt = 0;
+    }
+
+#pragma unroll 1
+    for (int v = 0; v < nv; ++v) {
+        const float4* map = feat + v * map_stride;
+        if (s_cam[v].affine) accumulate_view<PAIRS, RECIP, true, GATHER>(s_cam[v], map, pitch, X, Y, Z, e, acc);
+        else accumulate_view<PAIRS, RECIP, false, GATHER>(s_cam[v], map, pitch, X, Y, Z, e, acc);
+    }
+
+    const long long row = out_off + ((long long)blockIdx.z * D + b) * D + c0;
+#pragma unroll
+    for (int j = 0; j < 2 * PAIRS; ++j) {
+        const int cnt = acc[j].cnt;
+        const float n = cnt <= 0 ? 1e-8f : (float)cnt;
+        const float r = cnt <= 0 ? 1e8f : __frcp_rn(n);
+        const f32x2 m_xy = div_count2(acc[j].s_xy, n, r), m_zw = div_count2(acc[j].s_zw, n, r);
+        const f32x2 v_xy = sub2(div_count2(acc[j].q_xy, n, r), mul2_rounded(m_xy, m_xy));
+        const f32x2 v_zw = sub2(div_count2(acc[j].q_zw, n, r), mul2_rounded(m_zw, m_zw));
+        float* o = volume + row + 32 * j;
+        __stcs(o, lo(m_xy));
+        __stcs(o + channel_stride, hi(m_xy));
+        __stcs(o + 2 * channel_stride, lo(m_zw));
+        __stcs(o + 3 * channel_stride, hi(m_zw));
+        __stcs(o + 4 * channel_stride, lo(v_xy));
+        __stcs(o + 5 * channel_stride, hi(v_xy));
+        __stcs(o + 6 * channel_stride, lo(v_zw));
+        __stcs(o + 7 * channel_stride, hi(v_zw));
+        __stcs(mask_volume + row + 32 * j, cnt > min_vis_view ? 1.0f : 0.0f);
+    }
+}
+
 // Backward w.r.t. the feature maps.  With m_v the view validity, n' the clamped count,
 //   mean_k = sum_v m_v f_vk / n',  var_k = sum_v m_v f_vk^2 / n' - mean_k^2
 //   d/df_vk = m_v / n' * ( g_mean_k + 2 g_var_k (f_vk - mean_k) )
-// scattered to the four bilinear corners with 16-byte vector atomics.
+// scattered to the four bilinear corners of the padded channels-last gradient map with
+// 16-byte vector atomics (two passes over the views: mean first, then scatter).
 template <bool RECIP>
 __global__ void __launch_bounds__(256)
 volume_agg_bwd_kernel(const float4* __restrict__ feat, int nv, int H, int W, const float* __restrict__ w2c,
-                      const float* __restrict__ k_stage, const float* __restrict__ grid, int D, int a0,
-                      long long n_vox, long long out_off, long long channel_stride, float hx, float hy,
-                      float inv_hx, float inv_hy, const float* __restrict__ grad_volume,
-                      float4* __restrict__ grad_feat) {
+                      const float* __restrict__ k_stage, float k_row_scale, const float* __restrict__ grid, int D, int a0,
+                      long long out_off, long long channel_stride, Extent e,
+                      const float* __restrict__ grad_volume, float4* __restrict__ grad_feat) {
     __shared__ Cam s_cam[GENS_MAX_VIEWS];
-    load_cams(s_cam, w2c, k_stage, nv);
-    const long long n0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n0 >= n_vox) return;
-    const int DD = D * D;
-    const int a = a0 + (int)(n0 / DD);
-    const int rem = (int)(n0 % DD);
-    const float X = __ldg(grid + a), Y = __ldg(grid + rem / D), Z = __ldg(grid + rem % D);
-
-    const long long o = out_off + n0;
+    load_cams(s_cam, w2c, k_stage, k_row_scale, nv);
+    const int c = blockIdx.x * 32 + threadIdx.x, b = blockIdx.y * 8 + threadIdx.y, a = a0 + blockIdx.z;
+    if (c >= D || b >= D) return;
+    const float X = __ldg(grid + a), Y = __ldg(grid + b), Z = __ldg(grid + c);
+    const long long o = out_off + ((long long)blockIdx.z * D + b) * D + c;
     float gm[4], gv[4];
     bool any = false;
 #pragma unroll
@@ -265,26 +411,18 @@ volume_agg_bwd_kernel(const float4* __restrict__ feat, int nv, int H, int W, con
         any |= (gm[k] != 0.f) | (gv[k] != 0.f);
     }
     if (!any) return;
+    const int pitch = W + 1;
+    const long long map_stride = (long long)(H + 1) * pitch;
 
-    const long long map_stride = (long long)H * W;
-    float4 f[GENS_MAX_VIEWS];
-    Footprint fp[GENS_MAX_VIEWS];
-    unsigned valid_bits = 0;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     int cnt = 0;
 #pragma unroll 1
     for (int v = 0; v < nv; ++v) {
-        const Cam& cam = s_cam[v];
-        float pre[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) pre[r] = __fmaf_rn(cam.w2c[4 * r + 1], Y, __fmul_rn(cam.w2c[4 * r], X));
-        Proj p = project_finish<RECIP>(cam, pre, Z, hx, hy, inv_hx, inv_hy, W, H);
+        const Proj p = project_scalar<RECIP>(s_cam[v], X, Y, Z, e);
         if (p.valid) {
-            fp[v] = footprint(p.ix, p.iy);
-            f[v] = sample4(feat + v * map_stride, H, W, fp[v]);
-            valid_bits |= 1u << v;
+            const float4 f = sample_padded(feat + v * map_stride, pitch, footprint(p.ix, p.iy));
             cnt += 1;
-            s.x += f[v].x; s.y += f[v].y; s.z += f[v].z; s.w += f[v].w;
+            s.x += f.x; s.y += f.y; s.z += f.z; s.w += f.w;
         }
     }
     if (cnt == 0) return;
@@ -292,39 +430,56 @@ volume_agg_bwd_kernel(const float4* __restrict__ feat, int nv, int H, int W, con
     const float mean[4] = {s.x * inv_n, s.y * inv_n, s.z * inv_n, s.w * inv_n};
 #pragma unroll 1
     for (int v = 0; v < nv; ++v) {
-        if (!((valid_bits >> v) & 1u)) continue;
-        const float fv[4] = {f[v].x, f[v].y, f[v].z, f[v].w};
+        const Proj p = project_scalar<RECIP>(s_cam[v], X, Y, Z, e);
+        if (!p.valid) continue;
+        const Footprint t = footprint(p.ix, p.iy);
+        const float4 f = sample_padded(feat + v * map_stride, pitch, t);
+        const float fv[4] = {f.x, f.y, f.z, f.w};
         float gf[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) gf[k] = inv_n * (gm[k] + 2.0f * gv[k] * (fv[k] - mean[k]));
-        float4* gmap = grad_feat + v * map_stride;
-        const Footprint& t = fp[v];
-        const bool x1_in = t.x0 + 1 < W, y1_in = t.y0 + 1 < H;
-        const long long base = (long long)t.y0 * W + t.x0;
-        auto scat = [&](long long idx, float w) {
-            atomicAdd(gmap + idx, make_float4(gf[0] * w, gf[1] * w, gf[2] * w, gf[3] * w));
-        };
-        scat(base, t.w_nw);
-        if (x1_in) scat(base + 1, t.w_ne);
-        if (y1_in) scat(base + W, t.w_sw);
-        if (x1_in && y1_in) scat(base + W + 1, t.w_se);
+        float4* gp = grad_feat + v * map_stride + (t.y0 * pitch + t.x0);
+        atomicAdd(gp, make_float4(gf[0] * t.w_nw, gf[1] * t.w_nw, gf[2] * t.w_nw, gf[3] * t.w_nw));
+        atomicAdd(gp + 1, make_float4(gf[0] * t.w_ne, gf[1] * t.w_ne, gf[2] * t.w_ne, gf[3] * t.w_ne));
+        atomicAdd(gp + pitch, make_float4(gf[0] * t.w_sw, gf[1] * t.w_sw, gf[2] * t.w_sw, gf[3] * t.w_sw));
+        atomicAdd(gp + pitch + 1, make_float4(gf[0] * t.w_se, gf[1] * t.w_se, gf[2] * t.w_se, gf[3] * t.w_se));
     }
 }
 
+// (n,4,h,w) NCHW -> zero-padded channels-last (n, h+1, w+1, 4)
 __global__ void __launch_bounds__(256)
-nchw4_to_nhwc4_kernel(const float* __restrict__ src, float4* __restrict__ dst, long long hw, long long total) {
+pack_maps_kernel(const float* __restrict__ src, float4* __restrict__ dst, int h, int w, long long total) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const long long n = i / hw, p = i % hw;
-    const float* s = src + n * 4 * hw + p;
-    dst[i] = make_float4(__ldg(s), __ldg(s + hw), __ldg(s + 2 * hw), __ldg(s + 3 * hw));
+    const int pitch = w + 1;
+    const long long per = (long long)(h + 1) * pitch;
+    const long long n = i / per;
+    const int rem = (int)(i % per), y = rem / pitch, x = rem % pitch;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y < h && x < w) {
+        const long long hw = (long long)h * w;
+        const float* s = src + n * 4 * hw + (long long)y * w + x;
+        v = make_float4(__ldg(s), __ldg(s + hw), __ldg(s + 2 * hw), __ldg(s + 3 * hw));
+    }
+    dst[i] = v;
 }
 
-struct HalfExtent {
-    float hx, hy, inv_hx, inv_hy;
-};
-inline HalfExtent half_extent(int W, int H) {
-    HalfExtent e;
+// padded channels-last gradient (n, h+1, w+1, 4) -> (n,4,h,w) NCHW (padding rows/cols dropped;
+// they only ever receive zero-weight contributions)
+__global__ void __launch_bounds__(256)
+unpack_maps_kernel(const float4* __restrict__ src, float* __restrict__ dst, int h, int w, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long hw = (long long)h * w;
+    const long long n = i / hw;
+    const int rem = (int)(i % hw), y = rem / w, x = rem % w;
+    const float4 v = __ldg(src + n * (long long)(h + 1) * (w + 1) + (long long)y * (w + 1) + x);
+    float* d = dst + n * 4 * hw + rem;
+    d[0] = v.x; d[hw] = v.y; d[2 * hw] = v.z; d[3 * hw] = v.w;
+}
+
+inline Extent extent(int W, int H) {
+    Extent e;
     e.hx = (float)((double)(W - 1) / 2.0);  // python: (width - 1) / 2, then cast to the tensor dtype
     e.hy = (float)((double)(H - 1) / 2.0);
     e.inv_hx = 1.0f / e.hx;  // ATen CUDA div_true: opmath_t(1.0) / scalar
@@ -332,82 +487,143 @@ inline HalfExtent half_extent(int W, int H) {
     return e;
 }
 
+int g_k1_variant = 0;  // tuning knob (gens_debug_set_variant); 0 = shipped configuration
+
+inline bool bad_slab(int D, int a0, int a1, int a_base) { return a0 < 0 || a1 > D || a_base < 0 || a_base > a0; }
+
 }  // namespace
 
-extern "C" int gens_nchw4_to_nhwc4(const float* src, float* dst, int n, int h, int w, void* stream) {
-    GENS_CHECK_ARG(src && dst && n > 0 && h > 0 && w > 0);
-    const long long hw = (long long)h * w, total = hw * n;
-    nchw4_to_nhwc4_kernel<<<ceil_div_i(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        src, reinterpret_cast<float4*>(dst), hw, total);
+extern "C" int gens_debug_set_variant(int variant) {
+    g_k1_variant = variant;
+    return 0;
+}
+
+extern "C" int gens_pack_feature_maps(const float* src_nchw, float* dst_padded_nhwc, int n, int h, int w,
+                                      void* stream) {
+    GENS_CHECK_ARG(src_nchw && dst_padded_nhwc && n > 0 && h > 0 && w > 0);
+    const long long total = (long long)n * (h + 1) * (w + 1);
+    pack_maps_kernel<<<ceil_div_i(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        src_nchw, reinterpret_cast<float4*>(dst_padded_nhwc), h, w, total);
     return gens_launch_status();
 }
 
-extern "C" int gens_volume_agg_fwd(const float* feat_nhwc, int nv, int H, int W, const float* w2c,
-                                   const float* k_stage, const float* grid, int D, int a0, int a1, int a_base,
-                                   long long channel_stride, int min_vis_view, int div_mode, float* volume,
-                                   float* mask_volume, void* stream) {
-    GENS_CHECK_ARG(feat_nhwc && w2c && k_stage && grid && volume && mask_volume);
-    GENS_CHECK_ARG(nv > 0 && H > 0 && W > 0 && D > 0 && a0 >= 0 && a1 <= D && a_base >= 0 && a_base <= a0);
-    if (nv > GENS_MAX_VIEWS) return GENS_E_UNSUPPORTED;
-    if (a1 <= a0) return 0;
-    const long long n_vox = (long long)(a1 - a0) * D * D;
-    const long long out_off = (long long)(a0 - a_base) * D * D;
-    const HalfExtent e = half_extent(W, H);
-    const bool vec4 = (D % 4 == 0) && (channel_stride % 4 == 0) &&
-                      (((uintptr_t)volume | (uintptr_t)mask_volume) % 16 == 0);
-    cudaStream_t st = (cudaStream_t)stream;
-    const float4* feat = reinterpret_cast<const float4*>(feat_nhwc);
-#define GENS_LAUNCH_AGG(VEC, RECIP)                                                                          \
-    volume_agg_fwd_kernel<VEC, RECIP><<<ceil_div_i(n_vox / VEC, 256), 256, 0, st>>>(                          \
-        feat, nv, H, W, w2c, k_stage, grid, D, a0, n_vox / VEC, out_off, channel_stride, min_vis_view, e.hx, \
-        e.hy, e.inv_hx, e.inv_hy, volume, mask_volume)
-    if (vec4) {
-        if (div_mode == GENS_DIV_RECIP) GENS_LAUNCH_AGG(4, true); else GENS_LAUNCH_AGG(4, false);
+extern "C" int gens_unpack_feature_grads(const float* src_padded_nhwc, float* dst_nchw, int n, int h, int w,
+                                         void* stream) {
+    GENS_CHECK_ARG(src_padded_nhwc && dst_nchw && n > 0 && h > 0 && w > 0);
+    const long long total = (long long)n * h * w;
+    unpack_maps_kernel<<<ceil_div_i(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(src_padded_nhwc), dst_nchw, h, w, total);
+    return gens_launch_status();
+}
+
+namespace {
+
+int launch_agg_fwd(const gens_volume_scale_t& sc, int nv, const float* w2c, const float* intrs, int min_vis_view,
+                   int div_mode, cudaStream_t st) {
+    if (!(sc.feat_padded && sc.grid && sc.volume && sc.mask_volume)) return GENS_E_BADARG;
+    if (!(sc.H > 0 && sc.W > 0 && sc.D > 0) || bad_slab(sc.D, sc.a0, sc.a1, sc.a_base)) return GENS_E_BADARG;
+    if ((long long)(sc.H + 1) * (sc.W + 1) * nv >= (1LL << 31)) return GENS_E_UNSUPPORTED;
+    if (sc.a1 <= sc.a0) return 0;
+    const int D = sc.D, planes = sc.a1 - sc.a0;
+    const long long out_off = (long long)(sc.a0 - sc.a_base) * D * D;
+    const Extent e = extent(sc.W, sc.H);
+    const float4* feat = reinterpret_cast<const float4*>(sc.feat_padded);
+    const bool recip = div_mode == GENS_DIV_RECIP;
+    const dim3 block(32, 8);
+#define GENS_AGG_ARGS \
+    feat, nv, sc.H, sc.W, w2c, intrs, sc.k_row_scale, sc.grid, D, sc.a0, out_off, sc.channel_stride, min_vis_view, e, \
+        sc.volume, sc.mask_volume
+#define GENS_LAUNCH_PACKED(PAIRS, MINB, GATHER)                                                          \
+    do {                                                                                                 \
+        const dim3 g(D / (64 * PAIRS), ceil_div_i(D, 8), planes);                                        \
+        if (recip) volume_agg_packed_kernel<PAIRS, true, MINB, GATHER><<<g, block, 0, st>>>(GENS_AGG_ARGS); \
+        else volume_agg_packed_kernel<PAIRS, false, MINB, GATHER><<<g, block, 0, st>>>(GENS_AGG_ARGS);     \
+    } while (0)
+    const int variant = g_k1_variant;
+    if (D % 128 == 0 && variant == 1) {
+        GENS_LAUNCH_PACKED(2, 3, 1);
+    } else if (D % 128 == 0 && variant == 2) {
+        GENS_LAUNCH_PACKED(2, 2, 0);
+    } else if (D % 64 == 0) {
+        GENS_LAUNCH_PACKED(1, 4, 1);
     } else {
-        if (div_mode == GENS_DIV_RECIP) GENS_LAUNCH_AGG(1, true); else GENS_LAUNCH_AGG(1, false);
+        const dim3 g(ceil_div_i(D, 32), ceil_div_i(D, 8), planes);
+        if (recip) volume_agg_scalar_kernel<true><<<g, block, 0, st>>>(GENS_AGG_ARGS);
+        else volume_agg_scalar_kernel<false><<<g, block, 0, st>>>(GENS_AGG_ARGS);
     }
-#undef GENS_LAUNCH_AGG
+#undef GENS_LAUNCH_PACKED
+#undef GENS_AGG_ARGS
     return gens_launch_status();
 }
 
-extern "C" int gens_volume_project_debug(int nv, int H, int W, const float* w2c, const float* k_stage,
-                                         const float* grid, int D, int div_mode, int32_t* ix0, int32_t* iy0,
-                                         uint8_t* valid, void* stream) {
-    GENS_CHECK_ARG(w2c && k_stage && grid && ix0 && iy0 && valid && nv > 0 && D > 0 && H > 0 && W > 0);
+}  // namespace
+
+extern "C" int gens_volume_agg_fwd_multi(const gens_volume_scale_t* scales, int n_scales, int nv, const float* w2c,
+                                         const float* intrs, int min_vis_view, int div_mode, void* stream) {
+    GENS_CHECK_ARG(scales && n_scales > 0 && w2c && intrs && nv > 0);
     if (nv > GENS_MAX_VIEWS) return GENS_E_UNSUPPORTED;
-    const HalfExtent e = half_extent(W, H);
-    const long long D3 = (long long)D * D * D;
+    for (int i = 0; i < n_scales; ++i) {
+        const int rc = launch_agg_fwd(scales[i], nv, w2c, intrs, min_vis_view, div_mode, (cudaStream_t)stream);
+        if (rc != 0) return rc;
+    }
+    return 0;
+}
+
+extern "C" int gens_volume_agg_fwd(const float* feat_padded, int nv, int H, int W, const float* w2c,
+                                   const float* intrs, float k_row_scale, const float* grid, int D, int a0, int a1,
+                                   int a_base, long long channel_stride, int min_vis_view, int div_mode,
+                                   float* volume, float* mask_volume, void* stream) {
+    gens_volume_scale_t sc;
+    sc.feat_padded = feat_padded; sc.H = H; sc.W = W; sc.D = D; sc.a0 = a0; sc.a1 = a1; sc.a_base = a_base;
+    sc.channel_stride = channel_stride; sc.k_row_scale = k_row_scale; sc.grid = grid; sc.volume = volume;
+    sc.mask_volume = mask_volume;
+    return gens_volume_agg_fwd_multi(&sc, 1, nv, w2c, intrs, min_vis_view, div_mode, stream);
+}
+
+extern "C" int gens_pack_feature_maps_multi(const float* const* src_nchw, float* const* dst_padded, const int* h,
+                                            const int* w, int n_scales, int n, void* stream) {
+    GENS_CHECK_ARG(src_nchw && dst_padded && h && w && n_scales > 0 && n > 0);
+    for (int i = 0; i < n_scales; ++i) {
+        const int rc = gens_pack_feature_maps(src_nchw[i], dst_padded[i], n, h[i], w[i], stream);
+        if (rc != 0) return rc;
+    }
+    return 0;
+}
+
+extern "C" int gens_volume_project_debug(int nv, int H, int W, const float* w2c, const float* intrs,
+                                         float k_row_scale, const float* grid, int D, int div_mode, int32_t* ix0,
+                                         int32_t* iy0, uint8_t* valid, void* stream) {
+    GENS_CHECK_ARG(w2c && intrs && grid && ix0 && iy0 && valid && nv > 0 && D > 0 && H > 0 && W > 0);
+    if (nv > GENS_MAX_VIEWS) return GENS_E_UNSUPPORTED;
+    const Extent e = extent(W, H);
+    const dim3 block(32, 8), g(ceil_div_i(D, 32), ceil_div_i(D, 8), D);
     cudaStream_t st = (cudaStream_t)stream;
     if (div_mode == GENS_DIV_RECIP)
-        volume_project_debug_kernel<true><<<ceil_div_i(D3, 256), 256, 0, st>>>(
-            nv, H, W, w2c, k_stage, grid, D, e.hx, e.hy, e.inv_hx, e.inv_hy, ix0, iy0, valid);
+        volume_project_debug_kernel<true><<<g, block, 0, st>>>(nv, w2c, intrs, k_row_scale, grid, D, e, ix0, iy0, valid);
     else
-        volume_project_debug_kernel<false><<<ceil_div_i(D3, 256), 256, 0, st>>>(
-            nv, H, W, w2c, k_stage, grid, D, e.hx, e.hy, e.inv_hx, e.inv_hy, ix0, iy0, valid);
+        volume_project_debug_kernel<false><<<g, block, 0, st>>>(nv, w2c, intrs, k_row_scale, grid, D, e, ix0, iy0, valid);
     return gens_launch_status();
 }
 
-extern "C" int gens_volume_agg_bwd(const float* feat_nhwc, int nv, int H, int W, const float* w2c,
-                                   const float* k_stage, const float* grid, int D, int a0, int a1, int a_base,
-                                   long long channel_stride, int div_mode, const float* grad_volume,
-                                   float* grad_feat_nhwc, void* stream) {
-    GENS_CHECK_ARG(feat_nhwc && w2c && k_stage && grid && grad_volume && grad_feat_nhwc);
-    GENS_CHECK_ARG(nv > 0 && H > 0 && W > 0 && D > 0 && a0 >= 0 && a1 <= D && a_base >= 0 && a_base <= a0);
-    if (nv > GENS_MAX_VIEWS) return GENS_E_UNSUPPORTED;
+extern "C" int gens_volume_agg_bwd(const float* feat_padded, int nv, int H, int W, const float* w2c,
+                                   const float* intrs, float k_row_scale, const float* grid, int D, int a0, int a1,
+                                   int a_base, long long channel_stride, int div_mode, const float* grad_volume,
+                                   float* grad_feat_padded, void* stream) {
+    GENS_CHECK_ARG(feat_padded && w2c && intrs && grid && grad_volume && grad_feat_padded);
+    GENS_CHECK_ARG(nv > 0 && H > 0 && W > 0 && D > 0 && !bad_slab(D, a0, a1, a_base));
+    if (nv > GENS_MAX_VIEWS || (long long)(H + 1) * (W + 1) * nv >= (1LL << 31)) return GENS_E_UNSUPPORTED;
     if (a1 <= a0) return 0;
-    const long long n_vox = (long long)(a1 - a0) * D * D;
     const long long out_off = (long long)(a0 - a_base) * D * D;
-    const HalfExtent e = half_extent(W, H);
+    const Extent e = extent(W, H);
     cudaStream_t st = (cudaStream_t)stream;
-    const float4* feat = reinterpret_cast<const float4*>(feat_nhwc);
-    float4* gfeat = reinterpret_cast<float4*>(grad_feat_nhwc);
+    const float4* feat = reinterpret_cast<const float4*>(feat_padded);
+    float4* gfeat = reinterpret_cast<float4*>(grad_feat_padded);
+    const dim3 block(32, 8), g(ceil_div_i(D, 32), ceil_div_i(D, 8), a1 - a0);
     if (div_mode == GENS_DIV_RECIP)
-        volume_agg_bwd_kernel<true><<<ceil_div_i(n_vox, 256), 256, 0, st>>>(
-            feat, nv, H, W, w2c, k_stage, grid, D, a0, n_vox, out_off, channel_stride, e.hx, e.hy, e.inv_hx,
-            e.inv_hy, grad_volume, gfeat);
+        volume_agg_bwd_kernel<true><<<g, block, 0, st>>>(feat, nv, H, W, w2c, intrs, k_row_scale, grid, D, a0, out_off,
+                                                          channel_stride, e, grad_volume, gfeat);
     else
-        volume_agg_bwd_kernel<false><<<ceil_div_i(n_vox, 256), 256, 0, st>>>(
-            feat, nv, H, W, w2c, k_stage, grid, D, a0, n_vox, out_off, channel_stride, e.hx, e.hy, e.inv_hx,
-            e.inv_hy, grad_volume, gfeat);
+        volume_agg_bwd_kernel<false><<<g, block, 0, st>>>(feat, nv, H, W, w2c, intrs, k_row_scale, grid, D, a0, out_off,
+                                                           channel_stride, e, grad_volume, gfeat);
     return gens_launch_status();
 }

@@ -2,11 +2,13 @@
 
 `Volume.agg_mean_var(features, intrs, c2ws, min_vis_view=1)` keeps the reference signature and
 return convention (reference volume.py:13-63) but runs ONE fused CUDA kernel per scale (K1,
-csrc/volume_agg.cu) instead of ~320 ATen ops and >= 15 full-size temporaries.
+csrc/volume_agg.cu), all scales enqueued by a single C call, instead of ~320 ATen ops and >= 15
+full-size temporaries per scale.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Tuple
+import ctypes
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.nn as nn
@@ -18,70 +20,171 @@ from . import _lib
 # computes on the device the tensors live on, i.e. CUDA.
 DEFAULT_DIV_MODE = _lib.DIV_RECIP
 
+_GRID_CACHE: Dict[Tuple[int, str], torch.Tensor] = {}
 
-def to_channels_last4(feat: torch.Tensor) -> torch.Tensor:
-    """(n,4,h,w) NCHW -> (n,h,w,4) with our own transpose kernel."""
-    _lib.require_cuda(feat)
-    feat = _lib.f32c(feat)
-    n, c, h, w = feat.shape
-    if c != 4:
-        raise RuntimeError(f"gens_b200 volume kernels are built for 4-channel feature maps, got {c}")
-    out = torch.empty((n, h, w, 4), device=feat.device, dtype=torch.float32)
-    _lib.check(_lib.lib().gens_nchw4_to_nhwc4(_lib.ptr(feat), _lib.ptr(out), n, h, w,
-                                              _lib.stream_ptr(feat.device)), "gens_nchw4_to_nhwc4")
-    return out
+
+def voxel_axis(d: int, device) -> torch.Tensor:
+    """torch.linspace(-1, 1, d) on `device` -- the very call of the reference (volume.py:28), cached."""
+    key = (int(d), str(device))
+    g = _GRID_CACHE.get(key)
+    if g is None:
+        g = torch.linspace(-1, 1, d, device=device, dtype=torch.float32)
+        _GRID_CACHE[key] = g
+    return g
+
+
+def pack_feature_maps(feat: torch.Tensor) -> torch.Tensor:
+    """(n,4,h,w) NCHW -> zero-padded channels-last (n,h+1,w+1,4) with our own kernel."""
+    return pack_feature_pyramid([feat])[0]
+
+
+def pack_feature_pyramid(features: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """All scales with one C call (gens_pack_feature_maps_multi)."""
+    feats = []
+    for f in features:
+        _lib.require_cuda(f)
+        f = _lib.f32c(f)
+        if f.dim() != 4 or f.shape[1] != 4:
+            raise RuntimeError("gens_b200 volume kernels are built for 4-channel (n,4,h,w) feature maps, got "
+                               f"{tuple(f.shape)}")
+        feats.append(f)
+    n = feats[0].shape[0]
+    dev = feats[0].device
+    outs = [torch.empty((n, f.shape[2] + 1, f.shape[3] + 1, 4), device=dev, dtype=torch.float32) for f in feats]
+    k = len(feats)
+    src = (ctypes.c_void_p * k)(*[f.data_ptr() for f in feats])
+    dst = (ctypes.c_void_p * k)(*[o.data_ptr() for o in outs])
+    hs = (ctypes.c_int * k)(*[f.shape[2] for f in feats])
+    ws = (ctypes.c_int * k)(*[f.shape[3] for f in feats])
+    _lib.check(_lib.lib().gens_pack_feature_maps_multi(src, dst, hs, ws, k, n, _lib.stream_ptr(dev)),
+               "gens_pack_feature_maps_multi")
+    return outs
 
 
 def stage_cameras(intrs: torch.Tensor, c2ws: torch.Tensor, scale: int):
-    """The tiny host-side prologue of the reference, kept as torch ops on the tensors' device so
-    the matrices are bit-identical to the reference's (volume.py:24-25, :34)."""
+    """(w2c, k_stage) exactly as the reference prepares them (volume.py:24-25, :34); used by tests that
+    drive the single-scale C entry with pre-scaled intrinsics (k_row_scale = 1)."""
     k = intrs.clone()
     k[:, :2] *= 0.5 ** scale
     return _lib.f32c(torch.inverse(c2ws)), _lib.f32c(k)
 
 
 class _AggMeanVar(torch.autograd.Function):
-    """One scale.  Differentiable w.r.t. the feature map only (grid is under no_grad upstream)."""
+    """All scales of one build.  Differentiable w.r.t. the feature maps only (the voxel grid is under
+    no_grad in the reference, volume.py:27-44)."""
 
     @staticmethod
-    def forward(ctx, feat, w2c, k_stage, grid, d, slab, min_vis_view, div_mode):
-        a0, a1 = slab
-        feat_cl = to_channels_last4(feat)
-        nv, h, w, _ = feat_cl.shape
-        planes = a1 - a0
-        vol = torch.empty((1, 8, planes, d, d), device=feat.device, dtype=torch.float32)
-        msk = torch.empty((1, 1, planes, d, d), device=feat.device, dtype=torch.float32)
-        _lib.check(_lib.lib().gens_volume_agg_fwd(
-            _lib.ptr(feat_cl), nv, h, w, _lib.ptr(w2c), _lib.ptr(k_stage), _lib.ptr(grid), d, a0, a1, a0,
-            planes * d * d, int(min_vis_view), int(div_mode), _lib.ptr(vol), _lib.ptr(msk),
-            _lib.stream_ptr(feat.device)), "gens_volume_agg_fwd")
-        ctx.save_for_backward(feat_cl, w2c, k_stage, grid)
-        ctx.meta = (d, a0, a1, div_mode)
-        ctx.mark_non_differentiable(msk)
-        return vol, msk
+    def forward(ctx, w2c, intrs, dims, slabs, min_vis_view, div_mode, *features):
+        dev = features[0].device
+        packed = pack_feature_pyramid(features)
+        nv = features[0].shape[0]
+        n = len(dims)
+        scales = (_lib.VolumeScale * n)()
+        vols, masks, grids = [], [], []
+        for i, d in enumerate(dims):
+            a0, a1 = slabs[i]
+            planes = a1 - a0
+            vol = torch.empty((1, 8, planes, d, d), device=dev, dtype=torch.float32)
+            msk = torch.empty((1, 1, planes, d, d), device=dev, dtype=torch.float32)
+            grid = voxel_axis(d, dev)
+            sc = scales[i]
+            sc.feat_padded = packed[i].data_ptr()
+            sc.H, sc.W, sc.D = features[i].shape[2], features[i].shape[3], d
+            sc.a0, sc.a1, sc.a_base = a0, a1, a0
+            sc.channel_stride = planes * d * d
+            sc.k_row_scale = 0.5 ** i
+            sc.grid, sc.volume, sc.mask_volume = grid.data_ptr(), vol.data_ptr(), msk.data_ptr()
+            vols.append(vol)
+            masks.append(msk)
+            grids.append(grid)
+        _lib.check(_lib.lib().gens_volume_agg_fwd_multi(scales, n, nv, _lib.ptr(w2c), _lib.ptr(intrs),
+                                                        int(min_vis_view), int(div_mode), _lib.stream_ptr(dev)),
+                   "gens_volume_agg_fwd_multi")
+        ctx.save_for_backward(w2c, intrs, *packed)
+        ctx.meta = (list(dims), list(slabs), div_mode, [tuple(f.shape) for f in features])
+        ctx.mark_non_differentiable(*masks)
+        return (*vols, *masks)
 
     @staticmethod
-    def backward(ctx, g_vol, _g_msk):
-        feat_cl, w2c, k_stage, grid = ctx.saved_tensors
-        d, a0, a1, div_mode = ctx.meta
-        nv, h, w, _ = feat_cl.shape
-        g_vol = _lib.f32c(g_vol)
-        g_feat = torch.zeros_like(feat_cl)
-        _lib.check(_lib.lib().gens_volume_agg_bwd(
-            _lib.ptr(feat_cl), nv, h, w, _lib.ptr(w2c), _lib.ptr(k_stage), _lib.ptr(grid), d, a0, a1, a0,
-            (a1 - a0) * d * d, int(div_mode), _lib.ptr(g_vol), _lib.ptr(g_feat),
-            _lib.stream_ptr(g_vol.device)), "gens_volume_agg_bwd")
-        return g_feat.permute(0, 3, 1, 2), None, None, None, None, None, None, None
+    def backward(ctx, *grads):
+        w2c, intrs, *packed = ctx.saved_tensors
+        dims, slabs, div_mode, shapes = ctx.meta
+        n = len(dims)
+        dev = w2c.device
+        out = []
+        for i, d in enumerate(dims):
+            g_vol = grads[i]
+            if g_vol is None or not ctx.needs_input_grad[6 + i]:
+                out.append(None)
+                continue
+            g_vol = _lib.f32c(g_vol)
+            nv, _, h, w = shapes[i]
+            a0, a1 = slabs[i]
+            g_pad = torch.zeros_like(packed[i])
+            _lib.check(_lib.lib().gens_volume_agg_bwd(
+                _lib.ptr(packed[i]), nv, h, w, _lib.ptr(w2c), _lib.ptr(intrs), 0.5 ** i, _lib.ptr(voxel_axis(d, dev)),
+                d, a0, a1, a0, (a1 - a0) * d * d, int(div_mode), _lib.ptr(g_vol), _lib.ptr(g_pad),
+                _lib.stream_ptr(dev)), "gens_volume_agg_bwd")
+            g_nchw = torch.empty(shapes[i], device=dev, dtype=torch.float32)
+            _lib.check(_lib.lib().gens_unpack_feature_grads(_lib.ptr(g_pad), _lib.ptr(g_nchw), nv, h, w,
+                                                            _lib.stream_ptr(dev)), "gens_unpack_feature_grads")
+            out.append(g_nchw)
+        return (None, None, None, None, None, None, *out)
+
+
+def agg_mean_var(features, intrs, c2ws, dims, min_vis_view: int = 1,
+                 slabs: Optional[Sequence[Tuple[int, int]]] = None, div_mode: int = DEFAULT_DIV_MODE):
+    """The 5-scale build.  `slabs[i] = (a0, a1)` restricts scale i to planes of tensor dim 2 (the
+    multi-GPU sharding); default = full volumes.  Returns (volumes, mask_volumes) as the reference."""
+    _lib.require_cuda(intrs, c2ws, *features[:len(dims)])
+    w2c = _lib.f32c(torch.inverse(c2ws))  # same op as the reference (volume.py:34): bit-identical matrices
+    k = _lib.f32c(intrs)
+    slabs = [(0, d) for d in dims] if slabs is None else list(slabs)
+    out = _AggMeanVar.apply(w2c, k, tuple(dims), tuple(slabs), min_vis_view, div_mode, *features[:len(dims)])
+    n = len(dims)
+    return list(out[:n]), list(out[n:])
 
 
 def agg_mean_var_scale(feat, intrs, c2ws, scale: int, d: int, min_vis_view: int = 1,
                        slab: Optional[Tuple[int, int]] = None, div_mode: int = DEFAULT_DIV_MODE):
-    """One scale of the build; `slab=(a0,a1)` restricts it to planes of tensor dim 2."""
+    """One scale only (tests, slab experiments): same kernels, k_row_scale = 0.5**scale."""
     _lib.require_cuda(feat, intrs, c2ws)
-    w2c, k_stage = stage_cameras(intrs, c2ws, scale)
-    grid = torch.linspace(-1, 1, d).type_as(k_stage)  # same call as the reference (volume.py:28)
-    slab = (0, d) if slab is None else slab
-    return _AggMeanVar.apply(feat, w2c, k_stage, grid, d, slab, min_vis_view, div_mode)
+    dev = feat.device
+    w2c, k = _lib.f32c(torch.inverse(c2ws)), _lib.f32c(intrs)
+    a0, a1 = (0, d) if slab is None else slab
+
+    class _One(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, f):
+            packed = pack_feature_maps(f)
+            nv, _, h, w = f.shape
+            vol = torch.empty((1, 8, a1 - a0, d, d), device=dev, dtype=torch.float32)
+            msk = torch.empty((1, 1, a1 - a0, d, d), device=dev, dtype=torch.float32)
+            _lib.check(_lib.lib().gens_volume_agg_fwd(
+                _lib.ptr(packed), nv, h, w, _lib.ptr(w2c), _lib.ptr(k), 0.5 ** scale, _lib.ptr(voxel_axis(d, dev)), d,
+                a0, a1, a0, (a1 - a0) * d * d, int(min_vis_view), int(div_mode), _lib.ptr(vol), _lib.ptr(msk),
+                _lib.stream_ptr(dev)), "gens_volume_agg_fwd")
+            ctx.save_for_backward(packed)
+            ctx.shape = tuple(f.shape)
+            ctx.mark_non_differentiable(msk)
+            return vol, msk
+
+        @staticmethod
+        def backward(ctx, g_vol, _g):
+            (packed,) = ctx.saved_tensors
+            nv, _, h, w = ctx.shape
+            g_vol = _lib.f32c(g_vol)
+            g_pad = torch.zeros_like(packed)
+            _lib.check(_lib.lib().gens_volume_agg_bwd(
+                _lib.ptr(packed), nv, h, w, _lib.ptr(w2c), _lib.ptr(k), 0.5 ** scale, _lib.ptr(voxel_axis(d, dev)), d,
+                a0, a1, a0, (a1 - a0) * d * d, int(div_mode), _lib.ptr(g_vol), _lib.ptr(g_pad),
+                _lib.stream_ptr(dev)), "gens_volume_agg_bwd")
+            g = torch.empty(ctx.shape, device=dev, dtype=torch.float32)
+            _lib.check(_lib.lib().gens_unpack_feature_grads(_lib.ptr(g_pad), _lib.ptr(g), nv, h, w,
+                                                            _lib.stream_ptr(dev)), "gens_unpack_feature_grads")
+            return g
+
+    return _One.apply(feat)
 
 
 class Volume(nn.Module):
@@ -94,9 +197,4 @@ class Volume(nn.Module):
 
     def agg_mean_var(self, features: List[torch.Tensor], intrs: torch.Tensor, c2ws: torch.Tensor,
                      min_vis_view: int = 1):
-        volumes, mask_volumes = [], []
-        for i, d in enumerate(self.volume_dims):
-            vol, msk = agg_mean_var_scale(features[i], intrs, c2ws, i, d, min_vis_view, None, self.div_mode)
-            volumes.append(vol)
-            mask_volumes.append(msk)
-        return volumes, mask_volumes
+        return agg_mean_var(features, intrs, c2ws, self.volume_dims, min_vis_view, None, self.div_mode)

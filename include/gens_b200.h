@@ -38,43 +38,77 @@ extern "C" {
 int gens_abi_version(void);
 const char *gens_error_string(int code);
 
-/* ---- layout helper ---------------------------------------------------------------- */
-/* (n,4,h,w) NCHW -> (n,h,w,4) NHWC so that one bilinear corner is a single 16-byte load. */
-int gens_nchw4_to_nhwc4(const float *src, float *dst, int n, int h, int w, void *stream);
+/* ---- layout helpers ---------------------------------------------------------------- */
+/* (n,4,h,w) NCHW -> zero-padded channels-last (n, h+1, w+1, 4): one bilinear corner is a
+ * single 16-byte load and the +1 corners of every valid sample exist in memory. */
+int gens_pack_feature_maps(const float *src_nchw, float *dst_padded_nhwc, int n, int h, int w,
+                           void *stream);
+/* inverse for gradients: padded channels-last (n, h+1, w+1, 4) -> (n,4,h,w) NCHW */
+int gens_unpack_feature_grads(const float *src_padded_nhwc, float *dst_nchw, int n, int h, int w,
+                              void *stream);
 
 /* ---- K1: multi-view feature-volume aggregation ---------------------------------------
- * Replaces one scale of Volume.agg_mean_var (reference models/modules/volume.py:21-58):
- * project every voxel centre into every view, bilinear-sample the 4-channel feature map
- * (zeros padding, align_corners=True), masked sum / sum-of-squares / count over views,
- * write [mean(4), var(4)] and the visibility mask (count > min_vis_view).
+ * Replaces Volume.agg_mean_var (reference models/modules/volume.py:13-63): per scale, project
+ * every voxel centre into every view, bilinear-sample the 4-channel feature map (zeros
+ * padding, align_corners=True), masked sum / sum-of-squares / count over views, write
+ * [mean(4), var(4)] and the visibility mask (count > min_vis_view).
  *
- *   feat_nhwc (nv,H,W,4)   w2c (nv,4,4) = inverse(c2ws)   k_stage (nv,4,4) rows 0-1 scaled
- *   grid (D) = linspace(-1,1,D)
- *   planes [a0,a1) of tensor dim 2 (world x) are produced -- slab sharding.
- *   volume: channel c, voxel (a,b,c') is written at
- *           volume[c*channel_stride + ((a-a_base)*D + b)*D + c'], same for mask (1 channel)
- *           (a_base = a0, channel_stride = (a1-a0)*D*D for a slab buffer;
- *            a_base = 0,  channel_stride = D*D*D       for the full tensor).
- */
-int gens_volume_agg_fwd(const float *feat_nhwc, int nv, int H, int W, const float *w2c,
-                        const float *k_stage, const float *grid, int D, int a0, int a1,
-                        int a_base, long long channel_stride, int min_vis_view, int div_mode,
-                        float *volume, float *mask_volume, void *stream);
+ *   w2c   (nv,4,4) = inverse(c2ws)            (reference volume.py:34)
+ *   intrs (nv,4,4) unscaled intrinsics; rows 0-1 are multiplied by k_row_scale = 0.5^scale in
+ *                  the kernel, exactly like `intrs_stage[:, :2] *= 0.5**i` (volume.py:24-25)
+ * One scale: */
+typedef struct gens_volume_scale {
+    const float *feat_padded; /* (nv,H+1,W+1,4) from gens_pack_feature_maps                 */
+    int H, W;                 /* feature-map size of this scale                              */
+    int D;                    /* volume_dims[scale]                                          */
+    int a0, a1;               /* planes [a0,a1) of tensor dim 2 (world x) to build (slab)    */
+    int a_base;               /* plane index the output buffers start at                     */
+    long long channel_stride; /* elements between output channels                            */
+    float k_row_scale;        /* 0.5^scale                                                   */
+    const float *grid;        /* (D) = linspace(-1,1,D)                       (volume.py:28) */
+    float *volume;            /* channel c, voxel (a,b,c') at                                */
+    float *mask_volume;       /*   [c*channel_stride + ((a-a_base)*D + b)*D + c']            */
+} gens_volume_scale_t;
+/* (a_base = a0, channel_stride = (a1-a0)*D*D for a slab buffer;
+ *  a_base = 0,  channel_stride = D*D*D       for the full (1,8,D,D,D) tensor). */
+
+/* All scales of one build, launched back to back on `stream` (one host call per build). */
+int gens_volume_agg_fwd_multi(const gens_volume_scale_t *scales, int n_scales, int nv,
+                              const float *w2c, const float *intrs, int min_vis_view,
+                              int div_mode, void *stream);
+/* Single-scale convenience form of the same. */
+int gens_volume_agg_fwd(const float *feat_padded, int nv, int H, int W, const float *w2c,
+                        const float *intrs, float k_row_scale, const float *grid, int D, int a0,
+                        int a1, int a_base, long long channel_stride, int min_vis_view,
+                        int div_mode, float *volume, float *mask_volume, void *stream);
+/* Pack every scale's (n,4,h_i,w_i) map with one host call. */
+int gens_pack_feature_maps_multi(const float *const *src_nchw, float *const *dst_padded,
+                                 const int *h, const int *w, int n_scales, int n, void *stream);
 
 /* Debug/parity view of K1's projection stage: per (view, voxel) the floor corner index of
  * the bilinear footprint and the validity bit (volume.py:43).  Outputs are (nv, D,D,D);
  * ix0/iy0 are 0 where the view is invalid. */
-int gens_volume_project_debug(int nv, int H, int W, const float *w2c, const float *k_stage,
-                              const float *grid, int D, int div_mode, int32_t *ix0,
-                              int32_t *iy0, uint8_t *valid, void *stream);
+int gens_volume_project_debug(int nv, int H, int W, const float *w2c, const float *intrs,
+                              float k_row_scale, const float *grid, int D, int div_mode,
+                              int32_t *ix0, int32_t *iy0, uint8_t *valid, void *stream);
 
 /* Backward of K1 w.r.t. the feature maps (the voxel grid is under no_grad in the
- * reference, volume.py:27-44).  grad_volume addressed like `volume` above; grad_feat_nhwc
- * (nv,H,W,4) must be zero-initialised by the caller (atomic scatter). */
-int gens_volume_agg_bwd(const float *feat_nhwc, int nv, int H, int W, const float *w2c,
-                        const float *k_stage, const float *grid, int D, int a0, int a1,
-                        int a_base, long long channel_stride, int div_mode,
-                        const float *grad_volume, float *grad_feat_nhwc, void *stream);
+ * reference, volume.py:27-44).  grad_volume addressed like `volume` above; grad_feat_padded
+ * (nv,H+1,W+1,4) must be zero-initialised by the caller (atomic scatter). */
+int gens_volume_agg_bwd(const float *feat_padded, int nv, int H, int W, const float *w2c,
+                        const float *intrs, float k_row_scale, const float *grid, int D, int a0,
+                        int a1, int a_base, long long channel_stride, int div_mode,
+                        const float *grad_volume, float *grad_feat_padded, void *stream);
+
+/* Tuning knob for profiling sessions: selects among compiled-in launch configurations of K1
+ * (0 = the shipped one).  Results are identical for every variant. */
+int gens_debug_set_variant(int variant);
+
+/* Device self-test of the exact-division shortcuts K1 uses (tests only): [0] = mismatches of
+ * the count division s/n (every fp32 s, n = 1..max_n) and [1] = mismatches of the shared-
+ * reciprocal division over n_pair_cases random operand pairs, both against div.rn.f32. */
+int gens_selftest_division(int max_n, unsigned long long n_pair_cases,
+                           unsigned long long *d_mismatches2, void *stream);
 
 #ifdef __cplusplus
 }

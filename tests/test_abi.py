@@ -34,8 +34,8 @@ def test_abi_version_and_error_strings():
 
 def test_bad_arguments_are_rejected_without_a_gpu():
     h = _lib.lib()
-    assert h.gens_nchw4_to_nhwc4(None, None, 1, 1, 1, None) == -1
-    assert h.gens_volume_agg_fwd(None, 3, 4, 4, None, None, None, 8, 0, 8, 0, 512, 1, 0, None, None, None) == -1
+    assert h.gens_pack_feature_maps(None, None, 1, 1, 1, None) == -1
+    assert h.gens_volume_agg_fwd(None, 3, 4, 4, None, None, 1.0, None, 8, 0, 8, 0, 512, 1, 0, None, None, None) == -1
 
 
 def test_no_oracle_import_in_product():

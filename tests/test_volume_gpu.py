@@ -7,7 +7,7 @@ import torch
 
 from gens_b200 import _lib
 from gens_b200.synthetic import make_scene
-from gens_b200.volume import Volume, agg_mean_var_scale, stage_cameras, to_channels_last4
+from gens_b200.volume import Volume, agg_mean_var_scale, stage_cameras, pack_feature_maps
 from oracle import c_oracle, torch_oracle
 
 pytestmark = pytest.mark.gpu
@@ -17,6 +17,28 @@ DEV = "cuda:0"
 RTOL, ATOL = 1e-4, 1e-6
 
 
+def _run_k1(feat, w2c, k, d, div_mode, min_vis_view=1):
+    """Direct C-ABI call of K1 + its projection view on host-prepared camera matrices.  Every device
+    tensor is held in a local until the synchronising .cpu() so the allocator cannot recycle it."""
+    feat_d = pack_feature_maps(feat.to(DEV))
+    nv, _, h, w = feat.shape
+    w2c_d, k_d, grid_d = w2c.to(DEV).contiguous(), k.to(DEV).contiguous(), torch.linspace(-1, 1, d).to(DEV)
+    vol = torch.empty((8, d, d, d), device=DEV)
+    msk = torch.empty((d, d, d), device=DEV)
+    ix0 = torch.empty((nv, d, d, d), dtype=torch.int32, device=DEV)
+    iy0 = torch.empty_like(ix0)
+    valid = torch.empty((nv, d, d, d), dtype=torch.uint8, device=DEV)
+    L = _lib.lib()
+    _lib.check(L.gens_volume_agg_fwd(_lib.ptr(feat_d), nv, h, w, _lib.ptr(w2c_d), _lib.ptr(k_d), 1.0, _lib.ptr(grid_d),
+                                     d, 0, d, 0, d ** 3, min_vis_view, div_mode, _lib.ptr(vol), _lib.ptr(msk),
+                                     _lib.stream_ptr()), "gens_volume_agg_fwd")
+    _lib.check(L.gens_volume_project_debug(nv, h, w, _lib.ptr(w2c_d), _lib.ptr(k_d), 1.0, _lib.ptr(grid_d), d, div_mode,
+                                           _lib.ptr(ix0), _lib.ptr(iy0), _lib.ptr(valid), _lib.stream_ptr()),
+               "gens_volume_project_debug")
+    torch.cuda.synchronize()
+    return vol.cpu().numpy(), msk.cpu().numpy(), ix0.cpu().numpy(), iy0.cpu().numpy(), valid.cpu().numpy()
+
+
 def _project_debug(intrs, c2ws, scale, d, hw, div_mode):
     w2c, k = stage_cameras(intrs, c2ws, scale)
     grid = torch.linspace(-1, 1, d, device=DEV)
@@ -24,9 +46,10 @@ def _project_debug(intrs, c2ws, scale, d, hw, div_mode):
     ix0 = torch.empty((nv, d, d, d), dtype=torch.int32, device=DEV)
     iy0 = torch.empty_like(ix0)
     valid = torch.empty((nv, d, d, d), dtype=torch.uint8, device=DEV)
-    _lib.check(_lib.lib().gens_volume_project_debug(nv, hw[0], hw[1], _lib.ptr(w2c), _lib.ptr(k), _lib.ptr(grid), d,
+    _lib.check(_lib.lib().gens_volume_project_debug(nv, hw[0], hw[1], _lib.ptr(w2c), _lib.ptr(k), 1.0, _lib.ptr(grid), d,
                                                     div_mode, _lib.ptr(ix0), _lib.ptr(iy0), _lib.ptr(valid),
                                                     _lib.stream_ptr()), "project_debug")
+    torch.cuda.synchronize()
     return ix0.cpu().numpy(), iy0.cpu().numpy(), valid.cpu().numpy()
 
 
@@ -34,68 +57,42 @@ def test_golden_fixture_bit_exact_vs_reference_cpu(cuda_lib, golden_dir):
     """div_mode TRUE reproduces the reference's CPU run: masks and indices bit-exact, values 1e-4."""
     g = np.load(f"{golden_dir}/volume_agg.npz")
     intrs = torch.from_numpy(g["intrs"])
-    c2ws = torch.from_numpy(g["c2ws"])
-    # camera prologue on the CPU, exactly the golden run's matrices, then moved over
+    w2c = torch.inverse(torch.from_numpy(g["c2ws"]))  # camera prologue on the CPU, as in the golden run
     for i, d in enumerate(g["dims"]):
         d = int(d)
-        feat = torch.from_numpy(g[f"feat{i}"]).to(DEV)
+        feat = torch.from_numpy(g[f"feat{i}"])
         h, w = feat.shape[-2:]
         k = intrs.clone()
         k[:, :2] *= 0.5 ** i
-        w2c = torch.inverse(c2ws)
-        vol = torch.empty((8, d, d, d), device=DEV)
-        msk = torch.empty((d, d, d), device=DEV)
-        grid = torch.linspace(-1, 1, d)
-        _lib.check(_lib.lib().gens_volume_agg_fwd(
-            _lib.ptr(to_channels_last4(feat)), 3, h, w, _lib.ptr(w2c.to(DEV)), _lib.ptr(k.to(DEV)),
-            _lib.ptr(grid.to(DEV)), d, 0, d, 0, d ** 3, 1, _lib.DIV_TRUE, _lib.ptr(vol), _lib.ptr(msk),
-            _lib.stream_ptr()), "agg")
-        assert np.array_equal(msk.cpu().numpy(), g[f"mask{i}"])
+        vol, msk, ix0, iy0, valid = _run_k1(feat, w2c, k, d, _lib.DIV_TRUE)
+        assert np.array_equal(msk, g[f"mask{i}"])
         ref = g[f"volume{i}"]
-        assert np.all(np.abs(vol.cpu().numpy() - ref) <= ATOL + RTOL * np.abs(ref))
-        # projection stage
-        ix0 = torch.empty((3, d, d, d), dtype=torch.int32, device=DEV)
-        iy0 = torch.empty_like(ix0)
-        valid = torch.empty((3, d, d, d), dtype=torch.uint8, device=DEV)
-        _lib.check(_lib.lib().gens_volume_project_debug(
-            3, h, w, _lib.ptr(w2c.to(DEV)), _lib.ptr(k.to(DEV)), _lib.ptr(grid.to(DEV)), d, _lib.DIV_TRUE,
-            _lib.ptr(ix0), _lib.ptr(iy0), _lib.ptr(valid), _lib.stream_ptr()), "dbg")
+        assert np.all(np.abs(vol - ref) <= ATOL + RTOL * np.abs(ref))
         vm = g[f"viewmask{i}"]
-        assert np.array_equal(valid.cpu().numpy(), vm)
+        assert np.array_equal(valid, vm)
         rix, riy = torch_oracle.corner_indices(torch.from_numpy(g[f"grid{i}"]), (h, w))
         sel = vm.astype(bool)
-        assert np.array_equal(ix0.cpu().numpy()[sel], rix.numpy().reshape(vm.shape)[sel])
-        assert np.array_equal(iy0.cpu().numpy()[sel], riy.numpy().reshape(vm.shape)[sel])
+        assert np.array_equal(ix0[sel], rix.numpy().reshape(vm.shape)[sel])
+        assert np.array_equal(iy0[sel], riy.numpy().reshape(vm.shape)[sel])
 
 
-@pytest.mark.parametrize("nv,hw,dims", [(3, (240, 320), [64, 32, 16, 8, 4]), (5, (96, 128), [48, 20, 12, 6, 3])])
+@pytest.mark.parametrize("nv,hw,dims", [(3, (240, 320), [128, 64, 32, 16, 8, 4]), (5, (96, 128), [48, 20, 12, 6, 3])])
 def test_matches_c_oracle(cuda_lib, nv, hw, dims):
-    """Seeded synthetic scenes (config 1 shape + a ragged one with D % 4 != 0): CUDA == C oracle."""
-    sc = make_scene(hw[0], hw[1], nv, seed=3)
+    """Seeded synthetic scenes (config 1 shape incl. a packed-kernel scale, and a ragged one with
+    D % 4 != 0): CUDA == C oracle, bit for bit (masks, indices AND mean/var volumes)."""
+    sc = make_scene(hw[0], hw[1], nv, seed=3, n_scales=len(dims))
     for div_mode in (_lib.DIV_TRUE, _lib.DIV_RECIP):
         for i, d in enumerate(dims):
             w2c, k = stage_cameras(sc.intrs, sc.c2ws, i)
-            grid = torch.linspace(-1, 1, d)
             ovol, omsk, oix, oiy, ovm = c_oracle.volume_agg(sc.features[i].numpy(), w2c.numpy(), k.numpy(),
-                                                            grid.numpy(), div_mode=div_mode, debug=True)
-            feat = sc.features[i].to(DEV)
-            vol = torch.empty((8, d, d, d), device=DEV)
-            msk = torch.empty((d, d, d), device=DEV)
-            h, w = feat.shape[-2:]
-            _lib.check(_lib.lib().gens_volume_agg_fwd(
-                _lib.ptr(to_channels_last4(feat)), nv, h, w, _lib.ptr(w2c.to(DEV)), _lib.ptr(k.to(DEV)),
-                _lib.ptr(grid.to(DEV)), d, 0, d, 0, d ** 3, 1, div_mode, _lib.ptr(vol), _lib.ptr(msk),
-                _lib.stream_ptr()), "agg")
-            assert np.array_equal(msk.cpu().numpy(), omsk), (div_mode, d)
-            assert np.all(np.abs(vol.cpu().numpy() - ovol) <= ATOL + RTOL * np.abs(ovol)), (div_mode, d)
-            ix0 = torch.empty((nv, d, d, d), dtype=torch.int32, device=DEV)
-            iy0 = torch.empty_like(ix0)
-            valid = torch.empty((nv, d, d, d), dtype=torch.uint8, device=DEV)
-            _lib.check(_lib.lib().gens_volume_project_debug(
-                nv, h, w, _lib.ptr(w2c.to(DEV)), _lib.ptr(k.to(DEV)), _lib.ptr(grid.to(DEV)), d, div_mode,
-                _lib.ptr(ix0), _lib.ptr(iy0), _lib.ptr(valid), _lib.stream_ptr()), "dbg")
-            assert np.array_equal(valid.cpu().numpy(), ovm)
-            assert np.array_equal(ix0.cpu().numpy(), oix) and np.array_equal(iy0.cpu().numpy(), oiy)
+                                                            torch.linspace(-1, 1, d).numpy(), div_mode=div_mode,
+                                                            debug=True)
+            vol, msk, ix0, iy0, valid = _run_k1(sc.features[i], w2c, k, d, div_mode)
+            assert np.array_equal(msk, omsk), (div_mode, d)
+            assert np.array_equal(valid, ovm), (div_mode, d)
+            assert np.array_equal(ix0, oix) and np.array_equal(iy0, oiy), (div_mode, d)
+            assert np.all(np.abs(vol - ovol) <= ATOL + RTOL * np.abs(ovol)), (div_mode, d)
+            assert np.array_equal(vol, ovol), f"values not bit-identical to the oracle (div_mode {div_mode}, D {d})"
 
 
 def test_public_api_matches_aten_ops_on_gpu(cuda_lib):
@@ -154,4 +151,30 @@ def test_rejects_cpu_tensors_and_bad_channels(cuda_lib):
     with pytest.raises(RuntimeError):
         Volume(volume_dims=[8]).agg_mean_var(sc.features, sc.intrs, sc.c2ws)
     with pytest.raises(RuntimeError):
-        to_channels_last4(torch.zeros(1, 3, 4, 4, device=DEV))
+        pack_feature_maps(torch.zeros(1, 3, 4, 4, device=DEV))
+
+
+def test_exact_division_shortcuts(cuda_lib):
+    """K1's two division shortcuts are bit-identical to div.rn.f32: s/n for EVERY fp32 s and n = 1..16,
+    and the shared-reciprocal projection division on 2^32 random operand pairs."""
+    out = torch.zeros(2, dtype=torch.int64, device=DEV)
+    _lib.check(_lib.lib().gens_selftest_division(16, 1 << 32, _lib.ptr(out), _lib.stream_ptr()), "selftest")
+    torch.cuda.synchronize()
+    assert out.tolist() == [0, 0], out.tolist()
+
+
+def test_public_api_backward_all_scales(cuda_lib):
+    """Gradients through Volume.agg_mean_var (one autograd node for all scales) match autograd of the
+    ATen op sequence for every feature map."""
+    sc = make_scene(96, 128, 3, seed=9).to(DEV)
+    dims = [32, 16, 8]
+    feats = [f.clone().requires_grad_(True) for f in sc.features[:3]]
+    vols, _ = Volume(volume_dims=dims).agg_mean_var(feats, sc.intrs, sc.c2ws)
+    gouts = [torch.randn_like(v) for v in vols]
+    grads = torch.autograd.grad(vols, feats, gouts)
+    feats2 = [f.clone().requires_grad_(True) for f in sc.features[:3]]
+    rvols, _ = torch_oracle.agg_mean_var(feats2, sc.intrs, sc.c2ws, dims)
+    rgrads = torch.autograd.grad(rvols, feats2, gouts)
+    for g, rg in zip(grads, rgrads):
+        scale = rg.abs().max().item()
+        assert torch.all((g - rg).abs() <= 1e-5 * scale + 1e-4 * rg.abs())
