@@ -27,6 +27,27 @@ class VolumeScale(ctypes.Structure):
     ]
 
 
+MAX_SCALES = 8
+
+
+class Pyramid(ctypes.Structure):
+    """Mirror of gens_pyramid_t."""
+    _fields_ = [("vol", _vp * MAX_SCALES), ("dim", _i * MAX_SCALES), ("n_scales", _i)]
+
+
+def make_pyramid(tensors, dims):
+    p = Pyramid()
+    if len(tensors) > MAX_SCALES:
+        raise RuntimeError(f"gens_b200 supports at most {MAX_SCALES} scales, got {len(tensors)}")
+    for i, (t, d) in enumerate(zip(tensors, dims)):
+        p.vol[i] = t.data_ptr() if t is not None else None
+        p.dim[i] = int(d)
+    p.n_scales = len(tensors)
+    return p
+
+
+_PP = ctypes.POINTER(Pyramid)
+
 _SIGNATURES = {
     "gens_abi_version": ([], _i),
     "gens_error_string": ([_i], ctypes.c_char_p),
@@ -37,6 +58,12 @@ _SIGNATURES = {
     "gens_volume_agg_fwd": ([_vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _i, _i, _i, _ll, _i, _i, _vp, _vp, _vp], _i),
     "gens_volume_project_debug": ([_i, _i, _i, _vp, _vp, _f, _vp, _i, _i, _vp, _vp, _vp, _vp], _i),
     "gens_volume_agg_bwd": ([_vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _i, _i, _i, _ll, _i, _vp, _vp, _vp], _i),
+    "gens_pack_volume": ([_vp, _vp, _i, _vp], _i),
+    "gens_unpack_volume": ([_vp, _vp, _i, _vp], _i),
+    "gens_mask_nearest": ([_vp, _ll, _PP, _i, _vp, _vp, _vp], _i),
+    "gens_trilinear_fwd": ([_vp, _ll, _PP, _vp, _vp], _i),
+    "gens_trilinear_bwd": ([_vp, _ll, _PP, _vp, _vp, _PP, _vp], _i),
+    "gens_trilinear_bwd2": ([_vp, _ll, _PP, _vp, _vp, _vp, _vp, _PP, _vp], _i),
     "gens_debug_set_variant": ([_i], _i),
     "gens_selftest_division": ([_i, ctypes.c_ulonglong, _vp, _vp], _i),
 }

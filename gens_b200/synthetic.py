@@ -123,3 +123,18 @@ def make_scene(h: int, w: int, nv: int, seed: int = 0, n_scales: int = 5, feat_c
     feats = [torch.randn(nv, feat_ch, h >> i, w >> i, generator=g) * 0.5 for i in range(n_scales)]
     imgs = torch.rand(nv, 3, h, w, generator=g) if with_images else None
     return Scene(intrs, c2ws, near, far, (h, w), radius, feats, imgs)
+
+
+def make_reg_volumes(dims, seed: int = 0, ch: int = 4):
+    """Stand-ins for the regularised volumes RegNetwork hands to the renderer: smooth random fields
+    (low-resolution noise, trilinearly up-sampled) plus a little high-frequency noise, (1,ch,D,D,D)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(seed + 1000)
+    vols = []
+    for d in dims:
+        lo_res = max(d // 4, 2)
+        base = torch.randn(1, ch, lo_res, lo_res, lo_res, generator=g) * 0.5
+        v = F.interpolate(base, size=(d, d, d), mode="trilinear", align_corners=True)
+        v = v + 0.05 * torch.randn(1, ch, d, d, d, generator=g)
+        vols.append(v.contiguous())
+    return vols

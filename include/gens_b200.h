@@ -100,6 +100,48 @@ int gens_volume_agg_bwd(const float *feat_padded, int nv, int H, int W, const fl
                         int a1, int a_base, long long channel_stride, int div_mode,
                         const float *grad_volume, float *grad_feat_padded, void *stream);
 
+/* ---- K2 / K3: multi-scale volume look-ups ---------------------------------------------
+ * Replace projector.lookup_volume (reference models/modules/projector.py:217-245), the autograd
+ * triple cug.grid_sample_3d (models/modules/grid_sample_cuda/cuda_gridsample.py:71-123) and the
+ * native second-derivative op it binds, `gridsample_grad2.grad2_3d`
+ * (gridsample_cuda.cpp:39-55, gridsample_cuda.cu:212-533).
+ * A point p = (p0,p1,p2) addresses tensor dims (2,3,4) of the volumes (the reference's
+ * pts.flip(-1) + grid_sample convention); every scale of the pyramid is handled by one launch. */
+#define GENS_MAX_SCALES 8
+typedef struct gens_pyramid {
+    const float *vol[GENS_MAX_SCALES]; /* per scale: device pointer (layout stated per function) */
+    int dim[GENS_MAX_SCALES];          /* per scale: D                                            */
+    int n_scales;
+} gens_pyramid_t;
+
+/* (1,4,D,D,D) NCDHW -> channels-last (D,D,D,4) (one trilinear corner = one 16-byte load), and back. */
+int gens_pack_volume(const float *src_ncdhw, float *dst_channels_last, int D, void *stream);
+int gens_unpack_volume(const float *src_channels_last, float *dst_ncdhw, int D, void *stream);
+
+/* K2: F.grid_sample(mask, mode='nearest', align_corners=False) on every scale (projector.py:231,
+ * :240); masks->vol[s] = (D,D,D) fp32 as the reference stores them.  any_out (n) uint8 = OR over
+ * scales of (value != 0) -- the `.any(dim=-1)` every caller applies -- and/or each_out (n,S) fp32
+ * = the sampled values.  aten_cuda_flavour: 1 = un-normalise with the fused multiply-subtract of
+ * ATen's CUDA build, 0 = separately rounded as its CPU build. */
+int gens_mask_nearest(const float *pts, long long n, const gens_pyramid_t *masks,
+                      int aten_cuda_flavour, uint8_t *any_out, float *each_out, void *stream);
+
+/* K3 forward: trilinear (zeros padding, align_corners=True) features of every scale,
+ * out (n, 4*S); vols->vol[s] = channels-last (D,D,D,4). */
+int gens_trilinear_fwd(const float *pts, long long n, const gens_pyramid_t *vols, float *out,
+                       void *stream);
+/* K3 backward (aten::grid_sampler_3d_backward x S): g_out (n,4*S) -> g_pts (n,3) (may be null)
+ * and, if g_vols != NULL, atomic scatter into zero-initialised channels-last gradient volumes. */
+int gens_trilinear_bwd(const float *pts, long long n, const gens_pyramid_t *vols,
+                       const float *g_out, float *g_pts, const gens_pyramid_t *g_vols,
+                       void *stream);
+/* K3 backward-of-backward (grad2_3d with grad2_grad_input = 0): given gg_pts (n,3) = gradient
+ * w.r.t. g_pts, returns gg_out (n,4*S) = gradient w.r.t. g_out, g2_pts (n,3) = gradient w.r.t.
+ * pts (mixed second derivatives) and optionally scatters the gradient w.r.t. the volumes. */
+int gens_trilinear_bwd2(const float *pts, long long n, const gens_pyramid_t *vols,
+                        const float *g_out, const float *gg_pts, float *gg_out, float *g2_pts,
+                        const gens_pyramid_t *g2_vols, void *stream);
+
 /* Tuning knob for profiling sessions: selects among compiled-in launch configurations of K1
  * (0 = the shipped one).  Results are identical for every variant. */
 int gens_debug_set_variant(int variant);

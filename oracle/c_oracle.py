@@ -62,3 +62,21 @@ def volume_agg(feat, w2c, k_stage, grid, min_vis_view=1, div_mode=DIV_TRUE, a0=0
     if debug:
         return vol, msk, ix0, iy0, vm
     return vol, msk
+
+
+def nearest(pts, vol, fused=0):
+    """F.grid_sample(mode='nearest', align_corners=False) of a (D,D,D) volume at (n,3) points."""
+    pts, vol = _f32(pts), _f32(vol)
+    n, d = pts.shape[0], vol.shape[-1]
+    out = np.zeros(n, np.float32)
+    lib().gens_oracle_nearest(_p(pts), ctypes.c_long(n), _p(vol), d, int(fused), _p(out))
+    return out
+
+
+def trilinear(pts, vol):
+    """grid_sample 3-D (bilinear, zeros, align_corners=True) of a (C,D,D,D) volume -> (n,C)."""
+    pts, vol = _f32(pts), _f32(vol)
+    n, c, d = pts.shape[0], vol.shape[0], vol.shape[-1]
+    out = np.zeros((n, c), np.float32)
+    lib().gens_oracle_trilinear(_p(pts), ctypes.c_long(n), _p(vol), c, d, _p(out))
+    return out

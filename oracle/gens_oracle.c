@@ -150,3 +150,61 @@ int gens_oracle_volume_agg(const float *feat, int nv, int C, int H, int W, const
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * lookup_volume (reference projector.py:217-245).  A point p=(p0,p1,p2) is flipped to the grid
+ * (x,y,z) = (p2,p1,p0), so p0 indexes tensor dim 2 (D), p1 dim 3 (H), p2 dim 4 (W).
+ * ------------------------------------------------------------------------------------------ */
+
+/* F.grid_sample(mode='nearest', padding_mode='zeros', align_corners=False) of one (D,D,D) volume.
+ * fused = 1 reproduces ATen's CUDA un-normalise (fma contraction of (c+1)*size-1). */
+int gens_oracle_nearest(const float *pts, long n, const float *vol, int D, int fused, float *out) {
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < n; ++i) {
+        float idx[3];
+        for (int k = 0; k < 3; ++k) {
+            float t = pts[3 * i + k] + 1.0f, s = (float)D;
+            float u = fused ? fmaf(t, s, -1.0f) : (t * s - 1.0f);
+            idx[k] = nearbyintf(u * 0.5f); /* round half to even */
+        }
+        float v = 0.0f;
+        if (idx[0] >= 0 && idx[0] < D && idx[1] >= 0 && idx[1] < D && idx[2] >= 0 && idx[2] < D)
+            v = vol[((long)idx[0] * D + (long)idx[1]) * D + (long)idx[2]];
+        out[i] = v;
+    }
+    return 0;
+}
+
+/* grid_sample 3-D, bilinear, zeros padding, align_corners=True of one (C,D,D,D) volume -> out (n,C).
+ * Weights and accumulation order as ATen's grid_sampler_3d kernel (tnw..bse, out += val*w). */
+int gens_oracle_trilinear(const float *pts, long n, const float *vol, int C, int D, float *out) {
+    const long D3 = (long)D * D * D;
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < n; ++i) {
+        /* grid x <- p2 (W), y <- p1 (H), z <- p0 (D) */
+        float ix = ((pts[3 * i + 2] + 1.0f) * 0.5f) * (float)(D - 1);
+        float iy = ((pts[3 * i + 1] + 1.0f) * 0.5f) * (float)(D - 1);
+        float iz = ((pts[3 * i + 0] + 1.0f) * 0.5f) * (float)(D - 1);
+        float x0 = floorf(ix), y0 = floorf(iy), z0 = floorf(iz);
+        float x1 = x0 + 1.0f, y1 = y0 + 1.0f, z1 = z0 + 1.0f;
+        float w[8];
+        w[0] = (x1 - ix) * (y1 - iy) * (z1 - iz); /* tnw */
+        w[1] = (ix - x0) * (y1 - iy) * (z1 - iz); /* tne */
+        w[2] = (x1 - ix) * (iy - y0) * (z1 - iz); /* tsw */
+        w[3] = (ix - x0) * (iy - y0) * (z1 - iz); /* tse */
+        w[4] = (x1 - ix) * (y1 - iy) * (iz - z0); /* bnw */
+        w[5] = (ix - x0) * (y1 - iy) * (iz - z0); /* bne */
+        w[6] = (x1 - ix) * (iy - y0) * (iz - z0); /* bsw */
+        w[7] = (ix - x0) * (iy - y0) * (iz - z0); /* bse */
+        for (int c = 0; c < C; ++c) {
+            float acc = 0.0f;
+            for (int k = 0; k < 8; ++k) {
+                float xf = (k & 1) ? x1 : x0, yf = (k & 2) ? y1 : y0, zf = (k & 4) ? z1 : z0;
+                if (xf >= 0 && xf < D && yf >= 0 && yf < D && zf >= 0 && zf < D)
+                    acc = fmaf(vol[c * D3 + ((long)zf * D + (long)yf) * D + (long)xf], w[k], acc);
+            }
+            out[i * C + c] = acc;
+        }
+    }
+    return 0;
+}

@@ -65,3 +65,39 @@ def corner_indices(grid, hw):
     ix = ((grid[..., 0] + 1) / 2) * (w - 1)
     iy = ((grid[..., 1] + 1) / 2) * (h - 1)
     return torch.floor(ix).to(torch.int32), torch.floor(iy).to(torch.int32)
+
+
+# ---- lookup_volume (reference projector.py:217-245) -------------------------------------------
+def trilinear_dd(vol, pts):
+    """Double-differentiable trilinear look-up of a (1,C,D,D,D) volume at (n,3) points, built from
+    elementary torch ops (ATen's grid_sampler_3d_backward has no derivative of its own; the reference
+    needs its CUDA-only grad2 kernel for that).  p=(p0,p1,p2) addresses tensor dims (2,3,4);
+    align_corners=True, zeros padding.  Returns (n,C)."""
+    _, c, d, _, _ = vol.shape
+    u = ((pts + 1) / 2) * (d - 1)
+    i0 = torch.floor(u).detach()
+    t = u - i0
+    flat = vol.reshape(c, -1)
+    out = 0
+    for da in (0, 1):
+        for db in (0, 1):
+            for dc in (0, 1):
+                a, b, cc = i0[:, 0] + da, i0[:, 1] + db, i0[:, 2] + dc
+                w = (t[:, 0] if da else 1 - t[:, 0]) * (t[:, 1] if db else 1 - t[:, 1]) * (t[:, 2] if dc else 1 - t[:, 2])
+                ok = (a >= 0) & (a < d) & (b >= 0) & (b < d) & (cc >= 0) & (cc < d)
+                idx = (a.clamp(0, d - 1) * d + b.clamp(0, d - 1)) * d + cc.clamp(0, d - 1)
+                out = out + (flat[:, idx.long()] * ok.to(vol.dtype) * w).t()
+    return out
+
+
+def lookup_volume(pts, volumes, sample_mode="grad"):
+    """ATen-op restatement of projector.lookup_volume for a list of volumes -> (n, sum C)."""
+    grid = pts.reshape(1, 1, 1, -1, 3).flip(-1)
+    outs = []
+    for v in volumes:
+        if sample_mode == "grad":
+            o = F.grid_sample(v, grid, mode="bilinear", padding_mode="zeros", align_corners=True)
+        else:
+            o = F.grid_sample(v, grid, mode="nearest", padding_mode="zeros", align_corners=False)
+        outs.append(o.reshape(v.shape[1], -1).t())
+    return torch.cat(outs, -1)

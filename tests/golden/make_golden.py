@@ -107,7 +107,98 @@ def golden_volume():
           [float(out[f"mask{i}"].mean()) for i in range(len(dims))])
 
 
+RENDER_DIMS = [32, 16, 8, 4, 2]
+RENDER_HW = (96, 128)
+
+
+def render_inputs():
+    """Deterministic inputs of the render-half fixtures; tests rebuild them from the same seeds."""
+    from gens_b200.synthetic import make_reg_volumes
+    scene = make_scene(RENDER_HW[0], RENDER_HW[1], 3, seed=11)
+    volumes = make_reg_volumes(RENDER_DIMS, seed=11)
+    return scene, volumes
+
+
+def golden_render():
+    sys.path.insert(0, HERE)
+    import ref_shims
+    ref_shims.install()
+    import models.modules.implicit_surface as IS
+    import models.modules.projector as PJ
+    volume_mod = load_ref_module("models/modules/volume.py", "ref_volume")
+
+    torch.manual_seed(0)
+    surf = IS.ImplicitSurface(Conf(ref_shims.REF_CONF))
+    # random-init colour net is fine; nudge the variance so inv_s is the init value exp(3)
+    scene, volumes = render_inputs()
+    _, masks = volume_mod.Volume(Conf(volume_dims=RENDER_DIMS)).agg_mean_var(scene.features, scene.intrs, scene.c2ws)
+    out = {"mask_fill": np.array([float(m.mean()) for m in masks])}
+    for k, v in surf.state_dict().items():
+        out["sd/" + k] = v.numpy()
+    for i, m in enumerate(masks):
+        out[f"mask{i}"] = m[0, 0].numpy().astype(np.uint8)
+
+    rays_o, rays_d = scene.rays(step=8)
+    sel = torch.arange(0, rays_o.shape[0], 4)[:48]
+    rays_o, rays_d = rays_o[sel].contiguous(), rays_d[sel].contiguous()
+    out["rays_o"], out["rays_d"] = rays_o.numpy(), rays_d.numpy()
+
+    # ---- lookup_volume: nearest masks / trilinear features, points inside and outside the cube
+    g = torch.Generator().manual_seed(5)
+    pts = (torch.rand(4000, 3, generator=g) * 2.6 - 1.3)
+    pts[:8] = torch.tensor([[-1., -1, -1], [1, 1, 1], [0, 0, 0], [1, -1, 0.5], [-1.0001, 0, 0], [0.999999, 0.5, -0.5],
+                            [0.03125, 0.0625, -0.09375], [1.2, 1.2, 1.2]])
+    out["lv_pts"] = pts.numpy()
+    out["lv_nearest"] = PJ.lookup_volume(pts, masks, sample_mode="nearest").numpy()
+    out["lv_feat"] = PJ.lookup_volume(pts, volumes, sample_mode="grad").detach().numpy()
+
+    # ---- SDF network: value, gradient, second-order "smooth" on points along the rays
+    z = scene.near + (scene.far - scene.near) * torch.linspace(0, 1, 40)[None, :]
+    spts = (rays_o[:, None, :] + rays_d[:, None, :] * z[..., None]).reshape(-1, 3)
+    out["sdf_pts"] = spts.numpy()
+    out["sdf_out"] = surf.sdf_network(spts, volumes).detach().numpy()
+    gr, sm = surf.sdf_network.gradient(spts.clone(), volumes)
+    out["sdf_grad"], out["sdf_smooth"] = gr.detach().numpy(), sm.detach().numpy()
+
+    # ---- lookup_feature + colour network
+    fv, rd, mk = PJ.lookup_feature(spts, scene.imgs, scene.intrs, scene.c2ws, scene.features)
+    out["lf_feat"], out["lf_raydiff"], out["lf_mask"] = fv.detach().numpy(), rd.numpy(), mk.numpy()
+    out["color"] = surf.color_network(fv, rd, mk).detach().numpy()
+
+    # ---- full render (perturb = 0); the 1024 random "sparse" points come from the global RNG
+    captured = {}
+    real_core = surf.render_core
+
+    def spy(rays_o_, rays_d_, z_vals, *a, **k):
+        captured["z_vals"] = z_vals.detach().clone()
+        return real_core(rays_o_, rays_d_, z_vals, *a, **k)
+
+    surf.render_core = spy
+    torch.manual_seed(123)
+    res = surf.render(rays_o, rays_d, scene.near, scene.far, volumes, masks, scene.imgs, scene.features,
+                      scene.features, scene.intrs, scene.c2ws, 1.0, None)
+    out["z_vals"] = captured["z_vals"].numpy()
+    for k, v in res.items():
+        out["render/" + k] = v.detach().numpy()
+    # coarse stage pieces for unit tests of up_sample / sample_pdf
+    with torch.no_grad():
+        z64 = scene.near + (scene.far - scene.near) * torch.linspace(0, 1, 64)[None, :]
+        z64 = z64.repeat(rays_o.shape[0], 1)
+        p64 = (rays_o[:, None, :] + rays_d[:, None, :] * z64[..., None]).reshape(-1, 3)
+        m64 = PJ.lookup_volume(p64, masks, sample_mode="nearest").any(dim=-1)
+        sdf64 = torch.ones(p64.shape[0], 1) * 100
+        sdf64[m64] = surf.sdf_network.sdf(p64[m64], volumes)
+        sdf64 = sdf64.reshape(-1, 64)
+        new_z = surf.up_sample(rays_o, rays_d, z64, sdf64, 16, masks, 64)
+    out["up_z64"], out["up_sdf64"], out["up_new_z"] = z64.numpy(), sdf64.numpy(), new_z.numpy()
+    np.savez_compressed(os.path.join(HERE, "render.npz"), **out)
+    print("render.npz written; mask fill", out["mask_fill"], "valid rays", int(res["valid_mask"].sum()),
+          "of", rays_o.shape[0], "weight_sum mean", float(res["weight_sum"].mean()))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["volume"]
+    which = sys.argv[1:] or ["volume", "render"]
     if "volume" in which:
         golden_volume()
+    if "render" in which:
+        golden_render()

@@ -68,3 +68,32 @@ def test_div_recip_differs_only_in_last_bit(golden_dir):
     _, _, _, _, vm0 = c_oracle.volume_agg(g["feat0"], w2c, g["intrs"], grid, debug=True, div_mode=c_oracle.DIV_TRUE)
     _, _, _, _, vm1 = c_oracle.volume_agg(g["feat0"], w2c, g["intrs"], grid, debug=True, div_mode=c_oracle.DIV_RECIP)
     assert (vm0 != vm1).mean() < 1e-4
+
+
+def _render_golden(golden_dir):
+    return np.load(f"{golden_dir}/render.npz")
+
+
+def _render_volumes():
+    from gens_b200.synthetic import make_reg_volumes
+    return make_reg_volumes([32, 16, 8, 4, 2], seed=11)
+
+
+def test_oracle_lookup_volume_matches_reference(golden_dir):
+    """Nearest mask look-ups: bit-exact.  Trilinear features: 1e-6 + 1e-5*|ref| (observed ~1e-7)."""
+    g = _render_golden(golden_dir)
+    pts = g["lv_pts"]
+    vols = _render_volumes()
+    for i in range(5):
+        got = c_oracle.nearest(pts, g[f"mask{i}"].astype(np.float32), fused=0)
+        assert np.array_equal(got, g["lv_nearest"][:, i])
+        feat = c_oracle.trilinear(pts, vols[i][0].numpy())
+        ref = g["lv_feat"][:, 4 * i:4 * i + 4]
+        assert np.all(np.abs(feat - ref) <= 1e-6 + 1e-5 * np.abs(ref))
+    tf = torch_oracle.lookup_volume(torch.from_numpy(pts), vols).numpy()
+    assert np.all(np.abs(tf - g["lv_feat"]) <= 1e-6 + 1e-5 * np.abs(g["lv_feat"]))
+    tn = torch_oracle.lookup_volume(torch.from_numpy(pts), [torch.from_numpy(g[f"mask{i}"].astype(np.float32))[None, None]
+                                                            for i in range(5)], "nearest").numpy()
+    assert np.array_equal(tn, g["lv_nearest"])
+    dd = torch.cat([torch_oracle.trilinear_dd(v, torch.from_numpy(pts)) for v in vols], -1).numpy()
+    assert np.all(np.abs(dd - g["lv_feat"]) <= 1e-6 + 1e-5 * np.abs(g["lv_feat"]))
