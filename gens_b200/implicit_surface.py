@@ -1,0 +1,344 @@
+"""NeuS-style ray marching through the multi-scale volumes -- drop-in for the reference's
+models/modules/implicit_surface.py (ImplicitSurface :47-499, sample_pdf :14-44).
+
+Same constructor keys, method names, argument order and output dictionary as the reference, so
+models/gens.py and runner.py call it unchanged.  Differences are confined to HOW the work is
+issued: every volume look-up is one fused multi-scale launch, nothing is compacted with boolean
+indexing (no `nonzero` host syncs -- masked points are evaluated and overwritten instead), the
+up-sampling loop runs on folded weights without autograd, and `validate` can march far more than
+256 rays per call.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .networks import BlendingNetwork, SDFNetwork, SingleVarianceNetwork
+from .projector import lookup_feature, lookup_volume, mask_nearest, surface_patch_warp
+
+FAR_SDF = 100.0  # value the reference assigns to samples outside every mask volume
+
+
+def sample_pdf(bins, weights, n_samples, det=False):
+    """Inverse-CDF sampling (NeRF), reference implicit_surface.py:14-44.  bins (B,M), weights (B,M-1)."""
+    w = weights + 1e-5
+    pdf = w / w.sum(-1, keepdim=True)
+    cdf = F.pad(torch.cumsum(pdf, -1), (1, 0))
+    if det:
+        u = torch.linspace(0.5 / n_samples, 1.0 - 0.5 / n_samples, steps=n_samples).type_as(w)
+        u = u.expand(cdf.shape[0], n_samples).contiguous()
+    else:
+        u = torch.rand(cdf.shape[0], n_samples).type_as(w)
+    hi = torch.searchsorted(cdf, u, right=True)
+    lo = (hi - 1).clamp(min=0)
+    hi = hi.clamp(max=cdf.shape[-1] - 1)
+    c_lo, c_hi = cdf.gather(1, lo), cdf.gather(1, hi)
+    b_lo, b_hi = bins.gather(1, lo), bins.gather(1, hi)
+    den = c_hi - c_lo
+    den = torch.where(den < 1e-5, torch.ones_like(den), den)
+    return b_lo + (u - c_lo) / den * (b_hi - b_lo)
+
+
+def _valid_or_first10(mask: torch.Tensor) -> torch.Tensor:
+    """The reference evaluates the first 10 points when a batch has no valid point at all
+    (implicit_surface.py:123-124, :176-177, :372-373); done on the device, without a sync."""
+    flat = mask.reshape(-1)
+    none = ~flat.any()
+    first = torch.arange(flat.numel(), device=flat.device) < 10
+    return (flat | (first & none)).reshape(mask.shape)
+
+
+def neus_weights(alpha: torch.Tensor) -> torch.Tensor:
+    """w_j = alpha_j * prod_{k<j} (1 - alpha_k + 1e-7)."""
+    trans = torch.cumprod(F.pad(1.0 - alpha + 1e-7, (1, 0), value=1.0), -1)[:, :-1]
+    return alpha * trans
+
+
+class ImplicitSurface(nn.Module):
+    def __init__(self, confs):
+        super().__init__()
+        self.n_samples = confs.get_int("render.n_samples")
+        self.n_importance = confs.get_int("render.n_importance")
+        self.up_sample_steps = confs.get_int("render.up_sample_steps")
+        self.perturb = confs.get_float("render.perturb")
+        self.sdf_network = SDFNetwork(**confs["sdf_network"])
+        self.color_network = BlendingNetwork(**confs["color_network"])
+        self.deviation_network = SingleVarianceNetwork(**confs["variance_network"])
+        self.val_chunk = 256  # rays per render() call in validate(); 256 = the reference's split
+
+    # ------------------------------------------------------------------ hierarchical sampling
+    def _sdf_masked(self, pts, volumes, mask_volumes, folded=None):
+        """SDF at (n,3) points, FAR_SDF outside the mask volumes (no gradient)."""
+        valid = _valid_or_first10(mask_nearest(pts, mask_volumes))
+        sdf = self.sdf_network.sdf_nograd(pts, volumes, folded)
+        return torch.where(valid[:, None], sdf, torch.full_like(sdf, FAR_SDF))
+
+    def up_sample(self, rays_o, rays_d, z_vals, sdf, n_importance, mask_volumes, inv_s):
+        """n_importance new depths per ray from the NeuS weights at a fixed inv_s (reference :60-109)."""
+        b, m = z_vals.shape
+        pts = rays_o[:, None, :] + rays_d[:, None, :] * z_vals[..., :, None]
+        valid = mask_nearest(pts.reshape(-1, 3), mask_volumes).reshape(b, m)
+        both = valid[:, :-1] & valid[:, 1:]
+        radius = torch.linalg.norm(pts, ord=2, dim=-1)
+        inside = ((radius[:, :-1] < 1.0) | (radius[:, 1:] < 1.0)) & both
+        sdf = sdf.reshape(b, m)
+        s0, s1, z0, z1 = sdf[:, :-1], sdf[:, 1:], z_vals[:, :-1], z_vals[:, 1:]
+        mid = (s0 + s1) * 0.5
+        slope = (s1 - s0) / (z1 - z0 + 1e-5)
+        slope = torch.minimum(F.pad(slope[:, :-1], (1, 0)), slope)  # min(previous section, this section)
+        slope = slope.clip(-1e3, 0.0) * inside
+        dist = z1 - z0
+        cdf_prev = torch.sigmoid((mid - slope * dist * 0.5) * inv_s)
+        cdf_next = torch.sigmoid((mid + slope * dist * 0.5) * inv_s)
+        alpha = (cdf_prev - cdf_next + 1e-5) / (cdf_prev + 1e-5)
+        return sample_pdf(z_vals, neus_weights(alpha), n_importance, det=True).detach()
+
+    def cat_z_vals(self, rays_o, rays_d, z_vals, new_z_vals, sdf, volumes, mask_volumes, last=False):
+        """Merge the new depths into the sorted ray (reference :111-133)."""
+        b = z_vals.shape[0]
+        z_all, order = torch.sort(torch.cat([z_vals, new_z_vals], dim=-1), dim=-1)
+        if not last:
+            pts = (rays_o[:, None, :] + rays_d[:, None, :] * new_z_vals[..., :, None]).reshape(-1, 3)
+            new_sdf = self._sdf_masked(pts, volumes, mask_volumes, getattr(self, "_folded", None)).reshape(b, -1)
+            sdf = torch.cat([sdf, new_sdf], dim=-1).gather(1, order)
+        return z_all, sdf
+
+    def tv_regularization(self, volume_feat_cas, volume_mask_cas=None):
+        """Masked total variation over the pyramid (reference :135-150, incl. its mx.sum() normaliser
+        for all three axes)."""
+        if volume_mask_cas is None:
+            volume_mask_cas = [torch.ones_like(v[:, :1]) for v in volume_feat_cas]
+        total = 0
+        for i, (vol, msk) in enumerate(zip(volume_feat_cas, volume_mask_cas)):
+            mx = (msk[:, :, 1:] * msk[:, :, :-1]) > 0
+            my = (msk[:, :, :, 1:] * msk[:, :, :, :-1]) > 0
+            mz = (msk[..., 1:] * msk[..., :-1]) > 0
+            norm = mx.sum() + 1e-8
+            tx = ((vol[:, :, 1:] - vol[:, :, :-1]) ** 2 * mx).sum() / norm
+            ty = ((vol[:, :, :, 1:] - vol[:, :, :, :-1]) ** 2 * my).sum() / norm
+            tz = ((vol[..., 1:] - vol[..., :-1]) ** 2 * mz).sum() / norm
+            total = total + torch.sqrt(tx + ty + tz) * 0.5 ** i
+        return total
+
+    # ------------------------------------------------------------------------------ rendering
+    def render_core(self, rays_o, rays_d, z_vals, sample_dist, volumes, mask_volumes, features, match_features,
+                    imgs, intrs, c2ws, cos_anneal_ratio, step):
+        """Composite one batch of rays (reference :152-349); returns the same 18 keys."""
+        b, n = z_vals.shape
+        dists = torch.cat([z_vals[:, 1:] - z_vals[:, :-1], z_vals.new_full((b, 1), sample_dist)], -1)
+        mid_z = z_vals + dists * 0.5
+        pts = (rays_o[:, None, :] + rays_d[:, None, :] * mid_z[..., :, None]).reshape(-1, 3)
+        dirs = rays_d[:, None, :].expand(b, n, 3).reshape(-1, 3)
+
+        voxel_mask = mask_nearest(pts, mask_volumes)  # (b*n,) bool, before the 10-point fallback
+        evaluated = _valid_or_first10(voxel_mask)
+        ev = evaluated[:, None]
+        vm = voxel_mask.reshape(b, n).float()
+
+        # SDF value, gradient and second-order smoothness term on every sample, masked afterwards
+        sdf_out = self.sdf_network(pts, volumes)
+        sdf = torch.where(ev, sdf_out[:, :1], torch.full_like(sdf_out[:, :1], FAR_SDF))
+        grad_all, smooth_all = self.sdf_network.gradient(pts.clone(), volumes)
+        gradients = torch.where(ev, grad_all, torch.zeros_like(grad_all))
+        smooth = torch.where(ev, smooth_all, torch.zeros_like(smooth_all))
+
+        # source-view colours
+        feat_views, ray_diff, mask_views = lookup_feature(pts, imgs, intrs, c2ws, features)
+        mask_views = mask_views & ev
+        colour = self.color_network(feat_views, ray_diff, mask_views)
+        colour = torch.where(ev, colour, torch.zeros_like(colour)).reshape(b, n, 3)
+        visible = (mask_views.reshape(b, n, -1).float().sum(dim=2) > 1).float()
+        valid_mask = visible.sum(dim=1, keepdim=True) > 8
+
+        inv_s = self.deviation_network(torch.zeros([1, 3]).type_as(rays_o))[:, :1].clip(1e-6, 1e6)
+        inv_s = inv_s.expand(b * n, 1)
+        true_cos = (dirs * gradients).sum(-1, keepdim=True)
+        iter_cos = -(F.relu(-true_cos * 0.5 + 0.5) * (1.0 - cos_anneal_ratio) + F.relu(-true_cos) * cos_anneal_ratio)
+        iter_cos = iter_cos * vm.reshape(-1, 1)
+        half = iter_cos.clip(-10.0, 10.0) * dists.reshape(-1, 1) * 0.5
+        cdf_prev = torch.sigmoid((sdf - half) * inv_s)
+        cdf_next = torch.sigmoid((sdf + half) * inv_s)
+        alpha = ((cdf_prev - cdf_next + 1e-5) / (cdf_prev + 1e-5)).reshape(b, n).clip(0.0, 1.0) * vm
+
+        pts_norm = torch.linalg.norm(pts, ord=2, dim=-1).reshape(b, n)
+        inside_sphere = (pts_norm < 1.0).float().detach() * vm
+        relax_inside_sphere = (pts_norm < 1.2).float().detach() * vm
+
+        weights = neus_weights(alpha)
+        weights_sum = weights.sum(dim=-1, keepdim=True)
+        color = (colour * weights[:, :, None]).sum(dim=1)
+        grads_bn = gradients.reshape(b, n, 3)
+        rot = torch.inverse(c2ws[0, :3, :3])
+        normal = (grads_bn * weights[:, :, None]).sum(dim=1) @ rot.t()
+        cam_rays_d = rays_d @ rot.t()
+        render_depth = (mid_z * weights).sum(dim=1) * cam_rays_d[:, 2]
+
+        gradient_error = (torch.linalg.norm(grads_bn, ord=2, dim=-1) - 1.0) ** 2
+        gradient_error = (relax_inside_sphere * gradient_error).sum() / (relax_inside_sphere.sum() + 1e-5)
+        smooth_pt = (smooth.reshape(b, n, 3) * weights[:, :, None].detach() * inside_sphere[:, :, None]).sum(dim=1)
+        smooth_error = torch.linalg.norm(smooth_pt, ord=2, dim=-1).abs().mean()
+
+        pts_random = torch.rand([1024, 3]).type_as(rays_o) * 2 - 1
+        sdf_random = self.sdf_network.sdf(pts_random, volumes)
+        tv_reg = self.tv_regularization(volumes, mask_volumes)
+
+        # first SDF zero crossing along the ray, linearly interpolated depth
+        sdf_d = sdf.reshape(b, n)
+        s0, s1 = sdf_d[:, :-1], sdf_d[:, 1:]
+        pair_valid = ((vm[:, :-1] * vm[:, 1:]) > 0).float()
+        crossing = (s0 * s1 <= 0).float()
+        rank = torch.arange(n - 1, 0, -1, device=sdf.device, dtype=sdf.dtype)  # n-1 ... 1: earliest wins
+        score = crossing * rank[None, :] * pair_valid
+        j0 = torch.argmax(score, 1, keepdim=True)
+        j1 = j0 + 1
+        mid_inside = (0.5 * (inside_sphere.gather(1, j0) + inside_sphere.gather(1, j1)) > 0.5).float()
+        mid_inside = mid_inside * (score.sum(dim=1, keepdim=True) > 0).float()
+        gd = grads_bn.detach()
+        g0 = gd.gather(1, j0.unsqueeze(-1).expand(-1, -1, 3))
+        g1 = gd.gather(1, j1.unsqueeze(-1).expand(-1, -1, 3))
+        cos_d = (g0 * g1).sum(dim=-1) / (torch.linalg.norm(g0, ord=2, dim=-1) * torch.linalg.norm(g1, ord=2, dim=-1)
+                                          + 1e-8)
+        mid_inside = mid_inside * (cos_d > 0.5)
+        sa, sb = sdf_d.gather(1, j0), sdf_d.gather(1, j1)
+        za, zb = mid_z.gather(1, j0), mid_z.gather(1, j1)
+        z_sdf0 = (sa * zb - sb * za) / (sa - sb + 1e-10)
+        sdf_depth = z_sdf0 * cam_rays_d[:, 2:3] * mid_inside
+        z_sdf0 = torch.where(z_sdf0 < 0, torch.zeros_like(z_sdf0), z_sdf0)
+        z_sdf0 = torch.where(z_sdf0 > torch.max(z_vals), torch.zeros_like(z_sdf0), z_sdf0)
+        pts_sdf0 = rays_o[:, None, :] + rays_d[:, None, :] * z_sdf0[..., :, None]
+        g_sdf0, _ = self.sdf_network.gradient(pts_sdf0.reshape(-1, 3), volumes)
+        g_sdf0 = g_sdf0.reshape(b, 1, 3)
+        g_norm = torch.linalg.norm(g_sdf0, ord=2, dim=-1, keepdim=True)
+        g_norm = torch.where(g_norm <= 0, torch.ones_like(g_norm) * 1e-8, g_norm)
+        g_sdf0 = ((g_sdf0 / g_norm) @ c2ws[0, :3, :3]).detach()  # normal in the reference camera frame
+
+        src = features if (step is None or step < 5) else match_features
+        f0 = src[0].detach()
+        ups = [F.interpolate(src[k].detach(), size=f0.shape[-2:], mode="bilinear") for k in (1, 2)]
+        warp_feats = torch.cat([f0] + ups, dim=1).detach()
+        ref_gray_val, sampled_gray_val = surface_patch_warp(pts_sdf0, g_sdf0, warp_feats, intrs, c2ws)
+
+        return {
+            'ref_gray_val': ref_gray_val,
+            'sampled_gray_val': sampled_gray_val,
+            'mid_inside_sphere': mid_inside,
+            'smooth_error': smooth_error,
+            'tv_reg': tv_reg,
+            'color_fine': color,
+            'render_depth': render_depth,
+            'valid_mask': valid_mask,
+            'sparse_sdf': torch.cat([sdf_random, sdf]),
+            'gradients': grads_bn,
+            'normal': normal,
+            's_val': 1.0 / inv_s,
+            'weights': weights,
+            'weight_sum': weights_sum,
+            'weight_max': torch.max(weights, dim=-1, keepdim=True)[0],
+            'gradient_error': gradient_error,
+            'inside_sphere': inside_sphere,
+            'sdf_depth': sdf_depth,
+        }
+
+    def render(self, rays_o, rays_d, near, far, volumes, mask_volumes, imgs, features, match_features, intrs, c2ws,
+               cos_anneal_ratio, step):
+        """64 uniform + 4x16 importance samples per ray, then render_core (reference :351-405)."""
+        b = len(rays_o)
+        near, far = near.repeat(b, 1), far.repeat(b, 1)
+        sample_dist = 2.0 / self.n_samples
+        z_vals = near + (far - near) * torch.linspace(0.0, 1.0, self.n_samples).type_as(near)[None, :]
+        if self.perturb > 0:
+            t_rand = (torch.rand([b, 1]) - 0.5).type_as(z_vals)
+            z_vals = z_vals + t_rand * 2.0 / self.n_samples
+        if self.n_importance > 0:
+            with torch.no_grad():
+                self._folded = self.sdf_network.folded_weights()
+                try:
+                    pts = (rays_o[:, None, :] + rays_d[:, None, :] * z_vals[..., :, None]).reshape(-1, 3)
+                    sdf = self._sdf_masked(pts, volumes, mask_volumes, self._folded).reshape(b, self.n_samples)
+                    per_step = self.n_importance // self.up_sample_steps
+                    for i in range(self.up_sample_steps):
+                        new_z = self.up_sample(rays_o, rays_d, z_vals, sdf, per_step, mask_volumes, 64 * 2 ** i)
+                        z_vals, sdf = self.cat_z_vals(rays_o, rays_d, z_vals, new_z, sdf, volumes, mask_volumes,
+                                                      last=(i + 1 == self.up_sample_steps))
+                finally:
+                    self._folded = None
+        return self.render_core(rays_o, rays_d, z_vals, sample_dist, volumes, mask_volumes, features, match_features,
+                                imgs, intrs, c2ws, cos_anneal_ratio=cos_anneal_ratio, step=step)
+
+    # ---------------------------------------------------------------------- geometry / driver
+    @torch.no_grad()
+    def sdf_grid(self, volumes, bound_min, bound_max, resolution, block: int = 128, out=None):
+        """u[x,y,z] = -sdf on a resolution^3 lattice (the loop of reference :407-421), evaluated in
+        `block`^3 chunks that stay on the device; returns a float32 CUDA tensor."""
+        dev = bound_min.device
+        axes = [torch.linspace(float(bound_min[k]), float(bound_max[k]), resolution, device=dev) for k in range(3)]
+        u = torch.empty((resolution,) * 3, device=dev, dtype=torch.float32) if out is None else out
+        folded = self.sdf_network.folded_weights()
+        for x0 in range(0, resolution, block):
+            for y0 in range(0, resolution, block):
+                for z0 in range(0, resolution, block):
+                    xs, ys, zs = axes[0][x0:x0 + block], axes[1][y0:y0 + block], axes[2][z0:z0 + block]
+                    pts = torch.stack(torch.meshgrid(xs, ys, zs, indexing="ij"), -1).reshape(-1, 3)
+                    val = self.sdf_network.sdf_nograd(pts, volumes, folded).reshape(len(xs), len(ys), len(zs))
+                    u[x0:x0 + len(xs), y0:y0 + len(ys), z0:z0 + len(zs)] = -val
+        return u
+
+    def extract_geometry(self, volumes, bound_min, bound_max, resolution, threshold):
+        """Marching cubes on the SDF lattice (reference :407-427); needs the `mcubes` package."""
+        import mcubes
+        u = self.sdf_grid(volumes, bound_min, bound_max, resolution).cpu().numpy()
+        vertices, triangles = mcubes.marching_cubes(u, threshold)
+        b_max, b_min = bound_max.detach().cpu().numpy(), bound_min.detach().cpu().numpy()
+        vertices = vertices / (resolution - 1.0) * (b_max - b_min)[None, :] + b_min[None, :]
+        return vertices, triangles
+
+    def validate(self, rays_o, rays_d, near, far, volumes, mask_volumes, imgs, features, match_features, intrs, c2ws,
+                 bound_min, bound_max, hw, cos_anneal_ratio=1.0, step=None, extract_geometry=True,
+                 mesh_resolution=512, threshold=0.0):
+        """Full-image render in chunks + optional mesh (reference :429-470).  Per-chunk results stay on
+        the device and are copied to the host once."""
+        outputs = {}
+        if extract_geometry:
+            vertices, triangles = self.extract_geometry(volumes, bound_min, bound_max, mesh_resolution, threshold)
+            outputs["vertices"], outputs["triangles"] = vertices, triangles
+        height, width = hw
+        rgb, nrm, sdepth, rdepth = [], [], [], []
+        for ro, rd in zip(rays_o.split(self.val_chunk), rays_d.split(self.val_chunk)):
+            res = self.render(ro, rd, near, far, volumes, mask_volumes, imgs, features, match_features, intrs, c2ws,
+                              cos_anneal_ratio, step)
+            rgb.append(res['color_fine'].detach())
+            n = res['gradients'] * res['weights'][:, :res['gradients'].shape[1], None] * res['inside_sphere'][..., None]
+            nrm.append(n.sum(dim=1).detach())
+            sdepth.append(res['sdf_depth'].detach())
+            rdepth.append(res['render_depth'].detach())
+        color_fine = torch.cat(rgb, dim=0).cpu()
+        normal_img = torch.cat(nrm, dim=0).cpu().numpy()
+        rot = np.linalg.inv(c2ws[0, :3, :3].detach().cpu().numpy())
+        outputs["color_fine"] = color_fine
+        outputs["img_fine"] = (color_fine.numpy().reshape([height, width, 3]) * 256).clip(0, 255)
+        outputs["normal_img"] = (np.matmul(rot[None, :, :], normal_img[:, :, None]).reshape([height, width, 3]) * 128
+                                 + 128).clip(0, 255)
+        outputs["sdf_depth"] = torch.cat(sdepth, dim=0).cpu().numpy().reshape([height, width])
+        outputs["render_depth"] = torch.cat(rdepth, dim=0).cpu().numpy().reshape([height, width])
+        return outputs
+
+    def forward(self, mode, ipts, volumes, mask_volumes, features, match_features, cos_anneal_ratio=1.0, step=None):
+        imgs, intrs, c2ws = ipts["imgs"], ipts["intrs"], ipts["c2ws"]
+        rays_o, rays_d, near, far = ipts["rays_o"], ipts["rays_d"], ipts["near"], ipts["far"]
+        if mode == "val":
+            outputs = self.validate(rays_o, rays_d, near, far, volumes, mask_volumes, imgs, features, match_features,
+                                    intrs, c2ws, ipts["bound_min"], ipts["bound_max"], ipts["hw"], cos_anneal_ratio,
+                                    step)
+        else:
+            outputs = self.render(rays_o, rays_d, near, far, volumes, mask_volumes, imgs, features, match_features,
+                                  intrs, c2ws, cos_anneal_ratio, step)
+        if "pseudo_pts" in ipts:
+            pseudo_pts = ipts["pseudo_pts"]
+            valid = mask_nearest(pseudo_pts, mask_volumes)
+            if not bool(valid.any()):
+                raise RuntimeError("No valid pseudo pts!")
+            sdf = self.sdf_network.sdf(pseudo_pts, volumes)
+            outputs["pseudo_sdf"] = torch.where(valid[:, None], sdf, torch.zeros_like(sdf))
+        return outputs

@@ -1,0 +1,226 @@
+"""The small MLPs on the ray-marching path, state_dict-compatible with the reference so its
+checkpoints load unchanged:
+
+  SDFNetwork             reference models/modules/sdf_network.py:28-153   (keys lin{l}.weight_g/weight_v/bias)
+  BlendingNetwork        reference models/modules/blending_network.py:22-117
+  SingleVarianceNetwork  reference models/modules/variance_network.py:5-11
+
+The dense layers stay on cuBLAS (plain library GEMMs, fp32: the 1e-4 parity budget rules out TF32);
+what changes is everything around them -- the multi-scale volume look-up is one fused launch
+(projector.lookup_volume) and the inference path (`SDFNetwork.sdf_nograd`) folds the weight
+normalisation once per call and never concatenates activations with the encoded features.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .projector import lookup_volume
+
+
+def positional_encoding(x: torch.Tensor, n_freqs: int) -> torch.Tensor:
+    """[x, sin(2^0 x), cos(2^0 x), ..., sin(2^(L-1) x), cos(2^(L-1) x)] (embedder.py:11-36)."""
+    if n_freqs <= 0:
+        return x
+    parts = [x]
+    for k in range(n_freqs):
+        f = float(2.0 ** k)
+        parts.append(torch.sin(x * f))
+        parts.append(torch.cos(x * f))
+    return torch.cat(parts, dim=-1)
+
+
+def encoded_width(d: int, n_freqs: int) -> int:
+    return d * (1 + 2 * n_freqs) if n_freqs > 0 else d
+
+
+class SDFNetwork(nn.Module):
+    def __init__(self, d_in, d_out, d_hidden, n_layers, skip_in=(4,), multires=0, bias=0.5, scale=1,
+                 geometric_init=True, weight_norm=True, inside_outside=False, feat_channels=32, feat_multires=2):
+        super().__init__()
+        self.multires, self.feat_multires = int(multires), int(feat_multires)
+        self.init_feat_channels = feat_channels
+        self.scale = scale
+        self.skip_in = tuple(skip_in)
+        pe_in = encoded_width(d_in, self.multires)
+        pe_feat = encoded_width(feat_channels, self.feat_multires)
+        self.pe_in, self.pe_feat = pe_in, pe_feat
+        widths = [pe_in] + [d_hidden + pe_feat] * n_layers + [d_out]
+        self.num_layers = len(widths)
+        last = self.num_layers - 2
+        for l in range(self.num_layers - 1):
+            fan_out = widths[l + 1] - (widths[0] if (l + 1) in self.skip_in else 0)
+            if l < last:
+                fan_out -= pe_feat  # the encoded features are re-attached in front of every hidden layer
+            lin = nn.Linear(widths[l], fan_out)
+            if geometric_init:
+                self._geometric_init(lin, l, last, widths, fan_out, bias, inside_outside, pe_feat)
+            if weight_norm:
+                lin = nn.utils.weight_norm(lin)
+            setattr(self, f"lin{l}", lin)
+        self.activation = nn.Softplus(beta=100)
+
+    def _geometric_init(self, lin, l, last, widths, fan_out, bias, inside_outside, pe_feat):
+        """Sphere initialisation of IDR/NeuS as the reference applies it (sdf_network.py:63-88): the
+        columns fed by positional-encoding terms and by the volume features start at zero."""
+        with torch.no_grad():
+            if l == last:
+                sign = -1.0 if inside_outside else 1.0
+                nn.init.normal_(lin.weight, mean=sign * math.sqrt(math.pi) / math.sqrt(widths[l]), std=1e-4)
+                nn.init.constant_(lin.bias, -sign * bias)
+                lin.weight[:, -pe_feat:] = 0.0
+                lin.bias[-pe_feat:] = 0.0
+                return
+            nn.init.constant_(lin.bias, 0.0)
+            std = math.sqrt(2) / math.sqrt(fan_out)
+            if self.multires > 0 and l == 0:
+                lin.weight.zero_()
+                nn.init.normal_(lin.weight[:, :3], 0.0, std)
+            elif self.multires > 0 and l in self.skip_in:
+                nn.init.normal_(lin.weight, 0.0, std)
+                lin.weight[:, -(widths[0] - 3 + pe_feat):] = 0.0
+            else:
+                nn.init.normal_(lin.weight, 0.0, std)
+                lin.weight[:, -pe_feat:] = 0.0
+
+    # -- reference-shaped path (autograd at op granularity; training and .gradient) -------------
+    def forward(self, inputs, volumes):
+        feats = positional_encoding(lookup_volume(inputs.clone(), volumes), self.feat_multires)
+        pos = positional_encoding(inputs * self.scale, self.multires)
+        x = pos
+        for l in range(self.num_layers - 1):
+            if l in self.skip_in:
+                x = torch.cat([x, pos], -1) / math.sqrt(2)
+            if 0 < l < self.num_layers - 1:
+                x = torch.cat([x, feats], -1)
+            x = getattr(self, f"lin{l}")(x)
+            if l < self.num_layers - 2:
+                x = self.activation(x)
+        return torch.cat([x[:, :1] / self.scale, x[:, 1:]], dim=-1)
+
+    def sdf(self, x, volumes):
+        return self.forward(x, volumes)[:, :1]
+
+    def sdf_hidden_appearance(self, x, volumes):
+        return self.forward(x, volumes)
+
+    @torch.enable_grad()
+    def gradient(self, x, volumes):
+        """(grad sdf, d/dx sum_k grad_k) with the graph kept, as sdf_network.py:131-153."""
+        x.requires_grad_(True)
+        y = self.sdf(x, volumes)
+        (g,) = torch.autograd.grad(y, x, torch.ones_like(y), create_graph=True, retain_graph=True)
+        (h,) = torch.autograd.grad(g, x, torch.ones_like(g), create_graph=True, retain_graph=True)
+        return g, h
+
+    # -- inference path ---------------------------------------------------------------------------
+    def folded_weights(self):
+        """Effective (weight, bias) per layer with the weight normalisation folded in."""
+        out = []
+        for l in range(self.num_layers - 1):
+            lin = getattr(self, f"lin{l}")
+            if hasattr(lin, "weight_g"):
+                w = torch._weight_norm(lin.weight_v, lin.weight_g, 0)
+            else:
+                w = lin.weight
+            out.append((w, lin.bias))
+        return out
+
+    @torch.no_grad()
+    def sdf_nograd(self, pts, volumes, folded=None):
+        """SDF values (n,1) without autograd bookkeeping: same arithmetic as forward()[:, :1], but the
+        encoded volume features enter every layer through ONE (n,100)x(100,sum fan_out) GEMM instead of
+        six concatenations, and only column 0 of the output layer is evaluated."""
+        folded = self.folded_weights() if folded is None else folded
+        feats = positional_encoding(lookup_volume(pts, volumes), self.feat_multires)
+        pos = positional_encoding(pts * self.scale, self.multires)
+        last = self.num_layers - 2
+        # feature columns of layers 1..last, stacked
+        wf = torch.cat([folded[l][0][: (1 if l == last else None), -self.pe_feat:] for l in range(1, last + 1)], 0)
+        feat_part = feats @ wf.t()
+        off = 0
+        x = F.softplus(F.linear(pos, folded[0][0], folded[0][1]), beta=100)
+        for l in range(1, last + 1):
+            w, b = folded[l]
+            rows = 1 if l == last else w.shape[0]
+            if l in self.skip_in:
+                x = torch.cat([x, pos], -1) / math.sqrt(2)
+            y = torch.addmm(feat_part[:, off:off + rows] + b[:rows], x, w[:rows, : x.shape[1]].t())
+            off += rows
+            x = y if l == last else F.softplus(y, beta=100)
+        return x / self.scale
+
+
+def _elu_mlp(sizes: Sequence[int], final_act: bool = True, sigmoid: bool = False) -> nn.Sequential:
+    """Linear/ELU stack whose module indices match the reference's nn.Sequential layouts."""
+    layers: List[nn.Module] = []
+    for i in range(len(sizes) - 1):
+        layers.append(nn.Linear(sizes[i], sizes[i + 1]))
+        if i < len(sizes) - 2 or final_act:
+            layers.append(nn.ELU(inplace=True))
+    if sigmoid:
+        layers.append(nn.Sigmoid())
+    return nn.Sequential(*layers)
+
+
+def _kaiming(m):
+    if isinstance(m, nn.Linear):
+        nn.init.kaiming_normal_(m.weight.data)
+        if m.bias is not None:
+            nn.init.zeros_(m.bias.data)
+
+
+class BlendingNetwork(nn.Module):
+    """IBRNet-style colour blending over the source views (blending_network.py:22-117)."""
+
+    def __init__(self, d_feature=16, anti_alias_pooling=True):
+        super().__init__()
+        self.anti_alias_pooling = anti_alias_pooling
+        if anti_alias_pooling:
+            self.s = nn.Parameter(torch.tensor(0.2), requires_grad=True)
+        c = d_feature + 3
+        self.ray_dir_fc = _elu_mlp([4, 16, c])
+        self.base_fc = _elu_mlp([3 * c, 64, 32])
+        self.vis_fc = _elu_mlp([32, 32, 33])
+        self.vis_fc2 = _elu_mlp([32, 32, 1], final_act=False, sigmoid=True)
+        self.rgb_fc = _elu_mlp([32 + 1 + 4, 16, 8, 1], final_act=False)
+        for net in (self.base_fc, self.vis_fc2, self.vis_fc, self.rgb_fc):
+            net.apply(_kaiming)
+
+    def forward(self, rgb_feat, ray_diff, mask):
+        """rgb_feat (n,ns,3+c), ray_diff (n,ns,4), mask (n,ns) -> rgb (n,3)."""
+        m = mask[:, :, None]
+        ns = rgb_feat.shape[1]
+        rgb_in = rgb_feat[..., :3]
+        feat = rgb_feat + self.ray_dir_fc(ray_diff)
+        if self.anti_alias_pooling:
+            dot = ray_diff[..., 3:4]
+            e = torch.exp(torch.abs(self.s) * (dot - 1))
+            w = (e - e.min(dim=1, keepdim=True)[0]) * m
+            w = w / (w.sum(dim=1, keepdim=True) + 1e-8)
+        else:
+            w = m / (m.sum(dim=1, keepdim=True) + 1e-8)
+        mean = (feat * w).sum(dim=1, keepdim=True)
+        var = (w * (feat - mean) ** 2).sum(dim=1, keepdim=True)
+        x = torch.cat([torch.cat([mean, var], -1).expand(-1, ns, -1), feat], dim=-1)
+        x = self.base_fc(x)
+        x_vis = self.vis_fc(x * w)
+        x_res, vis = x_vis[..., :-1], x_vis[..., -1:]
+        vis = torch.sigmoid(vis) * m
+        x = x + x_res
+        vis = self.vis_fc2(x * vis) * m
+        logits = self.rgb_fc(torch.cat([x, vis, ray_diff], dim=-1)).masked_fill(m == 0, -1e9)
+        return (rgb_in * F.softmax(logits, dim=1)).sum(dim=1)
+
+
+class SingleVarianceNetwork(nn.Module):
+    def __init__(self, init_val):
+        super().__init__()
+        self.register_parameter("variance", nn.Parameter(torch.tensor(init_val)))
+
+    def forward(self, x):
+        return torch.ones([len(x), 1]).type_as(x) * torch.exp(self.variance * 10.0)

@@ -171,3 +171,95 @@ def lookup_volume(pts: torch.Tensor, volume: Union[torch.Tensor, Sequence[torch.
             return mask_nearest(p, vols, want_each=True)
         raise RuntimeError("gens_b200: nearest look-up is implemented for 1-channel (mask) volumes")
     raise RuntimeError(f"gens_b200: unsupported sample_mode {sample_mode!r}")
+
+
+# ---- source-view reprojection (reference projector.py:278-349) --------------------------------
+def compute_angle(pts, ref_c2w, src_c2ws):
+    """IBRNet ray-direction difference features (n, ns, 4): unit (ref_dir - src_dir) and their dot."""
+    to_ref = ref_c2w[:3, 3][None, None, :] - pts[None, :, :]
+    to_ref = to_ref / (torch.norm(to_ref, dim=-1, keepdim=True) + 1e-6)
+    to_src = src_c2ws[:, :3, 3][:, None, :] - pts[None, :, :]
+    to_src = to_src / (torch.norm(to_src, dim=-1, keepdim=True) + 1e-6)
+    diff = to_ref - to_src
+    diff_dir = diff / torch.clamp(torch.norm(diff, dim=-1, keepdim=True), min=1e-6)
+    dot = (to_ref * to_src).sum(dim=-1, keepdim=True)
+    return torch.cat([diff_dir, dot], dim=-1).permute(1, 0, 2).contiguous()
+
+
+def lookup_feature(pts, imgs, intrs, c2ws, features):
+    """Project points into every source view at every scale, sample RGB (scale 0) and features.
+    Returns ((n,ns,3+sum c), (n,ns,4), (n,ns) bool) exactly as the reference (projector.py:294-349):
+    align-corners normalisation, align_corners=False sampling, no epsilon in the perspective divide."""
+    import torch.nn.functional as F
+    if not isinstance(features, (list, tuple)):
+        features = [features]
+    src_k, src_c2w, ref_c2w = intrs[1:], c2ws[1:], c2ws[0]
+    ray_diff = compute_angle(pts, ref_c2w, src_c2w)
+    ns, n = src_k.shape[0], pts.shape[0]
+    homo = torch.cat([pts.t(), pts.new_ones(1, n)], dim=0)  # (4,n)
+    w2c = torch.inverse(src_c2w)
+    sampled, masks = [], []
+    rgb = None
+    for i, feat in enumerate(features):
+        with torch.no_grad():
+            k = src_k.clone()
+            k[:, :2] = k[:, :2] * (0.5 ** i)
+            h, w = feat.shape[-2:]
+            cam = torch.matmul(w2c, homo[None])[:, :3]
+            img = torch.matmul(k[:, :3, :3], cam)
+            xy = img[:, :2] / img[:, 2:]
+            nx = xy[:, 0] / ((w - 1) / 2) - 1
+            ny = xy[:, 1] / ((h - 1) / 2) - 1
+            ok = (img[:, 2] > 0) & (xy[:, 0] >= 0) & (xy[:, 0] < w) & (xy[:, 1] >= 0) & (xy[:, 1] < h)
+            masks.append(ok.t())
+            grid = torch.stack([nx, ny], dim=-1).unsqueeze(2)  # (ns,n,1,2)
+        f = F.grid_sample(feat[1:], grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+        sampled.append(f.reshape(ns, feat.shape[1], n).permute(2, 0, 1))
+        if i == 0:
+            c = F.grid_sample(imgs[1:], grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+            rgb = c.reshape(ns, 3, n).permute(2, 0, 1)
+    mask = torch.stack(masks, dim=-1).all(dim=-1)
+    return torch.cat([rgb] + sampled, dim=2).float().contiguous(), ray_diff, mask.contiguous()
+
+
+# ---- feature-metric consistency patches (reference projector.py:353-437) ------------------------
+def surface_patch_warp(pts_sdf0, gradients_sdf0, images, intrinsics, poses, patch_size=11):
+    """Plane-induced homography warp of a patch_size^2 pixel patch around each surface point from the
+    reference view into the sources.  Returns ((1,B,p*p,c), (ns,B,p*p,c)); differentiable w.r.t. pts."""
+    import torch.nn.functional as F
+    b = pts_sdf0.shape[0]
+    r0, c0 = poses[0, :3, :3], poses[0, :3, 3]
+    k0 = intrinsics[0, :3, :3]
+    k0_inv = torch.inverse(intrinsics)[0, :3, :3]
+    x_ref = pts_sdf0 @ r0 - (c0 @ r0)[None, None, :]              # (B,1,3) point in the reference camera
+    proj = x_ref @ k0.t()                                         # (B,1,3)
+    disp = (gradients_sdf0 * x_ref).sum(-1, keepdim=True)         # n . X  (B,1,1)
+
+    k_src = intrinsics[1:, :3, :3]
+    ns = k_src.shape[0]
+    r_src_t = poses[1:, :3, :3].transpose(1, 2)                   # (ns,3,3) world -> source camera
+    r_rel = r_src_t @ r0                                          # (ns,3,3)
+    t_rel = (r_src_t @ (c0[None, :] - poses[1:, :3, 3])[..., None])  # (ns,3,1)
+    plane = t_rel[None] @ gradients_sdf0[:, None, :, :].expand(b, ns, 1, 3)   # (B,ns,3,3) = t n^T
+    hom = k_src[None] @ (r_rel[None] + plane / (disp[:, None] + 1e-10)) @ k0_inv[None, None]
+
+    centre = torch.stack([proj[:, 0, 0] / (proj[:, 0, 2] + 1e-8), proj[:, 0, 1] / (proj[:, 0, 2] + 1e-8)], -1).float()
+    half = patch_size // 2
+    r = torch.arange(-half, half + 1, device=centre.device, dtype=centre.dtype)
+    off = torch.stack(torch.meshgrid(r, r, indexing="ij")[::-1], dim=-1).reshape(1, -1, 2)  # x fastest
+    patch = centre[:, None, :] + off                               # (B,p*p,2)
+    h, w = images.shape[-2:]
+    npx = patch.shape[1]
+
+    uv1 = torch.cat([patch, torch.ones_like(patch[..., :1])], dim=-1)  # (B,p*p,3)
+    warped = torch.einsum("bsij,bpj->sbpi", hom, uv1).reshape(ns, -1, 3)
+    g = warped[..., :2] / (warped[..., 2:] + 1e-8)
+    gx = 2 * g[:, :, 0] / (w - 1) - 1.0
+    gy = 2 * g[:, :, 1] / (h - 1) - 1.0
+    src = F.grid_sample(images[1:], torch.stack([gx, gy], -1).view(ns, -1, 1, 2), align_corners=True)
+    sampled = src.view(ns, -1, b, npx).permute(0, 2, 3, 1).contiguous()
+    px = 2 * patch[..., 0] / (w - 1) - 1.0
+    py = 2 * patch[..., 1] / (h - 1) - 1.0
+    ref = F.grid_sample(images[:1], torch.stack([px, py], -1).detach().view(1, -1, 1, 2), align_corners=True)
+    ref = ref.view(1, -1, b, npx).permute(0, 2, 3, 1).contiguous()
+    return ref, sampled
