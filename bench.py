@@ -4,10 +4,14 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the hot path over BASELINE config 2 (480x640, 3 views, volume dims
-[256,128,64,32,16]): the 5-scale volume build.  `value` = voxel*views/s with inputs resident in
-HBM; `e2e` = the same through the public API with pinned host buffers, H2D of the feature
-pyramid + cameras and D2H of the volumes inside the timed region.  Prints ONE JSON line.
+BASELINE.json names two rates for the hot path, so the line carries both:
+  * headline `metric`/`value`: voxel*views/s of the 5-scale volume build of config 2 (480x640, 3 views,
+    volume dims [256,128,64,32,16]); one "step" = one build.  `value` has inputs resident in HBM; `e2e`
+    goes through the public API with pinned host buffers (H2D of the feature pyramid + cameras and D2H
+    of the volumes inside the timed region).
+  * `render`: ray-samples/s of ImplicitSurface.render over the full 480x640 image of the same config
+    (64+64 samples per ray, hierarchical up-sampling included), with its own e2e / cpu_baseline.
+Prints ONE JSON line.
 """
 from __future__ import annotations
 
@@ -129,6 +133,67 @@ def algorithmic_bytes_scale(d, nv, h, w):
     return d ** 3 * 9 * 4 + nv * 4 * h * w * 4
 
 
+
+RENDER_CHUNK = 8192          # rays per ImplicitSurface.render call (the reference's validate uses 256)
+
+
+def smooth_volumes(dims, device, seed=1):
+    """Stand-ins for RegNetwork's output (outside the hot path): smooth random fields, (1,4,D,D,D)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    vols = []
+    for d in dims:
+        lo = max(d // 8, 2)
+        base = torch.randn(1, 4, lo, lo, lo, device=device, generator=g) * 0.5
+        vols.append(torch.nn.functional.interpolate(base, size=(d, d, d), mode="trilinear",
+                                                    align_corners=True).contiguous())
+    return vols
+
+
+def build_surface(device, ops=None):
+    from gens_b200.config import gens_model_conf
+    from gens_b200.implicit_surface import ImplicitSurface
+    torch.manual_seed(0)
+    surf = ImplicitSurface(gens_model_conf(perturb=1.0)["implicit_surface"], ops=ops).to(device)
+    surf.eval()
+    return surf
+
+
+def render_rays(surf, sc, vols, masks, rays_o, rays_d, chunk):
+    """Full parity render (all 18 outputs computed) of the given rays; returns the per-ray image outputs."""
+    cols, deps, nrms, sdeps = [], [], [], []
+    with torch.no_grad():
+        for o, d in zip(rays_o.split(chunk), rays_d.split(chunk)):
+            r = surf.render(o, d, sc.near, sc.far, vols, masks, sc.imgs, sc.features, sc.features, sc.intrs,
+                            sc.c2ws, 1.0, None)
+            cols.append(r["color_fine"]); deps.append(r["render_depth"]); nrms.append(r["normal"])
+            sdeps.append(r["sdf_depth"])
+    return torch.cat(cols), torch.cat(deps), torch.cat(nrms), torch.cat(sdeps)
+
+
+def cpu_render_baseline(nv, n_rays=2048, dims=(64, 32, 16, 8, 4)):
+    """Reference-path render on host cores: the same host logic with every look-up expressed in ATen ops
+    on CPU tensors (oracle/torch_oracle.CpuOps).  Bounded sample: `n_rays` rays through a 64^3 pyramid."""
+    from gens_b200.synthetic import make_scene
+    from oracle import torch_oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sc = make_scene(HW[0], HW[1], nv, seed=0)
+    surf = build_surface(torch.device("cpu"), ops=torch_oracle.CpuOps)
+    vols = smooth_volumes(list(dims), torch.device("cpu"))
+    with torch.no_grad():
+        _, masks = torch_oracle.agg_mean_var([f for f in sc.features], sc.intrs, sc.c2ws, list(dims))
+    ro, rd = sc.rays(step=1)
+    sel = torch.arange(0, ro.shape[0], ro.shape[0] // n_rays)[:n_rays]
+    ro, rd = ro[sel].contiguous(), rd[sel].contiguous()
+    render_rays(surf, sc, vols, masks, ro[:64], rd[:64], 256)  # warm-up
+    t0 = time.perf_counter()
+    render_rays(surf, sc, vols, masks, ro, rd, 256)
+    dt = time.perf_counter() - t0
+    return {"value": n_rays * 128 / dt, "unit": "ray-samples/s", "cores": cores, "kind": "port",
+            "sample": f"{n_rays} rays x 128 samples, 256-ray chunks, volume dims {list(dims)} (ATen-op restatement "
+                      f"of ImplicitSurface.render on host tensors, all host threads)", "ms": dt * 1e3}
+
+
 # --------------------------------------------------------------------------- reference arm
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path: the same ATen op sequence as
@@ -150,6 +215,7 @@ def run_reference(args, rank, world):
             run()
         dt = (time.perf_counter() - t0) / args.steps
     val = voxel_views(args.nv) / dt
+    render = None if args.no_render else cpu_render_baseline(args.nv)
     line = {
         "impl": "reference", "metric": "voxel*views/s (volume build)", "value": val, "unit": "voxel*views/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
@@ -160,11 +226,76 @@ def run_reference(args, rank, world):
                          "sample": "full 5-scale build per step (ATen-op restatement of volume.py on host tensors)"},
         "e2e": {"value": val, "unit": "voxel*views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "render": None if render is None else {
+            "metric": "ray-samples/s (render)", "value": render["value"], "unit": "ray-samples/s",
+            "cpu_baseline": render, "e2e": {"value": render["value"], "unit": "ray-samples/s",
+                                            "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
     }
     print(json.dumps(line), flush=True)
 
 
 # --------------------------------------------------------------------------- our arm
+def bench_render(args, rank, world, dev, sc, host, vol_mod, timed):
+    """ray-samples/s of the full-image render (all 18 outputs of render() computed, i.e. the parity path)."""
+    from gens_b200 import _lib, parallel, projector
+    surf = build_surface(dev)
+    vols = smooth_volumes(DIMS, dev)
+    _, masks = vol_mod.agg_mean_var(sc.features, sc.intrs, sc.c2ws)
+    ro_all, rd_all = sc.rays(step=1)
+    n_total = ro_all.shape[0]
+    lo, hi = parallel.shard_range(n_total, rank, world)
+    ro, rd = ro_all[lo:hi].contiguous(), rd_all[lo:hi].contiguous()
+    chunk = args.render_chunk
+    launches0 = _lib.LAUNCHES
+
+    def step_device():
+        col, dep, nrm, sdep = render_rays(surf, sc, vols, masks, ro, rd, chunk)
+        out = torch.cat([col, dep[:, None], nrm, sdep], dim=1)  # (n_local, 8)
+        return parallel.gather_rays(out, n_total, rank, world)
+
+    ms, _ = timed(step_device, args.render_steps, 1)
+    launches = (_lib.LAUNCHES - launches0) // (args.render_steps + 1)
+    samples = n_total * 128
+    res = {"metric": "ray-samples/s (render)", "value": samples / (ms * 1e-3), "unit": "ray-samples/s",
+           "ms_per_step": ms, "steps": args.render_steps, "warmup": 1, "rays": n_total, "samples_per_ray": 128,
+           "chunk_rays": chunk, "outputs": "all 18 keys of render() (incl. second-order smooth term, TV, patch warp)",
+           "sharding": "none" if world == 1 else f"contiguous ray ranges over {world} ranks + final gather",
+           "gpu_launches_per_step": launches}
+
+    # e2e: rays from pinned host memory per chunk, image outputs back to pinned host memory per chunk
+    if world == 1:
+        pin_o, pin_d = ro_all.cpu().pin_memory(), rd_all.cpu().pin_memory()
+        pin_out = torch.empty((n_total, 8), dtype=torch.float32).pin_memory()
+
+        def step_e2e():
+            with torch.no_grad():
+                for a in range(0, n_total, chunk):
+                    o = pin_o[a:a + chunk].to(dev, non_blocking=True)
+                    d = pin_d[a:a + chunk].to(dev, non_blocking=True)
+                    r = surf.render(o, d, sc.near, sc.far, vols, masks, sc.imgs, sc.features, sc.features, sc.intrs,
+                                    sc.c2ws, 1.0, None)
+                    out = torch.cat([r["color_fine"], r["render_depth"][:, None], r["normal"], r["sdf_depth"]], 1)
+                    pin_out[a:a + chunk].copy_(out, non_blocking=True)
+        e_ms, _ = timed(step_e2e, max(1, args.render_steps // 2), 0)
+        res["e2e"] = {"value": samples / (e_ms * 1e-3), "unit": "ray-samples/s", "ms_per_step": e_ms,
+                      "h2d_bytes_per_step": n_total * 6 * 4, "d2h_bytes_per_step": n_total * 8 * 4}
+
+        # roofline view of the gather kernel (K3): logical bytes = 5 scales x 8 corners x 16 B per point
+        n_pts = 1 << 22
+        g = torch.Generator(device=dev).manual_seed(3)
+        pts = torch.rand(n_pts, 3, device=dev, generator=g) * 2 - 1
+        k3_ms, _ = timed(lambda: projector.lookup_volume(pts, vols), 10, 3)
+        peak, _ = measured_peak_gbs()
+        ach = n_pts * len(DIMS) * 8 * 16 / (k3_ms * 1e-3) / 1e9
+        res["roofline"] = {"bound": "hbm", "kernel": "trilinear_fwd_kernel (5 scales, 4.2M random points)",
+                           "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                           "ms": k3_ms, "note": "achieved = LOGICAL gather bytes (640 B/point); the volumes "
+                                                "(307 MB) are read through L2, compulsory HBM bytes are far fewer"}
+        if rank == 0 and not args.no_cpu:
+            res["cpu_baseline"] = cpu_render_baseline(args.nv)
+    return res
+
+
 def run_ours(args, rank, world, local):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- gens_b200 has no CPU fallback (use --impl reference)")
@@ -247,6 +378,9 @@ def run_ours(args, rank, world, local):
         e2e_ms = None
         if world == 1:
             e2e_ms, _ = timed(step_e2e, max(3, args.steps // 4), 2)
+        render = None
+        if not args.no_render:
+            render = bench_render(args, rank, world, dev, sc, host, vol_mod, timed)
     clk = clocks.summary()
 
     fill = None
@@ -294,6 +428,7 @@ def run_ours(args, rank, world, local):
                                             "ms_per_step": e2e_ms},
         "gpu_launches": 2 * len(DIMS) * args.steps,  # per step: 5 pack + 5 aggregation kernels
         "clocks": clk,
+        "render": render,
     }
     print(json.dumps(line), flush=True)
 
@@ -306,6 +441,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nv", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-render", action="store_true", help="volume-build metric only")
+    ap.add_argument("--render-steps", type=int, default=2, help="full-image renders timed for the render metric")
+    ap.add_argument("--render-chunk", type=int, default=RENDER_CHUNK)
     args = ap.parse_args()
     rank, world, local = dist_setup(args.gpus)
     if args.impl == "reference":

@@ -93,7 +93,12 @@ def lib():
     return _lib
 
 
+LAUNCHES = 0  # C-ABI calls made so far (each enqueues at least one of our kernels); bench.py reads it
+
+
 def check(code: int, what: str):
+    global LAUNCHES
+    LAUNCHES += 1
     if code != 0:
         msg = lib().gens_error_string(code)
         raise RuntimeError(f"{what} failed ({code}): {msg.decode() if msg else '?'}")

@@ -15,8 +15,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import projector as _cuda_ops
 from .networks import BlendingNetwork, SDFNetwork, SingleVarianceNetwork
-from .projector import lookup_feature, lookup_volume, mask_nearest, surface_patch_warp
 
 FAR_SDF = 100.0  # value the reference assigns to samples outside every mask volume
 
@@ -57,13 +57,17 @@ def neus_weights(alpha: torch.Tensor) -> torch.Tensor:
 
 
 class ImplicitSurface(nn.Module):
-    def __init__(self, confs):
+    def __init__(self, confs, ops=None):
+        """`ops` supplies lookup_volume / mask_nearest / lookup_feature / surface_patch_warp; the default
+        (and only shipped) provider is the CUDA one, gens_b200.projector.  Tests inject an ATen-on-CPU
+        provider from oracle/ to check this host logic against the reference's golden vectors."""
         super().__init__()
+        self.ops = _cuda_ops if ops is None else ops
         self.n_samples = confs.get_int("render.n_samples")
         self.n_importance = confs.get_int("render.n_importance")
         self.up_sample_steps = confs.get_int("render.up_sample_steps")
         self.perturb = confs.get_float("render.perturb")
-        self.sdf_network = SDFNetwork(**confs["sdf_network"])
+        self.sdf_network = SDFNetwork(**confs["sdf_network"], lookup=self.ops.lookup_volume)
         self.color_network = BlendingNetwork(**confs["color_network"])
         self.deviation_network = SingleVarianceNetwork(**confs["variance_network"])
         self.val_chunk = 256  # rays per render() call in validate(); 256 = the reference's split
@@ -71,7 +75,7 @@ class ImplicitSurface(nn.Module):
     # ------------------------------------------------------------------ hierarchical sampling
     def _sdf_masked(self, pts, volumes, mask_volumes, folded=None):
         """SDF at (n,3) points, FAR_SDF outside the mask volumes (no gradient)."""
-        valid = _valid_or_first10(mask_nearest(pts, mask_volumes))
+        valid = _valid_or_first10(self.ops.mask_nearest(pts, mask_volumes))
         sdf = self.sdf_network.sdf_nograd(pts, volumes, folded)
         return torch.where(valid[:, None], sdf, torch.full_like(sdf, FAR_SDF))
 
@@ -79,7 +83,7 @@ class ImplicitSurface(nn.Module):
         """n_importance new depths per ray from the NeuS weights at a fixed inv_s (reference :60-109)."""
         b, m = z_vals.shape
         pts = rays_o[:, None, :] + rays_d[:, None, :] * z_vals[..., :, None]
-        valid = mask_nearest(pts.reshape(-1, 3), mask_volumes).reshape(b, m)
+        valid = self.ops.mask_nearest(pts.reshape(-1, 3), mask_volumes).reshape(b, m)
         both = valid[:, :-1] & valid[:, 1:]
         radius = torch.linalg.norm(pts, ord=2, dim=-1)
         inside = ((radius[:, :-1] < 1.0) | (radius[:, 1:] < 1.0)) & both
@@ -132,7 +136,7 @@ class ImplicitSurface(nn.Module):
         pts = (rays_o[:, None, :] + rays_d[:, None, :] * mid_z[..., :, None]).reshape(-1, 3)
         dirs = rays_d[:, None, :].expand(b, n, 3).reshape(-1, 3)
 
-        voxel_mask = mask_nearest(pts, mask_volumes)  # (b*n,) bool, before the 10-point fallback
+        voxel_mask = self.ops.mask_nearest(pts, mask_volumes)  # (b*n,) bool, before the 10-point fallback
         evaluated = _valid_or_first10(voxel_mask)
         ev = evaluated[:, None]
         vm = voxel_mask.reshape(b, n).float()
@@ -145,7 +149,7 @@ class ImplicitSurface(nn.Module):
         smooth = torch.where(ev, smooth_all, torch.zeros_like(smooth_all))
 
         # source-view colours
-        feat_views, ray_diff, mask_views = lookup_feature(pts, imgs, intrs, c2ws, features)
+        feat_views, ray_diff, mask_views = self.ops.lookup_feature(pts, imgs, intrs, c2ws, features)
         mask_views = mask_views & ev
         colour = self.color_network(feat_views, ray_diff, mask_views)
         colour = torch.where(ev, colour, torch.zeros_like(colour)).reshape(b, n, 3)
@@ -218,7 +222,7 @@ class ImplicitSurface(nn.Module):
         f0 = src[0].detach()
         ups = [F.interpolate(src[k].detach(), size=f0.shape[-2:], mode="bilinear") for k in (1, 2)]
         warp_feats = torch.cat([f0] + ups, dim=1).detach()
-        ref_gray_val, sampled_gray_val = surface_patch_warp(pts_sdf0, g_sdf0, warp_feats, intrs, c2ws)
+        ref_gray_val, sampled_gray_val = self.ops.surface_patch_warp(pts_sdf0, g_sdf0, warp_feats, intrs, c2ws)
 
         return {
             'ref_gray_val': ref_gray_val,
@@ -336,7 +340,7 @@ class ImplicitSurface(nn.Module):
                                   intrs, c2ws, cos_anneal_ratio, step)
         if "pseudo_pts" in ipts:
             pseudo_pts = ipts["pseudo_pts"]
-            valid = mask_nearest(pseudo_pts, mask_volumes)
+            valid = self.ops.mask_nearest(pseudo_pts, mask_volumes)
             if not bool(valid.any()):
                 raise RuntimeError("No valid pseudo pts!")
             sdf = self.sdf_network.sdf(pseudo_pts, volumes)

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .projector import lookup_volume
+from . import projector as _projector
 
 
 def positional_encoding(x: torch.Tensor, n_freqs: int) -> torch.Tensor:
@@ -40,8 +40,10 @@ def encoded_width(d: int, n_freqs: int) -> int:
 
 class SDFNetwork(nn.Module):
     def __init__(self, d_in, d_out, d_hidden, n_layers, skip_in=(4,), multires=0, bias=0.5, scale=1,
-                 geometric_init=True, weight_norm=True, inside_outside=False, feat_channels=32, feat_multires=2):
+                 geometric_init=True, weight_norm=True, inside_outside=False, feat_channels=32, feat_multires=2,
+                 lookup=None):
         super().__init__()
+        self._lookup = _projector.lookup_volume if lookup is None else lookup
         self.multires, self.feat_multires = int(multires), int(feat_multires)
         self.init_feat_channels = feat_channels
         self.scale = scale
@@ -89,7 +91,7 @@ class SDFNetwork(nn.Module):
 
     # -- reference-shaped path (autograd at op granularity; training and .gradient) -------------
     def forward(self, inputs, volumes):
-        feats = positional_encoding(lookup_volume(inputs.clone(), volumes), self.feat_multires)
+        feats = positional_encoding(self._lookup(inputs.clone(), volumes), self.feat_multires)
         pos = positional_encoding(inputs * self.scale, self.multires)
         x = pos
         for l in range(self.num_layers - 1):
@@ -136,7 +138,7 @@ class SDFNetwork(nn.Module):
         encoded volume features enter every layer through ONE (n,100)x(100,sum fan_out) GEMM instead of
         six concatenations, and only column 0 of the output layer is evaluated."""
         folded = self.folded_weights() if folded is None else folded
-        feats = positional_encoding(lookup_volume(pts, volumes), self.feat_multires)
+        feats = positional_encoding(self._lookup(pts, volumes), self.feat_multires)
         pos = positional_encoding(pts * self.scale, self.multires)
         last = self.num_layers - 2
         # feature columns of layers 1..last, stacked

@@ -53,18 +53,19 @@ class Scene:
     def rays(self, step: int = 1):
         """Rays of the reference view through every `step`-th pixel, row-major (y, x)."""
         h, w = self.hw
+        intrs, c2ws = self.intrs.cpu(), self.c2ws.cpu()  # always generated on the host, then moved
         ys, xs = torch.meshgrid(
             torch.arange(0, h, step, dtype=torch.float32),
             torch.arange(0, w, step, dtype=torch.float32),
             indexing="ij",
         )
         p = torch.stack([xs.reshape(-1), ys.reshape(-1), torch.ones(xs.numel())], dim=-1)
-        kinv = torch.inverse(self.intrs[0, :3, :3])
+        kinv = torch.inverse(intrs[0, :3, :3])
         p = p @ kinv.T
         d = p / torch.linalg.norm(p, dim=-1, keepdim=True)
-        d = d @ self.c2ws[0, :3, :3].T
-        o = self.c2ws[0, :3, 3].expand_as(d).contiguous()
-        return o, d.contiguous()
+        d = d @ c2ws[0, :3, :3].T
+        o = c2ws[0, :3, 3].expand_as(d).contiguous()
+        return o.to(self.intrs.device), d.contiguous().to(self.intrs.device)
 
     def to(self, device):
         return Scene(

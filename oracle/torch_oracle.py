@@ -101,3 +101,94 @@ def lookup_volume(pts, volumes, sample_mode="grad"):
             o = F.grid_sample(v, grid, mode="nearest", padding_mode="zeros", align_corners=False)
         outs.append(o.reshape(v.shape[1], -1).t())
     return torch.cat(outs, -1)
+
+
+# ---- ATen-on-CPU provider of the ray marcher's look-up ops ------------------------------------
+class CpuOps:
+    """Drop-in for gens_b200.projector as the `ops` of gens_b200.implicit_surface.ImplicitSurface:
+    the same four look-ups expressed with ATen ops (device-agnostic, no CUDA extension).  Used (a)
+    by the CPU tests that pin the product's HOST logic to the reference's golden vectors and (b) as
+    the CPU baseline of bench.py's render metric.  `nearest_fused` is irrelevant here: ATen itself
+    picks the flavour of the device it runs on."""
+
+    @staticmethod
+    def lookup_volume(pts, volume, sample_mode="grad"):
+        vols = [volume] if isinstance(volume, torch.Tensor) else list(volume)
+        pts = pts.reshape(-1, 3)
+        if sample_mode == "grad":
+            if torch.is_grad_enabled() and pts.requires_grad:
+                # double-differentiable form (the reference needs its CUDA-only grad2 op for this)
+                return torch.cat([trilinear_dd(v, pts) for v in vols], -1)
+            return lookup_volume(pts, vols, "grad")
+        return lookup_volume(pts, vols, "nearest")
+
+    @staticmethod
+    def mask_nearest(pts, masks, want_each=False):
+        each = CpuOps.lookup_volume(pts, masks, "nearest")
+        return each if want_each else each.any(dim=-1)
+
+    @staticmethod
+    def lookup_feature(pts, imgs, intrs, c2ws, features):
+        """Reference projector.py:278-349 restated (see gens_b200.projector.lookup_feature for the contract)."""
+        if not isinstance(features, (list, tuple)):
+            features = [features]
+        src_k, src_c2w, ref_c = intrs[1:], c2ws[1:], c2ws[0, :3, 3]
+        a = ref_c[None, None] - pts[None]
+        a = a / (torch.norm(a, dim=-1, keepdim=True) + 1e-6)
+        b = src_c2w[:, :3, 3][:, None] - pts[None]
+        b = b / (torch.norm(b, dim=-1, keepdim=True) + 1e-6)
+        d = a - b
+        ray_diff = torch.cat([d / torch.clamp(torch.norm(d, dim=-1, keepdim=True), min=1e-6),
+                              (a * b).sum(-1, keepdim=True)], -1).permute(1, 0, 2).contiguous()
+        ns, n = src_k.shape[0], pts.shape[0]
+        homo = torch.cat([pts.t(), pts.new_ones(1, n)], 0)
+        w2c = torch.inverse(src_c2w)
+        out, masks, rgb = [], [], None
+        for i, feat in enumerate(features):
+            with torch.no_grad():
+                k = src_k.clone()
+                k[:, :2] = k[:, :2] * (0.5 ** i)
+                h, w = feat.shape[-2:]
+                img = torch.matmul(k[:, :3, :3], torch.matmul(w2c, homo[None])[:, :3])
+                xy = img[:, :2] / img[:, 2:]
+                nx, ny = xy[:, 0] / ((w - 1) / 2) - 1, xy[:, 1] / ((h - 1) / 2) - 1
+                masks.append(((img[:, 2] > 0) & (xy[:, 0] >= 0) & (xy[:, 0] < w) & (xy[:, 1] >= 0) & (xy[:, 1] < h)).t())
+                grid = torch.stack([nx, ny], -1).unsqueeze(2)
+            out.append(F.grid_sample(feat[1:], grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+                       .reshape(ns, feat.shape[1], n).permute(2, 0, 1))
+            if i == 0:
+                rgb = F.grid_sample(imgs[1:], grid, mode="bilinear", padding_mode="zeros", align_corners=False) \
+                    .reshape(ns, 3, n).permute(2, 0, 1)
+        return (torch.cat([rgb] + out, 2).float().contiguous(), ray_diff,
+                torch.stack(masks, -1).all(-1).contiguous())
+
+    @staticmethod
+    def surface_patch_warp(pts_sdf0, normals, images, intrinsics, poses, patch_size=11):
+        """Reference projector.py:353-437 restated: plane-induced homography patches."""
+        b = pts_sdf0.shape[0]
+        r0, c0 = poses[0, :3, :3], poses[0, :3, 3]
+        k0, k0_inv = intrinsics[0, :3, :3], torch.inverse(intrinsics)[0, :3, :3]
+        x_ref = pts_sdf0 @ r0 - (c0 @ r0)[None, None]
+        proj = x_ref @ k0.t()
+        disp = (normals * x_ref).sum(-1, keepdim=True)
+        ns = intrinsics.shape[0] - 1
+        r_src_t = poses[1:, :3, :3].transpose(1, 2)
+        t_rel = r_src_t @ (c0[None] - poses[1:, :3, 3])[..., None]
+        hom = intrinsics[1:, :3, :3][None] @ (
+            (r_src_t @ r0)[None] + (t_rel[None] @ normals[:, None].expand(b, ns, 1, 3)) / (disp[:, None] + 1e-10)
+        ) @ k0_inv[None, None]
+        centre = torch.stack([proj[:, 0, 0] / (proj[:, 0, 2] + 1e-8), proj[:, 0, 1] / (proj[:, 0, 2] + 1e-8)], -1)
+        half = patch_size // 2
+        r = torch.arange(-half, half + 1, device=centre.device, dtype=centre.dtype)
+        off = torch.stack(torch.meshgrid(r, r, indexing="ij")[::-1], -1).reshape(1, -1, 2)
+        patch = centre[:, None] + off
+        h, w = images.shape[-2:]
+        npx = patch.shape[1]
+        warped = torch.einsum("bsij,bpj->sbpi", hom, torch.cat([patch, torch.ones_like(patch[..., :1])], -1))
+        warped = warped.reshape(ns, -1, 3)
+        g = warped[..., :2] / (warped[..., 2:] + 1e-8)
+        grid = torch.stack([2 * g[..., 0] / (w - 1) - 1, 2 * g[..., 1] / (h - 1) - 1], -1).view(ns, -1, 1, 2)
+        src = F.grid_sample(images[1:], grid, align_corners=True).view(ns, -1, b, npx).permute(0, 2, 3, 1)
+        pgrid = torch.stack([2 * patch[..., 0] / (w - 1) - 1, 2 * patch[..., 1] / (h - 1) - 1], -1)
+        ref = F.grid_sample(images[:1], pgrid.detach().view(1, -1, 1, 2), align_corners=True)
+        return ref.view(1, -1, b, npx).permute(0, 2, 3, 1).contiguous(), src.contiguous()

@@ -15,27 +15,7 @@ DEV = "cuda:0"
 DIMS = [32, 16, 8, 4, 2]
 
 
-def _mismatch(name, got, ref, rtol=1e-4, atol_scale=1e-6, outlier_frac=0.0, outlier_rtol=1e-2):
-    """None if `got` matches `ref`, else a message.  outlier_frac: share of elements allowed to miss the
-    tight bound (but not outlier_rtol) -- for quantities that are DISCONTINUOUS in the sample position
-    (the gradient of a trilinear field jumps at voxel faces, so a 1e-7 difference in a sample depth between
-    the CPU golden run and the GPU can land on the other side of a face)."""
-    got = got.detach().float().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
-    if got.shape != ref.shape:
-        return f"{name}: shape {got.shape} != {ref.shape}"
-    scale = max(float(np.abs(ref).max()), 1.0) if ref.size else 1.0
-    err = np.abs(got.astype(np.float64) - ref.astype(np.float64))
-    bad = err > atol_scale * scale + rtol * np.abs(ref)
-    worse = err > outlier_rtol * (scale + np.abs(ref))
-    if bad.sum() > outlier_frac * bad.size or worse.any():
-        return (f"{name}: {bad.sum()} of {bad.size} outside tolerance ({worse.sum()} gross), "
-                f"max err {err.max():.3e} (scale {scale:.3e})")
-    return None
-
-
-def _check(name, got, ref, **kw):
-    msg = _mismatch(name, got, ref, **kw)
-    assert msg is None, msg
+from parity import JUMPY, check as _check, mismatch as _mismatch  # noqa: E402
 
 
 @pytest.fixture(scope="module")
@@ -91,9 +71,7 @@ def test_full_render_matches_reference(setup):
     assert np.array_equal(res["inside_sphere"].cpu().numpy(), g["render/inside_sphere"])
     assert np.array_equal(res["mid_inside_sphere"].cpu().numpy(), g["render/mid_inside_sphere"])
     loose = {"smooth_error": 1e-3}
-    # gradient-derived quantities (and the weights they steer through true_cos) inherit the jumps
-    jumpy = {"gradients": 2e-3, "normal": 2e-3, "ref_gray_val": 2e-3, "sampled_gray_val": 2e-3, "weights": 1e-2,
-             "weight_sum": 1e-2, "weight_max": 1e-2}
+    jumpy = JUMPY
     skip = {"valid_mask", "inside_sphere", "mid_inside_sphere", "sparse_sdf"}
     problems = []
     for k in ref_keys:
