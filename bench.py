@@ -309,7 +309,7 @@ def run_ours(args, rank, world, local):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     nv = args.nv
-    host = make_scene(HW[0], HW[1], nv, seed=0, with_images=False)
+    host = make_scene(HW[0], HW[1], nv, seed=0, with_images=True)
     sc = host.to(dev)
     vol_mod = Volume(volume_dims=DIMS)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
