@@ -64,6 +64,13 @@ _SIGNATURES = {
     "gens_trilinear_fwd": ([_vp, _ll, _PP, _vp, _vp], _i),
     "gens_trilinear_bwd": ([_vp, _ll, _PP, _vp, _vp, _PP, _vp], _i),
     "gens_trilinear_bwd2": ([_vp, _ll, _PP, _vp, _vp, _vp, _vp, _PP, _vp], _i),
+    "gens_trilinear_fwd_jvp": ([_vp, _ll, _PP, _vp, _vp, _vp, _vp], _i),
+    "gens_trilinear_vjp2": ([_vp, _ll, _PP, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "gens_sdf_encode": ([_vp, _vp, _vp, _ll, _f, _vp, _i, _i, _i, _vp, _vp, _vp], _i),
+    "gens_sdf_act_fwd": ([_vp, _vp, _i, _vp, _ll, _i, _f, _f, _vp, _i, _vp, _vp, _vp], _i),
+    "gens_copy_scaled": ([_vp, _i, _ll, _f, _vp, _i, _i, _vp], _i),
+    "gens_sdf_act_bwd": ([_vp, _i, _f, _vp, _vp, _ll, _i, _vp, _i, _vp], _i),
+    "gens_sdf_decode": ([_vp, _vp, _vp, _vp, _vp, _ll, _f, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "gens_debug_set_variant": ([_i], _i),
     "gens_selftest_division": ([_i, ctypes.c_ulonglong, _vp, _vp], _i),
 }

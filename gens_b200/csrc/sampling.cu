@@ -273,6 +273,65 @@ trilinear_bwd2_kernel(const float* __restrict__ pts, long long n, Pyr pyr, const
     g2_pts[3 * i + 2] = acc[2];
 }
 
+// value + directional derivative along u (forward-mode): f (n,4S), df = J u (n,4S)
+__global__ void __launch_bounds__(256)
+trilinear_fwd_jvp_kernel(const float* __restrict__ pts, long long n, Pyr pyr, float u0, float u1, float u2,
+                         float* __restrict__ out, float* __restrict__ dout) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float p0 = __ldg(pts + 3 * i), p1 = __ldg(pts + 3 * i + 1), p2 = __ldg(pts + 3 * i + 2);
+    float4* o = reinterpret_cast<float4*>(out + i * 4 * pyr.n);
+    float4* od = reinterpret_cast<float4*>(dout + i * 4 * pyr.n);
+#pragma unroll 1
+    for (int s = 0; s < pyr.n; ++s) {
+        const Cell c = locate(p0, p1, p2, pyr.dim[s]);
+        float4 v[2][2][2];
+        load_corners(pyr.vol[s], pyr.dim[s], c, v);
+        const Jet j = interpolate<1>(v, c);
+        o[s] = j.f;
+        float4 r = f4scale(j.d[0], u0 * c.mult);
+        r = f4axpy(u1 * c.mult, j.d[1], r);
+        od[s] = f4axpy(u2 * c.mult, j.d[2], r);
+    }
+}
+
+// reverse-mode through the look-up and its tangent, accumulated onto grad / smooth (n,3):
+//   grad   += J^T g          smooth += (H u)^T g + J^T dg
+__global__ void __launch_bounds__(256)
+trilinear_vjp2_kernel(const float* __restrict__ pts, long long n, Pyr pyr, float u0, float u1, float u2,
+                      const float* __restrict__ g_f, const float* __restrict__ dg_f, float* __restrict__ grad,
+                      float* __restrict__ smooth) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float p0 = __ldg(pts + 3 * i), p1 = __ldg(pts + 3 * i + 1), p2 = __ldg(pts + 3 * i + 2);
+    const float4* g4 = reinterpret_cast<const float4*>(g_f + i * 4 * pyr.n);
+    const float4* dg4 = reinterpret_cast<const float4*>(dg_f + i * 4 * pyr.n);
+    float ga[3] = {0.f, 0.f, 0.f}, sa[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int s = 0; s < pyr.n; ++s) {
+        const Cell c = locate(p0, p1, p2, pyr.dim[s]);
+        float4 v[2][2][2];
+        load_corners(pyr.vol[s], pyr.dim[s], c, v);
+        const Jet j = interpolate<2>(v, c);
+        const float4 g = __ldg(g4 + s), dg = __ldg(dg4 + s);
+        const float m = c.mult, mm = c.mult * c.mult;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            ga[k] = fmaf(m, f4dot(g, j.d[k]), ga[k]);
+            sa[k] = fmaf(m, f4dot(dg, j.d[k]), sa[k]);
+        }
+        const float hab = f4dot(g, j.dd[0]) * mm, hac = f4dot(g, j.dd[1]) * mm, hbc = f4dot(g, j.dd[2]) * mm;
+        sa[0] += u1 * hab + u2 * hac;
+        sa[1] += u0 * hab + u2 * hbc;
+        sa[2] += u0 * hac + u1 * hbc;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        grad[3 * i + k] += ga[k];
+        if (smooth) smooth[3 * i + k] += sa[k];
+    }
+}
+
 // (1,4,D,D,D) NCDHW <-> channels-last (D,D,D,4)
 __global__ void __launch_bounds__(256)
 pack_volume_kernel(const float* __restrict__ src, float4* __restrict__ dst, long long d3) {
@@ -371,5 +430,27 @@ extern "C" int gens_trilinear_bwd2(const float* pts, long long n, const gens_pyr
     fill_grad(g2_vols, p.n, gv);
     trilinear_bwd2_kernel<<<ceil_div_i(n, 256), 256, 0, (cudaStream_t)stream>>>(pts, n, p, g_out, gg_pts, gg_out, g2_pts,
                                                                               gv);
+    return gens_launch_status();
+}
+
+extern "C" int gens_trilinear_fwd_jvp(const float* pts, long long n, const gens_pyramid_t* vols, const float* u3,
+                                      float* out, float* dout, void* stream) {
+    GENS_CHECK_ARG(pts && out && dout && u3 && n >= 0);
+    Pyr p;
+    if (!fill_pyr(vols, p)) return GENS_E_BADARG;
+    if (n == 0) return 0;
+    trilinear_fwd_jvp_kernel<<<ceil_div_i(n, 256), 256, 0, (cudaStream_t)stream>>>(pts, n, p, u3[0], u3[1], u3[2], out,
+                                                                                  dout);
+    return gens_launch_status();
+}
+
+extern "C" int gens_trilinear_vjp2(const float* pts, long long n, const gens_pyramid_t* vols, const float* u3,
+                                   const float* g_f, const float* dg_f, float* grad, float* smooth, void* stream) {
+    GENS_CHECK_ARG(pts && g_f && dg_f && grad && u3 && n >= 0);
+    Pyr p;
+    if (!fill_pyr(vols, p)) return GENS_E_BADARG;
+    if (n == 0) return 0;
+    trilinear_vjp2_kernel<<<ceil_div_i(n, 256), 256, 0, (cudaStream_t)stream>>>(pts, n, p, u3[0], u3[1], u3[2], g_f, dg_f,
+                                                                               grad, smooth);
     return gens_launch_status();
 }

@@ -120,6 +120,11 @@ class SDFNetwork(nn.Module):
         return g, h
 
     # -- inference path ---------------------------------------------------------------------------
+    def value_grad_smooth_nograd(self, pts, volumes, need_smooth=True):
+        """(sdf, grad, smooth) without an autograd graph (CUDA only; see gens_b200/sdf_analytic.py)."""
+        from . import sdf_analytic
+        return sdf_analytic.value_grad_smooth(self, pts, volumes, None, need_smooth)
+
     def folded_weights(self):
         """Effective (weight, bias) per layer with the weight normalisation folded in."""
         out = []

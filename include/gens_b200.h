@@ -142,6 +142,40 @@ int gens_trilinear_bwd2(const float *pts, long long n, const gens_pyramid_t *vol
                         const float *g_out, const float *gg_pts, float *gg_out, float *g2_pts,
                         const gens_pyramid_t *g2_vols, void *stream);
 
+/* ---- analytic SDF pass (value, gradient, second-order term without an autograd graph) ----
+ * Replaces the two nested torch.autograd.grad(create_graph=True) calls of SDFNetwork.gradient
+ * (reference models/modules/sdf_network.py:131-153) in no-grad rendering.  Every work matrix has 2n
+ * rows: [0,n) primal, [n,2n) directional derivative along the HOST vector u3 (= (1,1,1), the
+ * reference's d_output2 = ones).  The dense layers between these kernels are plain SGEMMs. */
+/* K3 forward + JVP: out (n,4S) features, dout (n,4S) = J u. */
+int gens_trilinear_fwd_jvp(const float *pts, long long n, const gens_pyramid_t *vols, const float *u3,
+                           float *out, float *dout, void *stream);
+/* K3 reverse through value and tangent: grad (n,3) += J^T g_f ; smooth (n,3) += (H u)^T g_f + J^T dg_f
+ * (smooth may be NULL). */
+int gens_trilinear_vjp2(const float *pts, long long n, const gens_pyramid_t *vols, const float *u3,
+                        const float *g_f, const float *dg_f, float *grad, float *smooth, void *stream);
+/* positional encodings (embedder.py:11-36) of the scaled point and of the volume features, with
+ * tangents: pos (2n, 3(1+2*multires)), fe (2n, n_feat(1+2*feat_multires)). */
+int gens_sdf_encode(const float *pts, const float *feats, const float *dfeats, long long n, float scale,
+                    const float *u3, int multires, int feat_multires, int n_feat, float *pos, float *fe,
+                    void *stream);
+/* a = y + featpart + bias ; h = softplus_beta(a) -> x_out (2n rows, leading dim ld_x) scaled by
+ * out_scale; keeps sp1 = sp'(a) and sp2da = sp''(a) * da, both (n, fan_out). featpart may be NULL. */
+int gens_sdf_act_fwd(const float *y, const float *featpart, int ld_featpart, const float *bias,
+                     long long n, int fan_out, float beta, float out_scale, float *x_out, int ld_x,
+                     float *sp1, float *sp2da, void *stream);
+/* dst[:, col:col+width] = s * src  (the skip connection [h, pos]/sqrt(2), sdf_network.py:108) */
+int gens_copy_scaled(const float *src, int width, long long rows, float s, float *dst, int ld_dst,
+                     int col, void *stream);
+/* [g_a; dg_a] = softplus backward and its tangent from [g_h; dg_h] (scaled by in_scale). */
+int gens_sdf_act_bwd(const float *g, int ld_g, float in_scale, const float *sp1, const float *sp2da,
+                     long long n, int fan_out, float *ga, int ld_ga, void *stream);
+/* cotangents of the encodings -> g_f, dg_f (n,n_feat) and the positional part of grad / smooth (n,3). */
+int gens_sdf_decode(const float *pts, const float *feats, const float *dfeats, const float *g_pos,
+                    const float *g_fe, long long n, float scale, const float *u3, int multires,
+                    int feat_multires, int n_feat, float *g_f, float *dg_f, float *grad, float *smooth,
+                    void *stream);
+
 /* Tuning knob for profiling sessions: selects among compiled-in launch configurations of K1
  * (0 = the shipped one).  Results are identical for every variant. */
 int gens_debug_set_variant(int variant);

@@ -47,6 +47,27 @@ def test_sdf_network_value_gradient_smooth(setup):
     _check("sdf_smooth", smooth, g["sdf_smooth"], atol_scale=1e-5)
 
 
+def test_analytic_sdf_pass_matches_reference_and_autograd(setup):
+    """The hand-differentiated sweep (no autograd graph) against the golden values and the autograd path."""
+    g, surf, scene, volumes, masks = setup
+    pts = torch.from_numpy(g["sdf_pts"]).to(DEV)
+    sdf, grad, smooth = surf.sdf_network.value_grad_smooth_nograd(pts, volumes)
+    assert not sdf.requires_grad and not grad.requires_grad
+    _check("analytic sdf", sdf, g["sdf_out"][:, :1])
+    _check("analytic grad", grad, g["sdf_grad"])
+    _check("analytic smooth", smooth, g["sdf_smooth"], atol_scale=1e-5)
+    # off-grid random points, incl. outside the volumes
+    torch.manual_seed(3)
+    rnd = torch.rand(20000, 3, device=DEV) * 2.4 - 1.2
+    s2, g2, h2 = surf.sdf_network.value_grad_smooth_nograd(rnd, volumes)
+    ga, ha = surf.sdf_network.gradient(rnd.clone(), volumes)
+    _check("analytic vs autograd grad", g2, ga.detach().cpu().numpy())
+    _check("analytic vs autograd smooth", h2, ha.detach().cpu().numpy(), atol_scale=1e-5)
+    _check("analytic vs forward sdf", s2, surf.sdf_network.sdf(rnd, volumes).detach().cpu().numpy())
+    _, g3, none = surf.sdf_network.value_grad_smooth_nograd(rnd, volumes, need_smooth=False)
+    assert none is None and torch.equal(g3, g2)
+
+
 def test_up_sample_matches_reference(setup):
     g, surf, scene, volumes, masks = setup
     ro, rd = torch.from_numpy(g["rays_o"]).to(DEV), torch.from_numpy(g["rays_d"]).to(DEV)
@@ -85,6 +106,26 @@ def test_full_render_matches_reference(setup):
     _check("sparse_sdf[1024:]", res["sparse_sdf"][1024:], g["render/sparse_sdf"][1024:], atol_scale=1e-5)
 
 
+def test_full_render_nograd_analytic_path_matches_reference(setup):
+    """Same golden comparison for the inference path (torch.no_grad -> analytic SDF sweep)."""
+    g, surf, scene, volumes, masks = setup
+    ro, rd = torch.from_numpy(g["rays_o"]).to(DEV), torch.from_numpy(g["rays_d"]).to(DEV)
+    torch.manual_seed(123)
+    with torch.no_grad():
+        res = surf.render(ro, rd, scene.near, scene.far, volumes, masks, scene.imgs, scene.features,
+                          scene.features, scene.intrs, scene.c2ws, 1.0, None)
+    assert np.array_equal(res["valid_mask"].cpu().numpy(), g["render/valid_mask"])
+    assert np.array_equal(res["mid_inside_sphere"].cpu().numpy(), g["render/mid_inside_sphere"])
+    problems = []
+    for k in sorted(k[7:] for k in g.files if k.startswith("render/")):
+        if k in {"valid_mask", "inside_sphere", "mid_inside_sphere", "sparse_sdf"}:
+            continue
+        problems.append(_mismatch(k, res[k], g["render/" + k], rtol=1e-3 if k == "smooth_error" else 1e-4,
+                                  atol_scale=1e-5, outlier_frac=JUMPY.get(k, 0.0)))
+    problems = [p for p in problems if p]
+    assert not problems, "\n".join(problems)
+
+
 def test_render_is_chunk_invariant_and_masks_force_far(setup):
     """Property tests at ray counts the oracle cannot reach: per-ray outputs do not depend on how rays are
     batched, and rays that never enter a mask volume composite to zero weight."""
@@ -97,7 +138,8 @@ def test_render_is_chunk_invariant_and_masks_force_far(setup):
         half = surf.render(ro[:300], rd[:300], scene.near, scene.far, volumes, masks, scene.imgs, scene.features,
                            scene.features, scene.intrs, scene.c2ws, 1.0, None)
     for k in ("color_fine", "weights", "render_depth", "normal"):
-        assert torch.allclose(full[k][:300], half[k], rtol=1e-4, atol=1e-5), k
+        # different batch sizes pick different SGEMM tilings: same tolerance model as against the golden
+        _check(k, full[k][:300], half[k].cpu().numpy(), atol_scale=1e-5, outlier_frac=max(JUMPY.get(k, 0.0), 2e-3))
     empty = [torch.zeros_like(m) for m in masks]
     with torch.no_grad():
         none = surf.render(ro[:64], rd[:64], scene.near, scene.far, volumes, empty, scene.imgs, scene.features,
