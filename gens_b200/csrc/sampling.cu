@@ -383,6 +383,7 @@ extern "C" int gens_unpack_volume(const float* src_channels_last, float* dst_ncd
 
 extern "C" int gens_mask_nearest(const float* pts, long long n, const gens_pyramid_t* masks, int aten_cuda_flavour,
                                  uint8_t* any_out, float* each_out, void* stream) {
+    if (n == 0) return 0;
     GENS_CHECK_ARG(pts && masks && n >= 0 && (any_out || each_out));
     if (masks->n_scales <= 0 || masks->n_scales > GENS_MAX_SCALES) return GENS_E_UNSUPPORTED;
     if (n == 0) return 0;
@@ -399,6 +400,7 @@ extern "C" int gens_mask_nearest(const float* pts, long long n, const gens_pyram
 }
 
 extern "C" int gens_trilinear_fwd(const float* pts, long long n, const gens_pyramid_t* vols, float* out, void* stream) {
+    if (n == 0) return 0;
     GENS_CHECK_ARG(pts && out && n >= 0);
     Pyr p;
     if (!fill_pyr(vols, p)) return GENS_E_BADARG;
@@ -409,6 +411,7 @@ extern "C" int gens_trilinear_fwd(const float* pts, long long n, const gens_pyra
 
 extern "C" int gens_trilinear_bwd(const float* pts, long long n, const gens_pyramid_t* vols, const float* g_out,
                                   float* g_pts, const gens_pyramid_t* g_vols, void* stream) {
+    if (n == 0) return 0;
     GENS_CHECK_ARG(pts && g_out && n >= 0 && (g_pts || g_vols));
     Pyr p;
     if (!fill_pyr(vols, p)) return GENS_E_BADARG;
@@ -422,6 +425,7 @@ extern "C" int gens_trilinear_bwd(const float* pts, long long n, const gens_pyra
 extern "C" int gens_trilinear_bwd2(const float* pts, long long n, const gens_pyramid_t* vols, const float* g_out,
                                    const float* gg_pts, float* gg_out, float* g2_pts, const gens_pyramid_t* g2_vols,
                                    void* stream) {
+    if (n == 0) return 0;
     GENS_CHECK_ARG(pts && g_out && gg_pts && gg_out && g2_pts && n >= 0);
     Pyr p;
     if (!fill_pyr(vols, p)) return GENS_E_BADARG;
@@ -435,6 +439,7 @@ extern "C" int gens_trilinear_bwd2(const float* pts, long long n, const gens_pyr
 
 extern "C" int gens_trilinear_fwd_jvp(const float* pts, long long n, const gens_pyramid_t* vols, const float* u3,
                                       float* out, float* dout, void* stream) {
+    if (n == 0) return 0;
     GENS_CHECK_ARG(pts && out && dout && u3 && n >= 0);
     Pyr p;
     if (!fill_pyr(vols, p)) return GENS_E_BADARG;
@@ -446,6 +451,7 @@ extern "C" int gens_trilinear_fwd_jvp(const float* pts, long long n, const gens_
 
 extern "C" int gens_trilinear_vjp2(const float* pts, long long n, const gens_pyramid_t* vols, const float* u3,
                                    const float* g_f, const float* dg_f, float* grad, float* smooth, void* stream) {
+    if (n == 0) return 0;
     GENS_CHECK_ARG(pts && g_f && dg_f && grad && u3 && n >= 0);
     Pyr p;
     if (!fill_pyr(vols, p)) return GENS_E_BADARG;

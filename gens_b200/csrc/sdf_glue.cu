@@ -160,6 +160,7 @@ decode_kernel(const float* __restrict__ pts, const float* __restrict__ feats, co
 extern "C" int gens_sdf_encode(const float* pts, const float* feats, const float* dfeats, long long n, float scale,
                                const float* u3, int multires, int feat_multires, int n_feat, float* pos, float* fe,
                                void* stream) {
+    if (n == 0) return 0;
     GENS_CHECK_ARG(pts && feats && dfeats && u3 && pos && fe && n >= 0 && n_feat > 0);
     if (n == 0) return 0;
     const long long total = n * (3 + n_feat);
@@ -171,6 +172,7 @@ extern "C" int gens_sdf_encode(const float* pts, const float* feats, const float
 extern "C" int gens_sdf_act_fwd(const float* y, const float* featpart, int ld_featpart, const float* bias, long long n,
                                 int fan_out, float beta, float out_scale, float* x_out, int ld_x, float* sp1, float* sp2da,
                                 void* stream) {
+    if (n == 0) return 0;
     GENS_CHECK_ARG(y && bias && x_out && sp1 && sp2da && n >= 0 && fan_out > 0 && ld_x >= fan_out);
     if (n == 0) return 0;
     act_fwd_kernel<<<ceil_div_i(n * fan_out, 256), 256, 0, (cudaStream_t)stream>>>(
@@ -188,6 +190,7 @@ extern "C" int gens_copy_scaled(const float* src, int width, long long rows, flo
 
 extern "C" int gens_sdf_act_bwd(const float* g, int ld_g, float in_scale, const float* sp1, const float* sp2da,
                                 long long n, int fan_out, float* ga, int ld_ga, void* stream) {
+    if (n == 0) return 0;
     GENS_CHECK_ARG(g && sp1 && sp2da && ga && n >= 0 && fan_out > 0 && ld_g >= fan_out && ld_ga >= fan_out);
     if (n == 0) return 0;
     act_bwd_kernel<<<ceil_div_i(n * fan_out, 256), 256, 0, (cudaStream_t)stream>>>(g, ld_g, in_scale, sp1, sp2da, n,
@@ -199,6 +202,7 @@ extern "C" int gens_sdf_decode(const float* pts, const float* feats, const float
                                const float* g_fe, long long n, float scale, const float* u3, int multires,
                                int feat_multires, int n_feat, float* g_f, float* dg_f, float* grad, float* smooth,
                                void* stream) {
+    if (n == 0) return 0;
     GENS_CHECK_ARG(pts && feats && dfeats && g_pos && g_fe && u3 && g_f && dg_f && grad && smooth && n >= 0);
     if (n == 0) return 0;
     const long long total = n * (3 + n_feat);

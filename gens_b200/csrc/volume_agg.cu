@@ -627,3 +627,38 @@ extern "C" int gens_volume_agg_bwd(const float* feat_padded, int nv, int H, int 
                                                            channel_stride, e, grad_volume, gfeat);
     return gens_launch_status();
 }
+
+// ---- multi-GPU: scatter an all-gathered, rank-major slab buffer into the final NCDHW tensors --------
+namespace {
+// recv: per rank r a block of `rank_stride` floats; inside it, at `scale_off`, 9 channel planes of
+// (planes, D, D) floats (8 volume channels then the mask).  One thread moves one float4.
+__global__ void __launch_bounds__(256)
+unpack_slabs_kernel(const float4* __restrict__ recv, long long rank_stride4, long long scale_off4, int D, int planes,
+                    float4* __restrict__ volume, float4* __restrict__ mask, long long total4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const long long plane4 = (long long)D * D / 4;             // float4s per tensor plane
+    const long long chan4 = plane4 * D;                         // float4s per full channel
+    const int ch = (int)(i / chan4);
+    const long long rem = i % chan4;
+    const int a = (int)(rem / plane4);
+    const int r = a / planes;
+    const long long src = (long long)r * rank_stride4 + scale_off4 + ((long long)ch * planes + (a - r * planes)) * plane4 +
+                          rem % plane4;
+    const float4 v = __ldcs(recv + src);
+    if (ch < 8) __stcs(volume + i, v);
+    else __stcs(mask + (i - 8 * chan4), v);
+}
+}  // namespace
+
+extern "C" int gens_unpack_slabs(const float* recv, int world, long long rank_stride, long long scale_off, int D,
+                                 float* volume, float* mask_volume, void* stream) {
+    GENS_CHECK_ARG(recv && volume && mask_volume && world > 0 && D > 0);
+    if (D % world != 0 || ((long long)D * D) % 4 != 0 || rank_stride % 4 != 0 || scale_off % 4 != 0)
+        return GENS_E_UNSUPPORTED;
+    const long long total4 = 9LL * D * D * D / 4;
+    unpack_slabs_kernel<<<ceil_div_i(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(recv), rank_stride / 4, scale_off / 4, D, D / world,
+        reinterpret_cast<float4*>(volume), reinterpret_cast<float4*>(mask_volume), total4);
+    return gens_launch_status();
+}

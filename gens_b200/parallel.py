@@ -49,12 +49,54 @@ def gather_slabs(slab: torch.Tensor, d: int, world: int, group=None) -> torch.Te
     return torch.cat(pieces, dim=0).permute(1, 0, 2, 3).reshape(1, c, d, d, d).contiguous()
 
 
+def gather_slabs_inplace(full: torch.Tensor, d: int, rank: int, world: int, group=None) -> torch.Tensor:
+    """`full` (1,C,D,D,D) already holds this rank's planes [a0,a1) of every channel; fill in the rest.
+    In NCDHW every channel plane is the rank-ordered concatenation of the slabs, so one IN-PLACE
+    all-gather per channel (input = the rank's chunk of the output) assembles the tensor with no staging
+    copy; the C x S collectives of a build are issued as one coalesced NCCL group."""
+    if world == 1:
+        return full
+    if d % world != 0:
+        raise RuntimeError("in-place slab gather needs D divisible by the number of ranks")
+    a0, a1 = slab_bounds(d, rank, world)
+    for c in range(full.shape[1]):
+        dist.all_gather_into_tensor(full[0, c], full[0, c, a0:a1], group=group)
+    return full
+
+
 def sharded_agg_mean_var(volume_module, features, intrs, c2ws, rank: int, world: int, min_vis_view: int = 1,
                          group=None):
-    """Slab-sharded Volume.agg_mean_var + all-gather; same return value as the single-GPU call."""
+    """Slab-sharded Volume.agg_mean_var + all-gather; same return value as the single-GPU call.
+
+    When every D divides by the world size, K1 writes all scales' slabs (8 channels + mask each) straight
+    into ONE contiguous send buffer, a single all-gather moves it, and one scatter kernel per scale
+    (gens_unpack_slabs) lays the rank-major blocks out as the final NCDHW tensors."""
+    from . import _lib
     from .volume import agg_mean_var
     dims = volume_module.volume_dims
     slabs = [slab_bounds(d, rank, world) for d in dims]
+    if all(d % world == 0 and (d * d) % 4 == 0 for d in dims) and features[0].is_cuda:
+        dev = features[0].device
+        sizes = [9 * (d // world) * d * d for d in dims]
+        offs = [0]
+        for sz in sizes:
+            offs.append(offs[-1] + (sz + 3) // 4 * 4)
+        stride = offs[-1]
+        send = torch.empty(stride, device=dev, dtype=torch.float32)
+        outs = []
+        for d, off in zip(dims, offs):
+            p = d // world
+            outs.append((send[off: off + 8 * p * d * d].view(1, 8, p, d, d),
+                         send[off + 8 * p * d * d: off + 9 * p * d * d].view(1, 1, p, d, d)))
+        agg_mean_var(features, intrs, c2ws, dims, min_vis_view, slabs, volume_module.div_mode, outs=outs)
+        recv = torch.empty(world * stride, device=dev, dtype=torch.float32)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        vols = [torch.empty((1, 8, d, d, d), device=dev, dtype=torch.float32) for d in dims]
+        masks = [torch.empty((1, 1, d, d, d), device=dev, dtype=torch.float32) for d in dims]
+        for d, off, v, m in zip(dims, offs, vols, masks):
+            _lib.check(_lib.lib().gens_unpack_slabs(_lib.ptr(recv), world, stride, off, d, _lib.ptr(v), _lib.ptr(m),
+                                                    _lib.stream_ptr(dev)), "gens_unpack_slabs")
+        return vols, masks
     vols, masks = agg_mean_var(features, intrs, c2ws, dims, min_vis_view, slabs, volume_module.div_mode)
     full_v = [gather_slabs(v, d, world, group) for v, d in zip(vols, dims)]
     full_m = [gather_slabs(m, d, world, group) for m, d in zip(masks, dims)]

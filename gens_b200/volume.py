@@ -74,7 +74,7 @@ class _AggMeanVar(torch.autograd.Function):
     no_grad in the reference, volume.py:27-44)."""
 
     @staticmethod
-    def forward(ctx, w2c, intrs, dims, slabs, min_vis_view, div_mode, *features):
+    def forward(ctx, w2c, intrs, dims, slabs, min_vis_view, div_mode, outs, *features):
         dev = features[0].device
         packed = pack_feature_pyramid(features)
         nv = features[0].shape[0]
@@ -84,8 +84,11 @@ class _AggMeanVar(torch.autograd.Function):
         for i, d in enumerate(dims):
             a0, a1 = slabs[i]
             planes = a1 - a0
-            vol = torch.empty((1, 8, planes, d, d), device=dev, dtype=torch.float32)
-            msk = torch.empty((1, 1, planes, d, d), device=dev, dtype=torch.float32)
+            if outs is None:
+                vol = torch.empty((1, 8, planes, d, d), device=dev, dtype=torch.float32)
+                msk = torch.empty((1, 1, planes, d, d), device=dev, dtype=torch.float32)
+            else:  # caller-provided slab buffers (views into the all-gather send buffer)
+                vol, msk = outs[i]
             grid = voxel_axis(d, dev)
             sc = scales[i]
             sc.feat_padded = packed[i].data_ptr()
@@ -114,7 +117,7 @@ class _AggMeanVar(torch.autograd.Function):
         out = []
         for i, d in enumerate(dims):
             g_vol = grads[i]
-            if g_vol is None or not ctx.needs_input_grad[6 + i]:
+            if g_vol is None or not ctx.needs_input_grad[7 + i]:
                 out.append(None)
                 continue
             g_vol = _lib.f32c(g_vol)
@@ -129,18 +132,22 @@ class _AggMeanVar(torch.autograd.Function):
             _lib.check(_lib.lib().gens_unpack_feature_grads(_lib.ptr(g_pad), _lib.ptr(g_nchw), nv, h, w,
                                                             _lib.stream_ptr(dev)), "gens_unpack_feature_grads")
             out.append(g_nchw)
-        return (None, None, None, None, None, None, *out)
+        return (None, None, None, None, None, None, None, *out)
 
 
 def agg_mean_var(features, intrs, c2ws, dims, min_vis_view: int = 1,
-                 slabs: Optional[Sequence[Tuple[int, int]]] = None, div_mode: int = DEFAULT_DIV_MODE):
+                 slabs: Optional[Sequence[Tuple[int, int]]] = None, div_mode: int = DEFAULT_DIV_MODE,
+                 outs=None):
     """The 5-scale build.  `slabs[i] = (a0, a1)` restricts scale i to planes of tensor dim 2 (the
-    multi-GPU sharding); default = full volumes.  Returns (volumes, mask_volumes) as the reference."""
+    multi-GPU sharding); default = full volumes.  `outs[i] = (vol, mask)` lets the caller provide the
+    (contiguous, fp32) output buffers, e.g. views into an all-gather send buffer.
+    Returns (volumes, mask_volumes) as the reference."""
     _lib.require_cuda(intrs, c2ws, *features[:len(dims)])
     w2c = _lib.f32c(torch.inverse(c2ws))  # same op as the reference (volume.py:34): bit-identical matrices
     k = _lib.f32c(intrs)
     slabs = [(0, d) for d in dims] if slabs is None else list(slabs)
-    out = _AggMeanVar.apply(w2c, k, tuple(dims), tuple(slabs), min_vis_view, div_mode, *features[:len(dims)])
+    out = _AggMeanVar.apply(w2c, k, tuple(dims), tuple(slabs), min_vis_view, div_mode, outs,
+                            *features[:len(dims)])
     n = len(dims)
     return list(out[:n]), list(out[n:])
 

@@ -85,6 +85,12 @@ int gens_volume_agg_fwd(const float *feat_padded, int nv, int H, int W, const fl
 int gens_pack_feature_maps_multi(const float *const *src_nchw, float *const *dst_padded,
                                  const int *h, const int *w, int n_scales, int n, void *stream);
 
+/* Multi-GPU assembly: after ONE all-gather of the per-rank slab buffers (rank-major, `rank_stride`
+ * floats per rank; at `scale_off` inside each block the 8 volume channels + mask of this scale as
+ * (9, D/world, D, D)), scatter one scale into the final NCDHW tensors (1,8,D,D,D) / (1,1,D,D,D). */
+int gens_unpack_slabs(const float *recv, int world, long long rank_stride, long long scale_off, int D,
+                      float *volume, float *mask_volume, void *stream);
+
 /* Debug/parity view of K1's projection stage: per (view, voxel) the floor corner index of
  * the bilinear footprint and the validity bit (volume.py:43).  Outputs are (nv, D,D,D);
  * ix0/iy0 are 0 where the view is invalid. */

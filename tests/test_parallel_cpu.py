@@ -40,6 +40,14 @@ def _worker(rank, world, port, golden_dir, out_q):
             got_v = parallel.gather_slabs(slab_v, d, world)
             got_m = parallel.gather_slabs(slab_m, d, world)
             ok &= np.array_equal(got_v[0].numpy(), full_v) and np.array_equal(got_m[0, 0].numpy(), full_m)
+        # in-place per-channel gather (the NCCL path of sharded_agg_mean_var): slab already sits in the full tensor
+        d = 8
+        ref = torch.arange(3 * d ** 3, dtype=torch.float32).reshape(1, 3, d, d, d)
+        full = torch.full_like(ref, -1.0)
+        a0, a1 = parallel.slab_bounds(d, rank, world)
+        full[:, :, a0:a1] = ref[:, :, a0:a1]
+        parallel.gather_slabs_inplace(full, d, rank, world)
+        ok &= torch.equal(full, ref)
         n = 1001
         lo, hi = parallel.shard_range(n, rank, world)
         rays = torch.arange(n, dtype=torch.float32)[:, None].repeat(1, 3)
