@@ -103,6 +103,55 @@ def lookup_volume(pts, volumes, sample_mode="grad"):
     return torch.cat(outs, -1)
 
 
+# ---- the reference's three-level autograd of the volume look-up, in ATen ops --------------------
+def _cat_dd(vols, pts):
+    return torch.cat([trilinear_dd(v, pts) for v in vols], -1)
+
+
+class _RefLookup(torch.autograd.Function):
+    """Forward of cug.grid_sample_3d over a list of volumes (cuda_gridsample.py:71-91)."""
+
+    @staticmethod
+    def forward(ctx, pts, *vols):
+        ctx.save_for_backward(pts, *vols)
+        with torch.no_grad():
+            return _cat_dd(vols, pts)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        pts, *vols = ctx.saved_tensors
+        res = _RefLookupBackward.apply(g_out, pts, *vols)
+        return (res[0], *res[1:])
+
+
+class _RefLookupBackward(torch.autograd.Function):
+    """aten::grid_sampler_3d_backward, whose own backward is the reference's grad2_3d: its results
+    carry NO grad_fn (cuda_gridsample.py:110-123), i.e. third-order terms are dropped.  The oracle must
+    drop them too, otherwise training gradients would differ from the reference by those terms."""
+
+    @staticmethod
+    def forward(ctx, g_out, pts, *vols):
+        ctx.save_for_backward(g_out, pts, *vols)
+        with torch.enable_grad():
+            p = pts.detach().requires_grad_(True)
+            vs = [v.detach().requires_grad_(True) for v in vols]
+            y = _cat_dd(vs, p)
+            grads = torch.autograd.grad(y, [p] + vs, g_out.detach(), allow_unused=True)
+        return tuple(g.detach() if g is not None else torch.zeros_like(t) for g, t in zip(grads, [pts] + list(vols)))
+
+    @staticmethod
+    def backward(ctx, gg_pts, *gg_vols):
+        g_out, pts, *vols = ctx.saved_tensors
+        with torch.enable_grad():
+            go = g_out.detach().requires_grad_(True)
+            p = pts.detach().requires_grad_(True)
+            vs = [v.detach().requires_grad_(True) for v in vols]
+            y = _cat_dd(vs, p)
+            (g_pts,) = torch.autograd.grad(y, p, go, create_graph=True)
+            res = torch.autograd.grad((g_pts * gg_pts.detach()).sum(), [go, p] + vs, allow_unused=True)
+        return tuple(r.detach() if r is not None else None for r in res)
+
+
 # ---- ATen-on-CPU provider of the ray marcher's look-up ops ------------------------------------
 class CpuOps:
     """Drop-in for gens_b200.projector as the `ops` of gens_b200.implicit_surface.ImplicitSurface:
@@ -116,9 +165,9 @@ class CpuOps:
         vols = [volume] if isinstance(volume, torch.Tensor) else list(volume)
         pts = pts.reshape(-1, 3)
         if sample_mode == "grad":
-            if torch.is_grad_enabled() and pts.requires_grad:
-                # double-differentiable form (the reference needs its CUDA-only grad2 op for this)
-                return torch.cat([trilinear_dd(v, pts) for v in vols], -1)
+            if torch.is_grad_enabled() and (pts.requires_grad or any(v.requires_grad for v in vols)):
+                # the reference's three-level autograd (its CUDA-only grad2 op expressed in ATen ops)
+                return _RefLookup.apply(pts, *vols)
             return lookup_volume(pts, vols, "grad")
         return lookup_volume(pts, vols, "nearest")
 

@@ -1,0 +1,116 @@
+"""Config-3-shaped checks: the training graph (forward + losses + backward, incl. the second-order path
+through the SDF gradient) gives the same parameter / volume / feature gradients with the CUDA kernels as
+with the ATen-op oracle provider; validate()/forward()/sdf_grid drivers run and agree with direct calls."""
+import numpy as np
+import pytest
+import torch
+
+from gens_b200 import projector
+from gens_b200.config import gens_model_conf
+from gens_b200.implicit_surface import ImplicitSurface
+from gens_b200.synthetic import make_reg_volumes, make_scene
+from gens_b200.volume import Volume
+from oracle.torch_oracle import CpuOps
+from parity import check
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+DIMS = [16, 8, 4, 2, 2]
+
+
+def _loss(res):
+    # the loss terms that exercise every differentiable output (models/losses/loss.py:23-84, simplified weights)
+    return (res["color_fine"].abs().mean() + 0.1 * res["gradient_error"] + 0.01 * res["smooth_error"]
+            + 0.1 * res["tv_reg"] + 0.05 * torch.exp(-res["sparse_sdf"].abs() * 100).mean()
+            + 0.01 * res["sampled_gray_val"].abs().mean() + 0.01 * res["render_depth"].mean())
+
+
+def _run(surf, scene, volumes, masks, ro, rd, feats):
+    torch.manual_seed(5)
+    res = surf.render(ro, rd, scene.near, scene.far, volumes, masks, scene.imgs, feats, feats, scene.intrs,
+                      scene.c2ws, 0.7, 3)
+    loss = _loss(res)
+    loss.backward()
+    return loss
+
+
+def test_training_step_gradients_match_oracle_ops(cuda_lib):
+    nv = 5  # training uses 4 source views (confs/gens.conf:9)
+    scene = make_scene(64, 96, nv, seed=21)
+    conf = gens_model_conf(perturb=0.0)["implicit_surface"]
+    torch.manual_seed(0)
+    surf_c = ImplicitSurface(conf, ops=CpuOps)
+    surf_g = ImplicitSurface(conf).to(DEV)
+    surf_g.load_state_dict(surf_c.state_dict())
+    vols = make_reg_volumes(DIMS, seed=21)
+    masks = [torch.ones(1, 1, d, d, d) for d in DIMS]
+    ro, rd = scene.rays(step=8)
+    ro, rd = ro[::2][:24].contiguous(), rd[::2][:24].contiguous()
+
+    vc = [v.clone().requires_grad_(True) for v in vols]
+    fc = [f.clone().requires_grad_(True) for f in scene.features]
+    lc = _run(surf_c, scene, vc, masks, ro, rd, fc)
+
+    sg = scene.to(DEV)
+    vg = [v.clone().to(DEV).requires_grad_(True) for v in vols]
+    fg = [f.clone().to(DEV).requires_grad_(True) for f in scene.features]
+    projector.ATEN_CUDA_FLAVOUR = 0
+    try:
+        lg = _run(surf_g, sg, vg, [m.to(DEV) for m in masks], ro.to(DEV), rd.to(DEV), fg)
+    finally:
+        projector.ATEN_CUDA_FLAVOUR = 1
+    assert abs(lc.item() - lg.item()) <= 1e-4 * abs(lc.item()) + 1e-6
+    # gradients: 1e-3 relative to the tensor's scale (sums of ~3k samples through second-order terms)
+    for (name, pc), (_, pg) in zip(surf_c.named_parameters(), surf_g.named_parameters()):
+        if pc.grad is None:
+            assert pg.grad is None or float(pg.grad.abs().max()) == 0.0, name
+            continue
+        # absolute floor 5e-6: a few parameters (e.g. the scalar color_network.s) have gradients of that size
+        # that are sums of cancelling terms
+        check("grad " + name, pg.grad, pc.grad.numpy(), rtol=1e-3,
+              atol_scale=max(1e-3 * float(pc.grad.abs().max()), 5e-6))
+    for i, (a, b) in enumerate(zip(vg, vc)):
+        check(f"grad volume{i}", a.grad, b.grad.numpy(), rtol=1e-3, atol_scale=1e-3 * max(float(b.grad.abs().max()), 1e-12))
+    for i, (a, b) in enumerate(zip(fg, fc)):
+        if b.grad is not None:
+            check(f"grad feature{i}", a.grad, b.grad.numpy(), rtol=1e-3,
+                  atol_scale=1e-3 * max(float(b.grad.abs().max()), 1e-12))
+
+
+def test_validate_forward_and_sdf_grid_drivers(cuda_lib):
+    scene = make_scene(64, 96, 3, seed=4).to(DEV)
+    conf = gens_model_conf(perturb=0.0)["implicit_surface"]
+    torch.manual_seed(0)
+    surf = ImplicitSurface(conf).to(DEV)
+    dims = [32, 16, 8, 4, 2]
+    vols = [v.to(DEV) for v in make_reg_volumes(dims, seed=4)]
+    _, masks = Volume(volume_dims=dims).agg_mean_var(scene.features, scene.intrs, scene.c2ws)
+    ro, rd = scene.rays(step=4)  # 16 x 24 image
+    h, w = 16, 24
+    ipts = {"imgs": scene.imgs, "intrs": scene.intrs, "c2ws": scene.c2ws, "rays_o": ro, "rays_d": rd,
+            "near": scene.near, "far": scene.far, "bound_min": torch.tensor([-1.0, -1, -1], device=DEV),
+            "bound_max": torch.tensor([1.0, 1, 1], device=DEV), "hw": (h, w)}
+    with torch.no_grad():
+        torch.manual_seed(1)
+        out = surf.validate(ro, rd, scene.near, scene.far, vols, masks, scene.imgs, scene.features, scene.features,
+                            scene.intrs, scene.c2ws, ipts["bound_min"], ipts["bound_max"], (h, w),
+                            extract_geometry=False)
+        assert out["img_fine"].shape == (h, w, 3) and out["normal_img"].shape == (h, w, 3)
+        assert out["sdf_depth"].shape == (h, w) and out["render_depth"].shape == (h, w)
+        surf.val_chunk = 4096  # one big chunk must give the same image as the reference's 256-ray split
+        torch.manual_seed(1)
+        big = surf.validate(ro, rd, scene.near, scene.far, vols, masks, scene.imgs, scene.features, scene.features,
+                            scene.intrs, scene.c2ws, ipts["bound_min"], ipts["bound_max"], (h, w),
+                            extract_geometry=False)
+        assert np.allclose(big["img_fine"], out["img_fine"], atol=0.05)
+        # train-mode forward with pseudo points (implicit_surface.py:489-497)
+        ipts["pseudo_pts"] = torch.rand(200, 3, device=DEV) * 0.6 - 0.3
+        res = surf("train", {**ipts, "rays_o": ro[:64], "rays_d": rd[:64]}, vols, masks, scene.features,
+                   scene.features, 1.0, 10)
+        assert res["pseudo_sdf"].shape == (200, 1) and len(res) == 19
+        # lattice query in blocks == direct evaluation
+        u = surf.sdf_grid(vols, ipts["bound_min"], ipts["bound_max"], 40, block=16)
+        axes = torch.linspace(-1, 1, 40, device=DEV)
+        pts = torch.stack(torch.meshgrid(axes, axes, axes, indexing="ij"), -1).reshape(-1, 3)
+        direct = -surf.sdf_network.sdf_nograd(pts, vols).reshape(40, 40, 40)
+        assert torch.allclose(u, direct, rtol=1e-4, atol=1e-5)
