@@ -46,7 +46,22 @@ def make_pyramid(tensors, dims):
     return p
 
 
+class ImagePyramid(ctypes.Structure):
+    """Mirror of gens_image_pyramid_t."""
+    _fields_ = [("map", _vp * MAX_SCALES), ("h", _i * MAX_SCALES), ("w", _i * MAX_SCALES), ("n_scales", _i)]
+
+
+def make_image_pyramid(tensors, sizes):
+    p = ImagePyramid()
+    for i, (t, (h, w)) in enumerate(zip(tensors, sizes)):
+        p.map[i] = t.data_ptr() if t is not None else None
+        p.h[i], p.w[i] = int(h), int(w)
+    p.n_scales = len(tensors)
+    return p
+
+
 _PP = ctypes.POINTER(Pyramid)
+_IP = ctypes.POINTER(ImagePyramid)
 
 _SIGNATURES = {
     "gens_abi_version": ([], _i),
@@ -72,6 +87,10 @@ _SIGNATURES = {
     "gens_copy_scaled": ([_vp, _i, _ll, _f, _vp, _i, _i, _vp], _i),
     "gens_sdf_act_bwd": ([_vp, _i, _f, _vp, _vp, _ll, _i, _vp, _i, _vp], _i),
     "gens_sdf_decode": ([_vp, _vp, _vp, _vp, _vp, _ll, _f, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
+    "gens_pack_nhwc4": ([_vp, _vp, _i, _i, _i, _i, _vp], _i),
+    "gens_unpack_nhwc4": ([_vp, _vp, _i, _i, _i, _i, _vp], _i),
+    "gens_lookup_feature_fwd": ([_vp, _ll, _i, _vp, _vp, _vp, _vp, _IP, _vp, _i, _vp, _vp, _vp, _vp], _i),
+    "gens_lookup_feature_bwd": ([_vp, _ll, _i, _vp, _vp, _IP, _i, _vp, _IP, _vp], _i),
     "gens_debug_set_variant": ([_i], _i),
     "gens_selftest_division": ([_i, ctypes.c_ulonglong, _vp, _vp], _i),
 }

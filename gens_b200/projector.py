@@ -173,53 +173,85 @@ def lookup_volume(pts: torch.Tensor, volume: Union[torch.Tensor, Sequence[torch.
     raise RuntimeError(f"gens_b200: unsupported sample_mode {sample_mode!r}")
 
 
-# ---- source-view reprojection (reference projector.py:278-349) --------------------------------
-def compute_angle(pts, ref_c2w, src_c2ws):
-    """IBRNet ray-direction difference features (n, ns, 4): unit (ref_dir - src_dir) and their dot."""
-    to_ref = ref_c2w[:3, 3][None, None, :] - pts[None, :, :]
-    to_ref = to_ref / (torch.norm(to_ref, dim=-1, keepdim=True) + 1e-6)
-    to_src = src_c2ws[:, :3, 3][:, None, :] - pts[None, :, :]
-    to_src = to_src / (torch.norm(to_src, dim=-1, keepdim=True) + 1e-6)
-    diff = to_ref - to_src
-    diff_dir = diff / torch.clamp(torch.norm(diff, dim=-1, keepdim=True), min=1e-6)
-    dot = (to_ref * to_src).sum(dim=-1, keepdim=True)
-    return torch.cat([diff_dir, dot], dim=-1).permute(1, 0, 2).contiguous()
+# ---- source-view reprojection (reference projector.py:278-349): K6 -----------------------------
+def _pack_nhwc4(t: torch.Tensor) -> torch.Tensor:
+    """(n,c,h,w), c in {3,4} -> channels-last (n,h,w,4)."""
+    t = _lib.f32c(t)
+    n, c, h, w = t.shape
+    out = torch.empty((n, h, w, 4), device=t.device, dtype=torch.float32)
+    _lib.check(_lib.lib().gens_pack_nhwc4(_lib.ptr(t), _lib.ptr(out), n, c, h, w, _lib.stream_ptr(t.device)),
+               "gens_pack_nhwc4")
+    return out
+
+
+class _LookupFeature(torch.autograd.Function):
+    """One launch for all source views and scales; differentiable w.r.t. the feature maps only (the
+    sampling grid is under no_grad in the reference, projector.py:318-334)."""
+
+    @staticmethod
+    def forward(ctx, pts, w2c_src, k_src, c2w_ref, c2w_src, imgs_src, *feats):
+        n, ns = pts.shape[0], k_src.shape[0]
+        dev = pts.device
+        packed = [_pack_nhwc4(f[1:]) for f in feats]
+        rgb = _pack_nhwc4(imgs_src)
+        sizes = [(f.shape[2], f.shape[3]) for f in feats]
+        pyr = _lib.make_image_pyramid(packed, sizes)
+        width = 3 + 4 * len(feats)
+        out = torch.empty((n, ns, width), device=dev, dtype=torch.float32)
+        ray_diff = torch.empty((n, ns, 4), device=dev, dtype=torch.float32)
+        mask = torch.empty((n, ns), device=dev, dtype=torch.uint8)
+        _lib.check(_lib.lib().gens_lookup_feature_fwd(
+            _lib.ptr(pts), n, ns, _lib.ptr(w2c_src), _lib.ptr(k_src), _lib.ptr(c2w_ref), _lib.ptr(c2w_src), pyr,
+            _lib.ptr(rgb), ATEN_CUDA_FLAVOUR, _lib.ptr(out), _lib.ptr(ray_diff), _lib.ptr(mask),
+            _lib.stream_ptr(dev)), "gens_lookup_feature_fwd")
+        ctx.save_for_backward(pts, w2c_src, k_src, *packed)
+        ctx.shapes = [tuple(f.shape) for f in feats]
+        ctx.flavour = ATEN_CUDA_FLAVOUR
+        mask = mask.bool()
+        ctx.mark_non_differentiable(ray_diff, mask)
+        return out, ray_diff, mask
+
+    @staticmethod
+    def backward(ctx, g_out, _g_rd, _g_mask):
+        pts, w2c_src, k_src, *packed = ctx.saved_tensors
+        n, ns = pts.shape[0], k_src.shape[0]
+        dev = pts.device
+        g_out = _lib.f32c(g_out)
+        need = ctx.needs_input_grad[6:]
+        g_cl = [torch.zeros_like(p) if nd else None for p, nd in zip(packed, need)]
+        sizes = [(sh[2], sh[3]) for sh in ctx.shapes]
+        if any(need):
+            _lib.check(_lib.lib().gens_lookup_feature_bwd(
+                _lib.ptr(pts), n, ns, _lib.ptr(w2c_src), _lib.ptr(k_src), _lib.make_image_pyramid(packed, sizes),
+                ctx.flavour, _lib.ptr(g_out), _lib.make_image_pyramid(g_cl, sizes), _lib.stream_ptr(dev)),
+                "gens_lookup_feature_bwd")
+        grads = []
+        for g, sh in zip(g_cl, ctx.shapes):
+            if g is None:
+                grads.append(None)
+                continue
+            full = torch.zeros(sh, device=dev, dtype=torch.float32)  # the reference view (index 0) gets no gradient
+            src = torch.empty((sh[0] - 1,) + sh[1:], device=dev, dtype=torch.float32)
+            _lib.check(_lib.lib().gens_unpack_nhwc4(_lib.ptr(g), _lib.ptr(src), sh[0] - 1, sh[1], sh[2], sh[3],
+                                                    _lib.stream_ptr(dev)), "gens_unpack_nhwc4")
+            full[1:] = src
+            grads.append(full)
+        return (None, None, None, None, None, None, *grads)
 
 
 def lookup_feature(pts, imgs, intrs, c2ws, features):
     """Project points into every source view at every scale, sample RGB (scale 0) and features.
     Returns ((n,ns,3+sum c), (n,ns,4), (n,ns) bool) exactly as the reference (projector.py:294-349):
     align-corners normalisation, align_corners=False sampling, no epsilon in the perspective divide."""
-    import torch.nn.functional as F
     if not isinstance(features, (list, tuple)):
         features = [features]
-    src_k, src_c2w, ref_c2w = intrs[1:], c2ws[1:], c2ws[0]
-    ray_diff = compute_angle(pts, ref_c2w, src_c2w)
-    ns, n = src_k.shape[0], pts.shape[0]
-    homo = torch.cat([pts.t(), pts.new_ones(1, n)], dim=0)  # (4,n)
-    w2c = torch.inverse(src_c2w)
-    sampled, masks = [], []
-    rgb = None
-    for i, feat in enumerate(features):
-        with torch.no_grad():
-            k = src_k.clone()
-            k[:, :2] = k[:, :2] * (0.5 ** i)
-            h, w = feat.shape[-2:]
-            cam = torch.matmul(w2c, homo[None])[:, :3]
-            img = torch.matmul(k[:, :3, :3], cam)
-            xy = img[:, :2] / img[:, 2:]
-            nx = xy[:, 0] / ((w - 1) / 2) - 1
-            ny = xy[:, 1] / ((h - 1) / 2) - 1
-            ok = (img[:, 2] > 0) & (xy[:, 0] >= 0) & (xy[:, 0] < w) & (xy[:, 1] >= 0) & (xy[:, 1] < h)
-            masks.append(ok.t())
-            grid = torch.stack([nx, ny], dim=-1).unsqueeze(2)  # (ns,n,1,2)
-        f = F.grid_sample(feat[1:], grid, mode="bilinear", padding_mode="zeros", align_corners=False)
-        sampled.append(f.reshape(ns, feat.shape[1], n).permute(2, 0, 1))
-        if i == 0:
-            c = F.grid_sample(imgs[1:], grid, mode="bilinear", padding_mode="zeros", align_corners=False)
-            rgb = c.reshape(ns, 3, n).permute(2, 0, 1)
-    mask = torch.stack(masks, dim=-1).all(dim=-1)
-    return torch.cat([rgb] + sampled, dim=2).float().contiguous(), ray_diff, mask.contiguous()
+    _lib.require_cuda(pts, imgs, intrs, c2ws, *features)
+    if any(f.shape[1] != 4 for f in features) or imgs.shape[1] != 3:
+        raise RuntimeError("gens_b200.lookup_feature is built for 4-channel feature maps and RGB images")
+    p = _lib.f32c(pts.reshape(-1, 3))
+    w2c_src = _lib.f32c(torch.inverse(c2ws[1:]))  # same op as the reference (projector.py:322)
+    k_src = _lib.f32c(intrs[1:])
+    return _LookupFeature.apply(p, w2c_src, k_src, _lib.f32c(c2ws[0]), _lib.f32c(c2ws[1:]), imgs[1:], *features)
 
 
 # ---- feature-metric consistency patches (reference projector.py:353-437) ------------------------

@@ -148,6 +148,35 @@ int gens_trilinear_bwd2(const float *pts, long long n, const gens_pyramid_t *vol
                         const float *g_out, const float *gg_pts, float *gg_out, float *g2_pts,
                         const gens_pyramid_t *g2_vols, void *stream);
 
+/* ---- K6: source-view reprojection sampling ----------------------------------------------
+ * Replaces projector.lookup_feature + compute_angle (reference models/modules/projector.py:278-349). */
+typedef struct gens_image_pyramid {
+    const float *map[GENS_MAX_SCALES]; /* per scale: channels-last (n_src, h, w, 4) device pointer */
+    int h[GENS_MAX_SCALES], w[GENS_MAX_SCALES];
+    int n_scales;
+} gens_image_pyramid_t;
+
+/* (n,c,h,w) NCHW with c in {3,4} -> channels-last (n,h,w,4) (4th channel 0 for RGB), and back. */
+int gens_pack_nhwc4(const float *src_nchw, float *dst_nhwc4, int n, int c, int h, int w, void *stream);
+int gens_unpack_nhwc4(const float *src_nhwc4, float *dst_nchw, int n, int c, int h, int w, void *stream);
+
+/* For every (point, source view): feat_out (n, n_src, 3+4S) = [rgb, f_0..f_{S-1}] sampled bilinearly
+ * (align_corners=False, zeros padding), raydiff_out (n, n_src, 4), mask_out (n, n_src) uint8 = visible at
+ * every scale.  w2c_src = inverse(c2ws[1:]), k_src = intrs[1:] (4x4 each, rows 0-1 scaled by 0.5^i in the
+ * kernel), c2w_ref = c2ws[0], c2w_src = c2ws[1:].  aten_cuda_flavour as for gens_mask_nearest /
+ * GENS_DIV_RECIP. */
+int gens_lookup_feature_fwd(const float *pts, long long n, int n_src, const float *w2c_src,
+                            const float *k_src, const float *c2w_ref, const float *c2w_src,
+                            const gens_image_pyramid_t *feats, const float *rgb_nhwc4,
+                            int aten_cuda_flavour, float *feat_out, float *raydiff_out,
+                            uint8_t *mask_out, void *stream);
+/* Backward w.r.t. the feature maps (the sampling grid is under no_grad in the reference): scatter
+ * g_feat (n, n_src, 3+4S) into zero-initialised channels-last gradient maps g_feats (NULL entries skipped). */
+int gens_lookup_feature_bwd(const float *pts, long long n, int n_src, const float *w2c_src,
+                            const float *k_src, const gens_image_pyramid_t *feats,
+                            int aten_cuda_flavour, const float *g_feat,
+                            const gens_image_pyramid_t *g_feats, void *stream);
+
 /* ---- analytic SDF pass (value, gradient, second-order term without an autograd graph) ----
  * Replaces the two nested torch.autograd.grad(create_graph=True) calls of SDFNetwork.gradient
  * (reference models/modules/sdf_network.py:131-153) in no-grad rendering.  Every work matrix has 2n
