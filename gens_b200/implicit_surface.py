@@ -72,6 +72,7 @@ class ImplicitSurface(nn.Module):
         self.deviation_network = SingleVarianceNetwork(**confs["variance_network"])
         self.val_chunk = 256  # rays per render() call in validate(); 256 = the reference's split
         self.analytic_nograd = True  # under torch.no_grad(): hand-differentiated SDF sweep instead of autograd
+        self.fused_upsample = True   # K5 warp-per-ray kernels for up_sample / cat_z_vals (CUDA tensors)
 
     # ------------------------------------------------------------------ hierarchical sampling
     def _sdf_masked(self, pts, volumes, mask_volumes, folded=None):
@@ -83,6 +84,9 @@ class ImplicitSurface(nn.Module):
     def up_sample(self, rays_o, rays_d, z_vals, sdf, n_importance, mask_volumes, inv_s):
         """n_importance new depths per ray from the NeuS weights at a fixed inv_s (reference :60-109)."""
         b, m = z_vals.shape
+        if self.fused_upsample and self.ops is _cuda_ops and z_vals.is_cuda and m <= 128 and n_importance <= 32:
+            # K5: one warp per ray, shuffle prefix product, in-kernel inverse CDF (csrc/raymarch.cu)
+            return self.ops.upsample_rays(rays_o, rays_d, z_vals, sdf, mask_volumes, inv_s, n_importance)
         pts = rays_o[:, None, :] + rays_d[:, None, :] * z_vals[..., :, None]
         valid = self.ops.mask_nearest(pts.reshape(-1, 3), mask_volumes).reshape(b, m)
         both = valid[:, :-1] & valid[:, 1:]
@@ -103,6 +107,14 @@ class ImplicitSurface(nn.Module):
     def cat_z_vals(self, rays_o, rays_d, z_vals, new_z_vals, sdf, volumes, mask_volumes, last=False):
         """Merge the new depths into the sorted ray (reference :111-133)."""
         b = z_vals.shape[0]
+        if self.fused_upsample and self.ops is _cuda_ops and z_vals.is_cuda and z_vals.shape[1] <= 160 \
+                and new_z_vals.shape[1] <= 32:
+            new_sdf = None
+            if not last:
+                pts = (rays_o[:, None, :] + rays_d[:, None, :] * new_z_vals[..., :, None]).reshape(-1, 3)
+                new_sdf = self._sdf_masked(pts, volumes, mask_volumes, getattr(self, "_folded", None))
+            z_all, sdf_all = self.ops.merge_samples(z_vals, sdf, new_z_vals, new_sdf)
+            return z_all, (sdf if last else sdf_all)
         z_all, order = torch.sort(torch.cat([z_vals, new_z_vals], dim=-1), dim=-1)
         if not last:
             pts = (rays_o[:, None, :] + rays_d[:, None, :] * new_z_vals[..., :, None]).reshape(-1, 3)

@@ -295,3 +295,36 @@ def surface_patch_warp(pts_sdf0, gradients_sdf0, images, intrinsics, poses, patc
     ref = F.grid_sample(images[:1], torch.stack([px, py], -1).detach().view(1, -1, 1, 2), align_corners=True)
     ref = ref.view(1, -1, b, npx).permute(0, 2, 3, 1).contiguous()
     return ref, sampled
+
+
+# ---- K5: warp-per-ray hierarchical up-sampling (reference implicit_surface.py:60-133) --------------
+def upsample_rays(rays_o, rays_d, z_vals, sdf, mask_volumes, inv_s: float, n_new: int):
+    """up_sample + sample_pdf(det=True) fused, one warp per ray: (B,M) sorted depths/SDF -> (B,n_new)."""
+    _lib.require_cuda(rays_o, rays_d, z_vals, sdf)
+    b, m = z_vals.shape
+    ms = [_lib.f32c(v) for v in _as_list(mask_volumes)]
+    pyr = _lib.make_pyramid(ms, [v.shape[2] for v in ms])
+    out = torch.empty((b, n_new), device=z_vals.device, dtype=torch.float32)
+    _lib.check(_lib.lib().gens_upsample_rays(
+        _lib.ptr(_lib.f32c(rays_o)), _lib.ptr(_lib.f32c(rays_d)), _lib.ptr(_lib.f32c(z_vals)),
+        _lib.ptr(_lib.f32c(sdf.reshape(b, m))), b, m, pyr, ATEN_CUDA_FLAVOUR, float(inv_s), int(n_new), _lib.ptr(out),
+        _lib.stream_ptr(z_vals.device)), "gens_upsample_rays")
+    return out
+
+
+def merge_samples(z_vals, sdf, new_z, new_sdf=None):
+    """Merge ascending new depths into the sorted ray (the sort/gather of cat_z_vals); SDF follows if given."""
+    _lib.require_cuda(z_vals, new_z)
+    b, m = z_vals.shape
+    k = new_z.shape[1]
+    dev = z_vals.device
+    z_out = torch.empty((b, m + k), device=dev, dtype=torch.float32)
+    with_sdf = new_sdf is not None
+    sdf_out = torch.empty((b, m + k), device=dev, dtype=torch.float32) if with_sdf else None
+    sdf_c = _lib.f32c(sdf.reshape(b, m)) if with_sdf else None
+    nsdf_c = _lib.f32c(new_sdf.reshape(b, k)) if with_sdf else None
+    _lib.check(_lib.lib().gens_merge_samples(
+        _lib.ptr(_lib.f32c(z_vals)), _lib.ptr(sdf_c) if with_sdf else None, _lib.ptr(_lib.f32c(new_z)),
+        _lib.ptr(nsdf_c) if with_sdf else None, b, m, k, _lib.ptr(z_out), _lib.ptr(sdf_out) if with_sdf else None,
+        _lib.stream_ptr(dev)), "gens_merge_samples")
+    return z_out, sdf_out

@@ -177,6 +177,18 @@ int gens_lookup_feature_bwd(const float *pts, long long n, int n_src, const floa
                             int aten_cuda_flavour, const float *g_feat,
                             const gens_image_pyramid_t *g_feats, void *stream);
 
+/* ---- K5: hierarchical up-sampling, one warp per ray ----------------------------------------
+ * One iteration of the loop in ImplicitSurface.render (reference models/modules/implicit_surface.py:378-393).
+ * gens_upsample_rays = up_sample (:60-109) + sample_pdf(det=True) (:14-44): z_vals/sdf (n_rays, n_samples<=128)
+ * sorted along each ray, masks = the (D,D,D) fp32 mask pyramid, inv_s = 64*2^i; writes new_z (n_rays, n_new<=32).
+ * gens_merge_samples = the concat/sort/gather of cat_z_vals (:111-133): merges the (already ascending) new
+ * depths into the ray; sdf_out may be NULL (last iteration, only depths are needed). */
+int gens_upsample_rays(const float *rays_o, const float *rays_d, const float *z_vals, const float *sdf,
+                       int n_rays, int n_samples, const gens_pyramid_t *masks, int aten_cuda_flavour,
+                       float inv_s, int n_new, float *new_z, void *stream);
+int gens_merge_samples(const float *z_vals, const float *sdf, const float *new_z, const float *new_sdf,
+                       int n_rays, int n_samples, int n_new, float *z_out, float *sdf_out, void *stream);
+
 /* ---- analytic SDF pass (value, gradient, second-order term without an autograd graph) ----
  * Replaces the two nested torch.autograd.grad(create_graph=True) calls of SDFNetwork.gradient
  * (reference models/modules/sdf_network.py:131-153) in no-grad rendering.  Every work matrix has 2n

@@ -79,6 +79,30 @@ def test_up_sample_matches_reference(setup):
     _check("up_sample z", new_z, g["up_new_z"], atol_scale=1e-5)
 
 
+def test_k5_kernels_match_torch_path(setup):
+    """Warp-per-ray up-sampling / merge kernels vs the ATen-op formulation of the same methods, all four
+    iterations of the schedule (M = 64, 80, 96, 112), incl. rays that never hit a mask voxel."""
+    g, surf, scene, volumes, masks = setup
+    ro, rd = scene.rays(step=2)
+    with torch.no_grad():
+        z = scene.near + (scene.far - scene.near) * torch.linspace(0, 1, 64, device=DEV)[None, :]
+        z = z.repeat(ro.shape[0], 1).contiguous()
+        sdf = surf._sdf_masked((ro[:, None] + rd[:, None] * z[..., None]).reshape(-1, 3), volumes, masks).reshape(-1, 64)
+        for i in range(4):
+            surf.fused_upsample = True
+            nz_k = surf.up_sample(ro, rd, z, sdf, 16, masks, 64 * 2 ** i)
+            surf.fused_upsample = False
+            nz_t = surf.up_sample(ro, rd, z, sdf, 16, masks, 64 * 2 ** i)
+            _check(f"K5 new_z iter {i}", nz_k, nz_t.cpu().numpy(), atol_scale=2e-6)
+            zt, st = surf.cat_z_vals(ro, rd, z, nz_t, sdf, volumes, masks, last=(i == 3))
+            surf.fused_upsample = True
+            zk, sk = surf.cat_z_vals(ro, rd, z, nz_t, sdf, volumes, masks, last=(i == 3))
+            assert torch.equal(zk, zt)
+            _check(f"K5 merged sdf iter {i}", sk, st.cpu().numpy())
+            z, sdf = zt, st
+    surf.fused_upsample = True
+
+
 def test_full_render_matches_reference(setup):
     g, surf, scene, volumes, masks = setup
     ro, rd = torch.from_numpy(g["rays_o"]).to(DEV), torch.from_numpy(g["rays_d"]).to(DEV)
@@ -111,9 +135,22 @@ def test_full_render_nograd_analytic_path_matches_reference(setup):
     g, surf, scene, volumes, masks = setup
     ro, rd = torch.from_numpy(g["rays_o"]).to(DEV), torch.from_numpy(g["rays_d"]).to(DEV)
     torch.manual_seed(123)
-    with torch.no_grad():
-        res = surf.render(ro, rd, scene.near, scene.far, volumes, masks, scene.imgs, scene.features,
-                          scene.features, scene.intrs, scene.c2ws, 1.0, None)
+    captured = {}
+    core = surf.render_core
+
+    def spy(ro_, rd_, z_vals, *a, **k):
+        captured["z"] = z_vals.detach().clone()
+        return core(ro_, rd_, z_vals, *a, **k)
+
+    surf.render_core = spy
+    try:
+        with torch.no_grad():
+            res = surf.render(ro, rd, scene.near, scene.far, volumes, masks, scene.imgs, scene.features,
+                              scene.features, scene.intrs, scene.c2ws, 1.0, None)
+    finally:
+        del surf.render_core
+    # the 128 sample depths per ray after the four K5 up-sampling iterations (sorted, from the reference run)
+    _check("z_vals after up-sampling", captured["z"], g["z_vals"], atol_scale=2e-6, outlier_frac=2e-3)
     assert np.array_equal(res["valid_mask"].cpu().numpy(), g["render/valid_mask"])
     assert np.array_equal(res["mid_inside_sphere"].cpu().numpy(), g["render/mid_inside_sphere"])
     problems = []
