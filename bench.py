@@ -134,7 +134,7 @@ def algorithmic_bytes_scale(d, nv, h, w):
 
 
 
-RENDER_CHUNK = 8192          # rays per ImplicitSurface.render call (the reference's validate uses 256)
+RENDER_CHUNK = 16384         # rays per ImplicitSurface.render call (the reference's validate uses 256)
 
 
 def smooth_volumes(dims, device, seed=1):

@@ -34,15 +34,17 @@ __device__ __forceinline__ void softplus3(float a, float beta, float& sp, float&
 __device__ __forceinline__ void encode_one(float x, float dx, int L, int d, int i, float* __restrict__ row,
                                            float* __restrict__ drow) {
     row[i] = x;
-    drow[i] = dx;
+    if (drow) drow[i] = dx;
     float f = 1.0f;
     for (int k = 0; k < L; ++k) {
         float s, c;
         sincosf(x * f, &s, &c);
         row[(1 + 2 * k) * d + i] = s;
         row[(2 + 2 * k) * d + i] = c;
-        drow[(1 + 2 * k) * d + i] = f * c * dx;
-        drow[(2 + 2 * k) * d + i] = -f * s * dx;
+        if (drow) {
+            drow[(1 + 2 * k) * d + i] = f * c * dx;
+            drow[(2 + 2 * k) * d + i] = -f * s * dx;
+        }
         f *= 2.0f;
     }
 }
@@ -59,10 +61,11 @@ encode_kernel(const float* __restrict__ pts, const float* __restrict__ feats, co
     if (j < 3) {
         const int w = 3 * (1 + 2 * L_pos);
         const float u = j == 0 ? u0 : (j == 1 ? u1 : u2);
-        encode_one(pts[3 * p + j] * scale, u * scale, L_pos, 3, j, pos + p * w, pos + (n + p) * w);
+        encode_one(pts[3 * p + j] * scale, u * scale, L_pos, 3, j, pos + p * w, dfeats ? pos + (n + p) * w : nullptr);
     } else {
         const int c = j - 3, w = n_feat * (1 + 2 * L_feat);
-        encode_one(feats[p * n_feat + c], dfeats[p * n_feat + c], L_feat, n_feat, c, fe + p * w, fe + (n + p) * w);
+        encode_one(feats[p * n_feat + c], dfeats ? dfeats[p * n_feat + c] : 0.f, L_feat, n_feat, c, fe + p * w,
+                   dfeats ? fe + (n + p) * w : nullptr);
     }
 }
 
@@ -75,17 +78,18 @@ act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ fp, int ld
     if (i >= n * fo) return;
     const long long r = i / fo;
     const int c = (int)(i % fo);
-    float a = y[r * fo + c] + bias[c], da = y[(n + r) * fo + c];
-    if (fp) {
-        a += fp[r * ldfp + c];
-        da += fp[(n + r) * ldfp + c];
-    }
+    float a = y[r * fo + c] + bias[c];
+    if (fp) a += fp[r * ldfp + c];
     float sp, d1, d2;
     softplus3(a, beta, sp, d1, d2);
     x_out[r * ldx + c] = sp * out_scale;
-    x_out[(n + r) * ldx + c] = d1 * da * out_scale;
-    s1[i] = d1;
-    t2[i] = d2 * da;
+    if (s1) {  // tangent rows present
+        float da = y[(n + r) * fo + c];
+        if (fp) da += fp[(n + r) * ldfp + c];
+        x_out[(n + r) * ldx + c] = d1 * da * out_scale;
+        s1[i] = d1;
+        t2[i] = d2 * da;
+    }
 }
 
 // copy a (2n, w) block scaled into columns [col, col+w) of x_out (the skip connection [h, pos]/sqrt 2)
@@ -161,7 +165,7 @@ extern "C" int gens_sdf_encode(const float* pts, const float* feats, const float
                                const float* u3, int multires, int feat_multires, int n_feat, float* pos, float* fe,
                                void* stream) {
     if (n == 0) return 0;
-    GENS_CHECK_ARG(pts && feats && dfeats && u3 && pos && fe && n >= 0 && n_feat > 0);
+    GENS_CHECK_ARG(pts && feats && u3 && pos && fe && n >= 0 && n_feat > 0);  // dfeats NULL: value only (n rows)
     if (n == 0) return 0;
     const long long total = n * (3 + n_feat);
     encode_kernel<<<ceil_div_i(total, 256), 256, 0, (cudaStream_t)stream>>>(pts, feats, dfeats, n, scale, u3[0], u3[1],
@@ -173,7 +177,7 @@ extern "C" int gens_sdf_act_fwd(const float* y, const float* featpart, int ld_fe
                                 int fan_out, float beta, float out_scale, float* x_out, int ld_x, float* sp1, float* sp2da,
                                 void* stream) {
     if (n == 0) return 0;
-    GENS_CHECK_ARG(y && bias && x_out && sp1 && sp2da && n >= 0 && fan_out > 0 && ld_x >= fan_out);
+    GENS_CHECK_ARG(y && bias && x_out && n >= 0 && fan_out > 0 && ld_x >= fan_out && (!sp1 == !sp2da));
     if (n == 0) return 0;
     act_fwd_kernel<<<ceil_div_i(n * fan_out, 256), 256, 0, (cudaStream_t)stream>>>(
         y, featpart, ld_featpart, bias, n, fan_out, beta, out_scale, x_out, ld_x, sp1, sp2da);

@@ -74,6 +74,13 @@ class ImplicitSurface(nn.Module):
         self.analytic_nograd = True  # under torch.no_grad(): hand-differentiated SDF sweep instead of autograd
         self.fused_upsample = True   # K5 warp-per-ray kernels for up_sample / cat_z_vals (CUDA tensors)
 
+    def _fold_sdf(self):
+        """Weight-normalised SDF layers folded once per render / lattice call."""
+        if self.ops is _cuda_ops:
+            from .sdf_analytic import FoldedSDF
+            return FoldedSDF(self.sdf_network)
+        return self.sdf_network.folded_weights()
+
     # ------------------------------------------------------------------ hierarchical sampling
     def _sdf_masked(self, pts, volumes, mask_volumes, folded=None):
         """SDF at (n,3) points, FAR_SDF outside the mask volumes (no gradient)."""
@@ -279,7 +286,7 @@ class ImplicitSurface(nn.Module):
             z_vals = z_vals + t_rand * 2.0 / self.n_samples
         if self.n_importance > 0:
             with torch.no_grad():
-                self._folded = self.sdf_network.folded_weights()
+                self._folded = self._fold_sdf()
                 try:
                     pts = (rays_o[:, None, :] + rays_d[:, None, :] * z_vals[..., :, None]).reshape(-1, 3)
                     sdf = self._sdf_masked(pts, volumes, mask_volumes, self._folded).reshape(b, self.n_samples)
@@ -301,7 +308,7 @@ class ImplicitSurface(nn.Module):
         dev = bound_min.device
         axes = [torch.linspace(float(bound_min[k]), float(bound_max[k]), resolution, device=dev) for k in range(3)]
         u = torch.empty((resolution,) * 3, device=dev, dtype=torch.float32) if out is None else out
-        folded = self.sdf_network.folded_weights()
+        folded = self._fold_sdf()
         for x0 in range(0, resolution, block):
             for y0 in range(0, resolution, block):
                 for z0 in range(0, resolution, block):

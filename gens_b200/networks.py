@@ -142,7 +142,11 @@ class SDFNetwork(nn.Module):
         """SDF values (n,1) without autograd bookkeeping: same arithmetic as forward()[:, :1], but the
         encoded volume features enter every layer through ONE (n,100)x(100,sum fan_out) GEMM instead of
         six concatenations, and only column 0 of the output layer is evaluated."""
-        folded = self.folded_weights() if folded is None else folded
+        if self._lookup is _projector.lookup_volume and pts.is_cuda:
+            from . import sdf_analytic  # fused CUDA stages (csrc/sdf_glue.cu); `folded` may be a FoldedSDF
+            fw = folded if isinstance(folded, sdf_analytic.FoldedSDF) else None
+            return sdf_analytic.value_only(self, pts, volumes, fw)
+        folded = self.folded_weights() if folded is None or not isinstance(folded, list) else folded
         feats = positional_encoding(self._lookup(pts, volumes), self.feat_multires)
         pos = positional_encoding(pts * self.scale, self.multires)
         last = self.num_layers - 2

@@ -153,3 +153,47 @@ def value_grad_smooth(net, pts: torch.Tensor, volumes, folded: Optional[FoldedSD
     _c(L.gens_trilinear_vjp2(P(pts), n, pyr, _U, P(g_f), P(dg_f), P(grad), P(smooth) if need_smooth else None, st),
        "gens_trilinear_vjp2")
     return sdf, grad, (smooth if need_smooth else None)
+
+
+@torch.no_grad()
+def value_only(net, pts: torch.Tensor, volumes, folded: Optional[FoldedSDF] = None) -> torch.Tensor:
+    """SDF values (n,1) with the same fused stages, primal rows only: one K3 launch, one encode launch,
+    one feature-part GEMM, then GEMM + fused bias/softplus per layer -- the evaluation the up-sampling loop
+    (112 of the 240 SDF evaluations per ray) and the mesh lattice use."""
+    _lib.require_cuda(pts)
+    L = _lib.lib()
+    fw = FoldedSDF(net) if folded is None else folded
+    pts = _lib.f32c(pts.reshape(-1, 3))
+    n = pts.shape[0]
+    dev = pts.device
+    st = _lib.stream_ptr(dev)
+    vols = [volumes] if isinstance(volumes, torch.Tensor) else list(volumes)
+    packed = [packed_volume(v) for v in vols]
+    pyr = _lib.make_pyramid(packed, [v.shape[2] for v in vols])
+    nf = 4 * len(vols)
+    new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+    P = _lib.ptr
+    feats = new(n, nf)
+    _c(L.gens_trilinear_fwd(P(pts), n, pyr, P(feats), st), "gens_trilinear_fwd")
+    pos, fe = new(n, fw.pe_in), new(n, fw.pe_feat)
+    _c(L.gens_sdf_encode(P(pts), P(feats), None, n, fw.scale, _U, fw.multires, fw.feat_multires, nf, P(pos), P(fe), st),
+       "gens_sdf_encode")
+    featpart = fe @ fw.wf_t
+    ldfp = featpart.shape[1]
+    last = fw.n_layers - 1
+    inv_sqrt2 = 1.0 / math.sqrt(2.0)
+    x = pos
+    for l in range(last):
+        fo = fw.fo[l]
+        y = x @ fw.wx_t[l]
+        nxt_skip = (l + 1) in fw.skip_in
+        width = fo + (fw.pe_in if nxt_skip else 0)
+        x_next = new(n, width)
+        fp_ptr = None if l == 0 else ctypes.c_void_p(featpart.data_ptr() + 4 * fw.off[l - 1])
+        _c(L.gens_sdf_act_fwd(P(y), fp_ptr, ldfp, P(fw.bias[l]), n, fo, 100.0, inv_sqrt2 if nxt_skip else 1.0,
+                              P(x_next), width, None, None, st), "gens_sdf_act_fwd")
+        if nxt_skip:
+            _c(L.gens_copy_scaled(P(pos), fw.pe_in, n, inv_sqrt2, P(x_next), width, fo, st), "gens_copy_scaled")
+        x = x_next
+    y_last = x @ fw.wx_t[last]
+    return (y_last + featpart[:, fw.off[last - 1]: fw.off[last - 1] + 1] + fw.bias[last]) / fw.scale

@@ -202,12 +202,14 @@ int gens_trilinear_fwd_jvp(const float *pts, long long n, const gens_pyramid_t *
 int gens_trilinear_vjp2(const float *pts, long long n, const gens_pyramid_t *vols, const float *u3,
                         const float *g_f, const float *dg_f, float *grad, float *smooth, void *stream);
 /* positional encodings (embedder.py:11-36) of the scaled point and of the volume features, with
- * tangents: pos (2n, 3(1+2*multires)), fe (2n, n_feat(1+2*feat_multires)). */
+ * tangents: pos (2n, 3(1+2*multires)), fe (2n, n_feat(1+2*feat_multires)).  dfeats == NULL: value only,
+ * n rows (the no-grad SDF evaluations of the up-sampling loop and of the mesh lattice). */
 int gens_sdf_encode(const float *pts, const float *feats, const float *dfeats, long long n, float scale,
                     const float *u3, int multires, int feat_multires, int n_feat, float *pos, float *fe,
                     void *stream);
 /* a = y + featpart + bias ; h = softplus_beta(a) -> x_out (2n rows, leading dim ld_x) scaled by
- * out_scale; keeps sp1 = sp'(a) and sp2da = sp''(a) * da, both (n, fan_out). featpart may be NULL. */
+ * out_scale; keeps sp1 = sp'(a) and sp2da = sp''(a) * da, both (n, fan_out). featpart may be NULL.
+ * sp1 == sp2da == NULL: value only (n rows, no tangent). */
 int gens_sdf_act_fwd(const float *y, const float *featpart, int ld_featpart, const float *bias,
                      long long n, int fan_out, float beta, float out_scale, float *x_out, int ld_x,
                      float *sp1, float *sp2da, void *stream);
