@@ -332,56 +332,65 @@ __device__ __forceinline__ void accumulate_view(const Cam& cam, const float4* __
     }
 }
 
-template <int PAIRS, bool RECIP, int MIN_BLOCKS, int GATHER>
+// ROWS: row-groups of 8 rows a block walks through, amortising the camera staging and its barriers.
+template <int PAIRS, bool RECIP, int MIN_BLOCKS, int GATHER, int ROWS>
 __global__ void __launch_bounds__(256, MIN_BLOCKS)
 volume_agg_packed_kernel(const float4* __restrict__ feat, int nv, int H, int W, const float* __restrict__ w2c,
                          const float* __restrict__ k_stage, float k_row_scale, const float* __restrict__ grid, int D, int a0,
                          long long out_off, long long channel_stride, int min_vis_view, Extent e,
                          float* __restrict__ volume, float* __restrict__ mask_volume) {
     __shared__ Cam s_cam[GENS_MAX_VIEWS];
+    __shared__ float s_inv_count[GENS_MAX_VIEWS + 1];  // RN(1/n) for the exact count division
+    if (threadIdx.y == 0 && threadIdx.x <= GENS_MAX_VIEWS)
+        s_inv_count[threadIdx.x] = threadIdx.x == 0 ? 1e8f : __fdiv_rn(1.0f, (float)threadIdx.x);
     load_cams(s_cam, w2c, k_stage, k_row_scale, nv);
-    const int c0 = blockIdx.x * (64 * PAIRS) + threadIdx.x, b = blockIdx.y * 8 + threadIdx.y, a = a0 + blockIdx.z;
-    if (b >= D) return;
-    const float X = __ldg(grid + a), Y = __ldg(grid + b);
+    const int c0 = blockIdx.x * (64 * PAIRS) + threadIdx.x, a = a0 + blockIdx.z;
+    const float X = __ldg(grid + a);
     f32x2 Z[PAIRS];
 #pragma unroll
     for (int h = 0; h < PAIRS; ++h) Z[h] = pk(__ldg(grid + c0 + 64 * h), __ldg(grid + c0 + 64 * h + 32));
     const int pitch = W + 1;
     const long long map_stride = (long long)(H + 1) * pitch;
 
-    Acc acc[2 * PAIRS];
+#pragma unroll 1
+    for (int rr = 0; rr < ROWS; ++rr) {
+        const int b = (blockIdx.y * ROWS + rr) * 8 + threadIdx.y;
+        if (b >= D) return;
+        const float Y = __ldg(grid + b);
+        Acc acc[2 * PAIRS];
 #pragma unroll
-    for (int j = 0; j < 2 * PAIRS; ++j) {
-        acc[j].s_xy = acc[j].s_zw = acc[j].q_xy = acc[j].q_zw = bc(0.0f);
-        acc[j].cnt = 0;
-    }
+        for (int j = 0; j < 2 * PAIRS; ++j) {
+            acc[j].s_xy = acc[j].s_zw = acc[j].q_xy = acc[j].q_zw = bc(0.0f);
+            acc[j].cnt = 0;
+        }
 
 #pragma unroll 1
-    for (int v = 0; v < nv; ++v) {
-        const float4* map = feat + v * map_stride;
-        if (s_cam[v].affine) accumulate_view<PAIRS, RECIP, true, GATHER>(s_cam[v], map, pitch, X, Y, Z, e, acc);
-        else accumulate_view<PAIRS, RECIP, false, GATHER>(s_cam[v], map, pitch, X, Y, Z, e, acc);
-    }
+        for (int v = 0; v < nv; ++v) {
+            const float4* map = feat + v * map_stride;
+            if (s_cam[v].affine) accumulate_view<PAIRS, RECIP, true, GATHER>(s_cam[v], map, pitch, X, Y, Z, e, acc);
+            else accumulate_view<PAIRS, RECIP, false, GATHER>(s_cam[v], map, pitch, X, Y, Z, e, acc);
+        }
 
-    const long long row = out_off + ((long long)blockIdx.z * D + b) * D + c0;
+        const long long row = out_off + ((long long)blockIdx.z * D + b) * D + c0;
 #pragma unroll
-    for (int j = 0; j < 2 * PAIRS; ++j) {
-        const int cnt = acc[j].cnt;
-        const float n = cnt <= 0 ? 1e-8f : (float)cnt;
-        const float r = cnt <= 0 ? 1e8f : __frcp_rn(n);
-        const f32x2 m_xy = div_count2(acc[j].s_xy, n, r), m_zw = div_count2(acc[j].s_zw, n, r);
-        const f32x2 v_xy = sub2(div_count2(acc[j].q_xy, n, r), mul2_rounded(m_xy, m_xy));
-        const f32x2 v_zw = sub2(div_count2(acc[j].q_zw, n, r), mul2_rounded(m_zw, m_zw));
-        float* o = volume + row + 32 * j;
-        __stcs(o, lo(m_xy));
-        __stcs(o + channel_stride, hi(m_xy));
-        __stcs(o + 2 * channel_stride, lo(m_zw));
-        __stcs(o + 3 * channel_stride, hi(m_zw));
-        __stcs(o + 4 * channel_stride, lo(v_xy));
-        __stcs(o + 5 * channel_stride, hi(v_xy));
-        __stcs(o + 6 * channel_stride, lo(v_zw));
-        __stcs(o + 7 * channel_stride, hi(v_zw));
-        __stcs(mask_volume + row + 32 * j, cnt > min_vis_view ? 1.0f : 0.0f);
+        for (int j = 0; j < 2 * PAIRS; ++j) {
+            const int cnt = acc[j].cnt;
+            const float n = cnt <= 0 ? 1e-8f : (float)cnt;
+            const float r = s_inv_count[cnt];
+            const f32x2 m_xy = div_count2(acc[j].s_xy, n, r), m_zw = div_count2(acc[j].s_zw, n, r);
+            const f32x2 v_xy = sub2(div_count2(acc[j].q_xy, n, r), mul2_rounded(m_xy, m_xy));
+            const f32x2 v_zw = sub2(div_count2(acc[j].q_zw, n, r), mul2_rounded(m_zw, m_zw));
+            float* o = volume + row + 32 * j;
+            __stcs(o, lo(m_xy));
+            __stcs(o + channel_stride, hi(m_xy));
+            __stcs(o + 2 * channel_stride, lo(m_zw));
+            __stcs(o + 3 * channel_stride, hi(m_zw));
+            __stcs(o + 4 * channel_stride, lo(v_xy));
+            __stcs(o + 5 * channel_stride, hi(v_xy));
+            __stcs(o + 6 * channel_stride, lo(v_zw));
+            __stcs(o + 7 * channel_stride, hi(v_zw));
+            __stcs(mask_volume + row + 32 * j, cnt > min_vis_view ? 1.0f : 0.0f);
+        }
     }
 }
 
@@ -533,19 +542,24 @@ int launch_agg_fwd(const gens_volume_scale_t& sc, int nv, const float* w2c, cons
 #define GENS_AGG_ARGS \
     feat, nv, sc.H, sc.W, w2c, intrs, sc.k_row_scale, sc.grid, D, sc.a0, out_off, sc.channel_stride, min_vis_view, e, \
         sc.volume, sc.mask_volume
-#define GENS_LAUNCH_PACKED(PAIRS, MINB, GATHER)                                                          \
-    do {                                                                                                 \
-        const dim3 g(D / (64 * PAIRS), ceil_div_i(D, 8), planes);                                        \
-        if (recip) volume_agg_packed_kernel<PAIRS, true, MINB, GATHER><<<g, block, 0, st>>>(GENS_AGG_ARGS); \
-        else volume_agg_packed_kernel<PAIRS, false, MINB, GATHER><<<g, block, 0, st>>>(GENS_AGG_ARGS);     \
+#define GENS_LAUNCH_PACKED(PAIRS, MINB, GATHER, ROWS)                                                              \
+    do {                                                                                                         \
+        const dim3 g(D / (64 * PAIRS), ceil_div_i(D, 8 * ROWS), planes);                                         \
+        if (recip) volume_agg_packed_kernel<PAIRS, true, MINB, GATHER, ROWS><<<g, block, 0, st>>>(GENS_AGG_ARGS); \
+        else volume_agg_packed_kernel<PAIRS, false, MINB, GATHER, ROWS><<<g, block, 0, st>>>(GENS_AGG_ARGS);     \
     } while (0)
     const int variant = g_k1_variant;
-    if (D % 128 == 0 && variant == 1) {
-        GENS_LAUNCH_PACKED(2, 3, 1);
-    } else if (D % 128 == 0 && variant == 2) {
-        GENS_LAUNCH_PACKED(2, 2, 0);
-    } else if (D % 64 == 0) {
-        GENS_LAUNCH_PACKED(1, 4, 1);
+    // rows per block: enough to amortise the camera staging, few enough to keep >= ~4 waves of blocks
+    const int rows = variant == 1 ? 1 : variant == 2 ? 2 : variant == 4 ? 4 : variant == 8 ? 8 : variant == 16 ? 16
+                   : (D >= 256 ? 8 : D >= 128 ? 2 : 1);
+    if (D % 64 == 0 && variant != 9) {
+        switch (rows) {
+            case 16: GENS_LAUNCH_PACKED(1, 4, 1, 16); break;
+            case 8: GENS_LAUNCH_PACKED(1, 4, 1, 8); break;
+            case 4: GENS_LAUNCH_PACKED(1, 4, 1, 4); break;
+            case 2: GENS_LAUNCH_PACKED(1, 4, 1, 2); break;
+            default: GENS_LAUNCH_PACKED(1, 4, 1, 1); break;
+        }
     } else {
         const dim3 g(ceil_div_i(D, 32), ceil_div_i(D, 8), planes);
         if (recip) volume_agg_scalar_kernel<true><<<g, block, 0, st>>>(GENS_AGG_ARGS);
