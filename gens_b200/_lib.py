@@ -152,3 +152,9 @@ def f32c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()
+
+
+def inverse(t: torch.Tensor) -> torch.Tensor:
+    """torch.inverse without its host-synchronising singularity check: same LU kernels (bit-identical
+    result for invertible input), but the caller's stream keeps running."""
+    return torch.linalg.inv_ex(t, check_errors=False)[0]

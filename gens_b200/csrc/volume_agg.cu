@@ -4,11 +4,13 @@
 // runs ~320 ATen ops and >= 15 full (nv,.,D^3) temporaries per scale, with ONE launch that
 // reads each feature map once (through L1/L2) and writes the 8+1 output channels once.
 //
-// Data layout.  Feature maps are re-packed once per call to channels-last with one zero
-// row/column of padding, (nv, H+1, W+1, 4): a bilinear corner is a single 16-byte read-only
-// load and the +1 corners of any valid sample exist in memory, so the four gathers are
-// unconditional.  Outputs are the reference's NCDHW planes, written with coalesced
-// streaming stores.
+// Data layout.  Feature maps are re-packed once per call (one launch for all scales) to "pixel
+// pairs": texel (x,y) of view v holds [f(x,y,0..3), f(x+1,y,0..3)] = 32 bytes, with one zero row
+// below and zeros for x+1 == W, shape (nv, H+1, W, 8).  A bilinear footprint is then TWO 256-bit
+// read-only loads (LDG.E.256: top and bottom pixel pair) instead of four 128-bit ones -- half
+// the L1 requests over the same cache lines, which is what bounds this kernel -- and the +1
+// corners of any valid sample exist in memory, so the gathers are unconditional.  Outputs are
+// the reference's NCDHW planes, written with coalesced streaming stores.
 //
 // Mapping (packed kernel, D % 128 == 0).  A warp owns 32 CONSECUTIVE voxels along the fastest
 // tensor dim (world z); a thread owns four voxels 32 apart.  Consecutive voxels project
@@ -22,6 +24,8 @@
 // restatement it is tested against bit-for-bit): two-stage projection as k-ascending fma
 // chains, IEEE division, two-moment variance E[x^2]-E[x]^2 (NOT Welford -- parity with the
 // reference's cancellation behaviour is the contract).
+#include <mutex>
+
 #include "common.cuh"
 #include "f32x2.cuh"
 
@@ -116,15 +120,15 @@ __device__ __forceinline__ void fma4(float4& acc, const float4 v, float w) {
     acc.w = __fmaf_rn(v.w, w, acc.w);
 }
 
-// Bilinear sample of a VALID footprint from the zero-padded channels-last map (pitch = W+1).
-__device__ __forceinline__ float4 sample_padded(const float4* __restrict__ map, int pitch, const Footprint& f) {
-    const float4* p = map + (f.y0 * pitch + f.x0);
-    const float4 v_nw = __ldg(p), v_ne = __ldg(p + 1), v_sw = __ldg(p + pitch), v_se = __ldg(p + pitch + 1);
+// Bilinear sample of a VALID footprint from the pixel-pair map (pitch = W texels of 32 bytes).
+__device__ __forceinline__ float4 sample_padded(const Pair* __restrict__ map, int pitch, const Footprint& f) {
+    const Pair* p = map + (f.y0 * pitch + f.x0);
+    const Pair top = ldg256(p), bot = ldg256(p + pitch);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    fma4(acc, v_nw, f.w_nw);
-    fma4(acc, v_ne, f.w_ne);
-    fma4(acc, v_sw, f.w_sw);
-    fma4(acc, v_se, f.w_se);
+    fma4(acc, top.a, f.w_nw);
+    fma4(acc, top.b, f.w_ne);
+    fma4(acc, bot.a, f.w_sw);
+    fma4(acc, bot.b, f.w_se);
     return acc;
 }
 
@@ -138,7 +142,7 @@ __device__ __forceinline__ f32x2 div_count2(f32x2 s, float n, float r) {
 
 template <bool RECIP>
 __global__ void __launch_bounds__(256)
-volume_agg_scalar_kernel(const float4* __restrict__ feat, int nv, int H, int W, const float* __restrict__ w2c,
+volume_agg_scalar_kernel(const Pair* __restrict__ feat, int nv, int H, int W, const float* __restrict__ w2c,
                          const float* __restrict__ k_stage, float k_row_scale, const float* __restrict__ grid, int D, int a0,
                          long long out_off, long long channel_stride, int min_vis_view, Extent e,
                          float* __restrict__ volume, float* __restrict__ mask_volume) {
@@ -147,7 +151,7 @@ volume_agg_scalar_kernel(const float4* __restrict__ feat, int nv, int H, int W, 
     const int c = blockIdx.x * 32 + threadIdx.x, b = blockIdx.y * 8 + threadIdx.y, a = a0 + blockIdx.z;
     if (c >= D || b >= D) return;
     const float X = __ldg(grid + a), Y = __ldg(grid + b), Z = __ldg(grid + c);
-    const int pitch = W + 1;
+    const int pitch = W;
     const long long map_stride = (long long)(H + 1) * pitch;
 
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
@@ -268,13 +272,14 @@ struct Corner4 {
     float4 nw, ne, sw, se;
 };
 
-__device__ __forceinline__ Corner4 gather4(const float4* __restrict__ map, int pitch, int x0, int y0) {
-    const float4* p = map + (y0 * pitch + x0);
+__device__ __forceinline__ Corner4 gather4(const Pair* __restrict__ map, int pitch, int x0, int y0) {
+    const Pair* p = map + (y0 * pitch + x0);
+    const Pair top = ldg256(p), bot = ldg256(p + pitch);
     Corner4 c;
-    c.nw = __ldg(p);
-    c.ne = __ldg(p + 1);
-    c.sw = __ldg(p + pitch);
-    c.se = __ldg(p + pitch + 1);
+    c.nw = top.a;
+    c.ne = top.b;
+    c.sw = bot.a;
+    c.se = bot.b;
     return c;
 }
 
@@ -299,7 +304,7 @@ __device__ __forceinline__ void blend_accumulate(const Corner4& v, float w_nw, f
 // four gathers before the first blend (8 loads in flight per thread); GATHER = 1: one voxel at a
 // time (4 in flight, 16 fewer live registers).
 template <int PAIRS, bool RECIP, bool AFFINE, int GATHER>
-__device__ __forceinline__ void accumulate_view(const Cam& cam, const float4* __restrict__ map, int pitch,
+__device__ __forceinline__ void accumulate_view(const Cam& cam, const Pair* __restrict__ map, int pitch,
                                                 float X, float Y, const f32x2 (&Z)[PAIRS], const Extent& e,
                                                 Acc (&acc)[2 * PAIRS]) {
     float pre[4];
@@ -335,7 +340,7 @@ __device__ __forceinline__ void accumulate_view(const Cam& cam, const float4* __
 // ROWS: row-groups of 8 rows a block walks through, amortising the camera staging and its barriers.
 template <int PAIRS, bool RECIP, int MIN_BLOCKS, int GATHER, int ROWS>
 __global__ void __launch_bounds__(256, MIN_BLOCKS)
-volume_agg_packed_kernel(const float4* __restrict__ feat, int nv, int H, int W, const float* __restrict__ w2c,
+volume_agg_packed_kernel(const Pair* __restrict__ feat, int nv, int H, int W, const float* __restrict__ w2c,
                          const float* __restrict__ k_stage, float k_row_scale, const float* __restrict__ grid, int D, int a0,
                          long long out_off, long long channel_stride, int min_vis_view, Extent e,
                          float* __restrict__ volume, float* __restrict__ mask_volume) {
@@ -349,7 +354,7 @@ volume_agg_packed_kernel(const float4* __restrict__ feat, int nv, int H, int W, 
     f32x2 Z[PAIRS];
 #pragma unroll
     for (int h = 0; h < PAIRS; ++h) Z[h] = pk(__ldg(grid + c0 + 64 * h), __ldg(grid + c0 + 64 * h + 32));
-    const int pitch = W + 1;
+    const int pitch = W;
     const long long map_stride = (long long)(H + 1) * pitch;
 
 #pragma unroll 1
@@ -366,7 +371,7 @@ volume_agg_packed_kernel(const float4* __restrict__ feat, int nv, int H, int W, 
 
 #pragma unroll 1
         for (int v = 0; v < nv; ++v) {
-            const float4* map = feat + v * map_stride;
+            const Pair* map = feat + v * map_stride;
             if (s_cam[v].affine) accumulate_view<PAIRS, RECIP, true, GATHER>(s_cam[v], map, pitch, X, Y, Z, e, acc);
             else accumulate_view<PAIRS, RECIP, false, GATHER>(s_cam[v], map, pitch, X, Y, Z, e, acc);
         }
@@ -398,10 +403,11 @@ volume_agg_packed_kernel(const float4* __restrict__ feat, int nv, int H, int W, 
 //   mean_k = sum_v m_v f_vk / n',  var_k = sum_v m_v f_vk^2 / n' - mean_k^2
 //   d/df_vk = m_v / n' * ( g_mean_k + 2 g_var_k (f_vk - mean_k) )
 // scattered to the four bilinear corners of the padded channels-last gradient map with
-// 16-byte vector atomics (two passes over the views: mean first, then scatter).
+// 16-byte vector atomics (two passes over the views: mean first, then scatter).  The features are read
+// from the forward's pixel-pair maps; the gradient map is (nv, H+1, W+1, 4).
 template <bool RECIP>
 __global__ void __launch_bounds__(256)
-volume_agg_bwd_kernel(const float4* __restrict__ feat, int nv, int H, int W, const float* __restrict__ w2c,
+volume_agg_bwd_kernel(const Pair* __restrict__ feat, int nv, int H, int W, const float* __restrict__ w2c,
                       const float* __restrict__ k_stage, float k_row_scale, const float* __restrict__ grid, int D, int a0,
                       long long out_off, long long channel_stride, Extent e,
                       const float* __restrict__ grad_volume, float4* __restrict__ grad_feat) {
@@ -420,8 +426,8 @@ volume_agg_bwd_kernel(const float4* __restrict__ feat, int nv, int H, int W, con
         any |= (gm[k] != 0.f) | (gv[k] != 0.f);
     }
     if (!any) return;
-    const int pitch = W + 1;
-    const long long map_stride = (long long)(H + 1) * pitch;
+    const int pitch = W, g_pitch = W + 1;  // features: pixel pairs; gradient: padded channels-last float4
+    const long long map_stride = (long long)(H + 1) * pitch, g_stride = (long long)(H + 1) * g_pitch;
 
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     int cnt = 0;
@@ -447,30 +453,51 @@ volume_agg_bwd_kernel(const float4* __restrict__ feat, int nv, int H, int W, con
         float gf[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) gf[k] = inv_n * (gm[k] + 2.0f * gv[k] * (fv[k] - mean[k]));
-        float4* gp = grad_feat + v * map_stride + (t.y0 * pitch + t.x0);
+        float4* gp = grad_feat + v * g_stride + (t.y0 * g_pitch + t.x0);
         atomicAdd(gp, make_float4(gf[0] * t.w_nw, gf[1] * t.w_nw, gf[2] * t.w_nw, gf[3] * t.w_nw));
         atomicAdd(gp + 1, make_float4(gf[0] * t.w_ne, gf[1] * t.w_ne, gf[2] * t.w_ne, gf[3] * t.w_ne));
-        atomicAdd(gp + pitch, make_float4(gf[0] * t.w_sw, gf[1] * t.w_sw, gf[2] * t.w_sw, gf[3] * t.w_sw));
-        atomicAdd(gp + pitch + 1, make_float4(gf[0] * t.w_se, gf[1] * t.w_se, gf[2] * t.w_se, gf[3] * t.w_se));
+        atomicAdd(gp + g_pitch, make_float4(gf[0] * t.w_sw, gf[1] * t.w_sw, gf[2] * t.w_sw, gf[3] * t.w_sw));
+        atomicAdd(gp + g_pitch + 1, make_float4(gf[0] * t.w_se, gf[1] * t.w_se, gf[2] * t.w_se, gf[3] * t.w_se));
     }
 }
 
-// (n,4,h,w) NCHW -> zero-padded channels-last (n, h+1, w+1, 4)
+// All scales of a pyramid, (n,4,h_i,w_i) NCHW -> pixel pairs (n, h_i+1, w_i, 8), ONE launch: a thread
+// writes one 32-byte texel [f(x,y,:), f(x+1,y,:)] (zeros for y == h and x+1 == w).
+struct PackJob {
+    const float* src;
+    float4* dst;
+    int h, w;
+    long long first;  // index of this scale's first texel in the launch-wide numbering
+};
+struct PackJobs {
+    PackJob job[GENS_MAX_SCALES];
+    int n_jobs, n_maps;
+    long long total;
+};
+
 __global__ void __launch_bounds__(256)
-pack_maps_kernel(const float* __restrict__ src, float4* __restrict__ dst, int h, int w, long long total) {
+pack_pairs_kernel(const __grid_constant__ PackJobs jobs) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int pitch = w + 1;
-    const long long per = (long long)(h + 1) * pitch;
-    const long long n = i / per;
-    const int rem = (int)(i % per), y = rem / pitch, x = rem % pitch;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (y < h && x < w) {
+    if (i >= jobs.total) return;
+    int s = 0;
+#pragma unroll
+    for (int k = 1; k < GENS_MAX_SCALES; ++k)
+        if (k < jobs.n_jobs && i >= jobs.job[k].first) s = k;
+    const PackJob& j = jobs.job[s];
+    const long long local = i - j.first;
+    const int h = j.h, w = j.w;
+    const long long per = (long long)(h + 1) * w;
+    const long long n = local / per;
+    const int rem = (int)(local % per), y = rem / w, x = rem % w;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (y < h) {
         const long long hw = (long long)h * w;
-        const float* s = src + n * 4 * hw + (long long)y * w + x;
-        v = make_float4(__ldg(s), __ldg(s + hw), __ldg(s + 2 * hw), __ldg(s + 3 * hw));
+        const float* p = j.src + n * 4 * hw + (long long)y * w + x;
+        a = make_float4(__ldg(p), __ldg(p + hw), __ldg(p + 2 * hw), __ldg(p + 3 * hw));
+        if (x + 1 < w) b = make_float4(__ldg(p + 1), __ldg(p + hw + 1), __ldg(p + 2 * hw + 1), __ldg(p + 3 * hw + 1));
     }
-    dst[i] = v;
+    j.dst[2 * local] = a;
+    j.dst[2 * local + 1] = b;
 }
 
 // padded channels-last gradient (n, h+1, w+1, 4) -> (n,4,h,w) NCHW (padding rows/cols dropped;
@@ -507,13 +534,30 @@ extern "C" int gens_debug_set_variant(int variant) {
     return 0;
 }
 
-extern "C" int gens_pack_feature_maps(const float* src_nchw, float* dst_padded_nhwc, int n, int h, int w,
-                                      void* stream) {
-    GENS_CHECK_ARG(src_nchw && dst_padded_nhwc && n > 0 && h > 0 && w > 0);
-    const long long total = (long long)n * (h + 1) * (w + 1);
-    pack_maps_kernel<<<ceil_div_i(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        src_nchw, reinterpret_cast<float4*>(dst_padded_nhwc), h, w, total);
+extern "C" int gens_pack_feature_maps_multi(const float* const* src_nchw, float* const* dst_pairs, const int* h,
+                                            const int* w, int n_scales, int n, void* stream) {
+    GENS_CHECK_ARG(src_nchw && dst_pairs && h && w && n_scales > 0 && n > 0);
+    if (n_scales > GENS_MAX_SCALES) return GENS_E_UNSUPPORTED;
+    PackJobs jobs;
+    jobs.n_jobs = n_scales;
+    jobs.n_maps = n;
+    long long total = 0;
+    for (int i = 0; i < n_scales; ++i) {
+        GENS_CHECK_ARG(src_nchw[i] && dst_pairs[i] && h[i] > 0 && w[i] > 0);
+        jobs.job[i].src = src_nchw[i];
+        jobs.job[i].dst = reinterpret_cast<float4*>(dst_pairs[i]);
+        jobs.job[i].h = h[i];
+        jobs.job[i].w = w[i];
+        jobs.job[i].first = total;
+        total += (long long)n * (h[i] + 1) * w[i];
+    }
+    jobs.total = total;
+    pack_pairs_kernel<<<ceil_div_i(total, 256), 256, 0, (cudaStream_t)stream>>>(jobs);
     return gens_launch_status();
+}
+
+extern "C" int gens_pack_feature_maps(const float* src_nchw, float* dst_pairs, int n, int h, int w, void* stream) {
+    return gens_pack_feature_maps_multi(&src_nchw, &dst_pairs, &h, &w, 1, n, stream);
 }
 
 extern "C" int gens_unpack_feature_grads(const float* src_padded_nhwc, float* dst_nchw, int n, int h, int w,
@@ -531,12 +575,12 @@ int launch_agg_fwd(const gens_volume_scale_t& sc, int nv, const float* w2c, cons
                    int div_mode, cudaStream_t st) {
     if (!(sc.feat_padded && sc.grid && sc.volume && sc.mask_volume)) return GENS_E_BADARG;
     if (!(sc.H > 0 && sc.W > 0 && sc.D > 0) || bad_slab(sc.D, sc.a0, sc.a1, sc.a_base)) return GENS_E_BADARG;
-    if ((long long)(sc.H + 1) * (sc.W + 1) * nv >= (1LL << 31)) return GENS_E_UNSUPPORTED;
+    if ((long long)(sc.H + 1) * (sc.W + 1) * nv >= (1LL << 28)) return GENS_E_UNSUPPORTED;
     if (sc.a1 <= sc.a0) return 0;
     const int D = sc.D, planes = sc.a1 - sc.a0;
     const long long out_off = (long long)(sc.a0 - sc.a_base) * D * D;
     const Extent e = extent(sc.W, sc.H);
-    const float4* feat = reinterpret_cast<const float4*>(sc.feat_padded);
+    const Pair* feat = reinterpret_cast<const Pair*>(sc.feat_padded);
     const bool recip = div_mode == GENS_DIV_RECIP;
     const dim3 block(32, 8);
 #define GENS_AGG_ARGS \
@@ -572,12 +616,60 @@ int launch_agg_fwd(const gens_volume_scale_t& sc, int nv, const float* w2c, cons
 
 }  // namespace
 
+namespace {
+// One auxiliary stream per device: the small scales of a build run beside the largest one instead of
+// behind it (their launch latencies and tails disappear into the big kernel).  Fork/join with events, so
+// the work is still ordered entirely by the caller's stream (and capturable in a CUDA graph).
+struct Fork {
+    cudaStream_t aux = nullptr;
+    cudaEvent_t forked = nullptr, joined = nullptr;
+    bool ok = false, tried = false;
+};
+std::mutex g_fork_mutex;
+Fork g_forks[64];
+
+Fork* fork_for_current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    Fork& f = g_forks[dev];
+    if (!f.tried) {
+        f.tried = true;
+        f.ok = cudaStreamCreateWithFlags(&f.aux, cudaStreamNonBlocking) == cudaSuccess &&
+               cudaEventCreateWithFlags(&f.forked, cudaEventDisableTiming) == cudaSuccess &&
+               cudaEventCreateWithFlags(&f.joined, cudaEventDisableTiming) == cudaSuccess;
+        if (!f.ok) cudaGetLastError();
+    }
+    return f.ok ? &f : nullptr;
+}
+}  // namespace
+
 extern "C" int gens_volume_agg_fwd_multi(const gens_volume_scale_t* scales, int n_scales, int nv, const float* w2c,
                                          const float* intrs, int min_vis_view, int div_mode, void* stream) {
     GENS_CHECK_ARG(scales && n_scales > 0 && w2c && intrs && nv > 0);
     if (nv > GENS_MAX_VIEWS) return GENS_E_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    int big = 0;
+    for (int i = 1; i < n_scales; ++i)
+        if (scales[i].D > scales[big].D) big = i;
+    std::lock_guard<std::mutex> lock(g_fork_mutex);
+    Fork* f = n_scales > 1 && g_k1_variant != 7 ? fork_for_current_device() : nullptr;
+    if (f && (cudaEventRecord(f->forked, st) != cudaSuccess || cudaStreamWaitEvent(f->aux, f->forked, 0) != cudaSuccess)) {
+        cudaGetLastError();
+        f = nullptr;
+    }
+    int rc = 0;
+    if (f) {
+        // largest scale on the caller's stream, the rest beside it
+        rc = launch_agg_fwd(scales[big], nv, w2c, intrs, min_vis_view, div_mode, st);
+        for (int i = 0; i < n_scales && rc == 0; ++i)
+            if (i != big) rc = launch_agg_fwd(scales[i], nv, w2c, intrs, min_vis_view, div_mode, f->aux);
+        // always join, even after an error, so the auxiliary stream never outlives the call's ordering
+        if (cudaEventRecord(f->joined, f->aux) != cudaSuccess || cudaStreamWaitEvent(st, f->joined, 0) != cudaSuccess)
+            return rc != 0 ? rc : gens_launch_status();
+        return rc;
+    }
     for (int i = 0; i < n_scales; ++i) {
-        const int rc = launch_agg_fwd(scales[i], nv, w2c, intrs, min_vis_view, div_mode, (cudaStream_t)stream);
+        rc = launch_agg_fwd(scales[i], nv, w2c, intrs, min_vis_view, div_mode, st);
         if (rc != 0) return rc;
     }
     return 0;
@@ -592,16 +684,6 @@ extern "C" int gens_volume_agg_fwd(const float* feat_padded, int nv, int H, int 
     sc.channel_stride = channel_stride; sc.k_row_scale = k_row_scale; sc.grid = grid; sc.volume = volume;
     sc.mask_volume = mask_volume;
     return gens_volume_agg_fwd_multi(&sc, 1, nv, w2c, intrs, min_vis_view, div_mode, stream);
-}
-
-extern "C" int gens_pack_feature_maps_multi(const float* const* src_nchw, float* const* dst_padded, const int* h,
-                                            const int* w, int n_scales, int n, void* stream) {
-    GENS_CHECK_ARG(src_nchw && dst_padded && h && w && n_scales > 0 && n > 0);
-    for (int i = 0; i < n_scales; ++i) {
-        const int rc = gens_pack_feature_maps(src_nchw[i], dst_padded[i], n, h[i], w[i], stream);
-        if (rc != 0) return rc;
-    }
-    return 0;
 }
 
 extern "C" int gens_volume_project_debug(int nv, int H, int W, const float* w2c, const float* intrs,
@@ -630,7 +712,7 @@ extern "C" int gens_volume_agg_bwd(const float* feat_padded, int nv, int H, int 
     const long long out_off = (long long)(a0 - a_base) * D * D;
     const Extent e = extent(W, H);
     cudaStream_t st = (cudaStream_t)stream;
-    const float4* feat = reinterpret_cast<const float4*>(feat_padded);
+    const Pair* feat = reinterpret_cast<const Pair*>(feat_padded);
     float4* gfeat = reinterpret_cast<float4*>(grad_feat_padded);
     const dim3 block(32, 8), g(ceil_div_i(D, 32), ceil_div_i(D, 8), a1 - a0);
     if (div_mode == GENS_DIV_RECIP)

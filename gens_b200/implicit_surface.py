@@ -16,6 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import projector as _cuda_ops
+from ._lib import inverse as _inverse
 from .networks import BlendingNetwork, SDFNetwork, SingleVarianceNetwork
 
 FAR_SDF = 100.0  # value the reference assigns to samples outside every mask volume
@@ -200,7 +201,7 @@ class ImplicitSurface(nn.Module):
         weights_sum = weights.sum(dim=-1, keepdim=True)
         color = (colour * weights[:, :, None]).sum(dim=1)
         grads_bn = gradients.reshape(b, n, 3)
-        rot = torch.inverse(c2ws[0, :3, :3])
+        rot = _inverse(c2ws[0, :3, :3])
         normal = (grads_bn * weights[:, :, None]).sum(dim=1) @ rot.t()
         cam_rays_d = rays_d @ rot.t()
         render_depth = (mid_z * weights).sum(dim=1) * cam_rays_d[:, 2]

@@ -249,7 +249,7 @@ def lookup_feature(pts, imgs, intrs, c2ws, features):
     if any(f.shape[1] != 4 for f in features) or imgs.shape[1] != 3:
         raise RuntimeError("gens_b200.lookup_feature is built for 4-channel feature maps and RGB images")
     p = _lib.f32c(pts.reshape(-1, 3))
-    w2c_src = _lib.f32c(torch.inverse(c2ws[1:]))  # same op as the reference (projector.py:322)
+    w2c_src = _lib.f32c(_lib.inverse(c2ws[1:]))  # same op as the reference (projector.py:322)
     k_src = _lib.f32c(intrs[1:])
     return _LookupFeature.apply(p, w2c_src, k_src, _lib.f32c(c2ws[0]), _lib.f32c(c2ws[1:]), imgs[1:], *features)
 
@@ -262,7 +262,7 @@ def surface_patch_warp(pts_sdf0, gradients_sdf0, images, intrinsics, poses, patc
     b = pts_sdf0.shape[0]
     r0, c0 = poses[0, :3, :3], poses[0, :3, 3]
     k0 = intrinsics[0, :3, :3]
-    k0_inv = torch.inverse(intrinsics)[0, :3, :3]
+    k0_inv = _lib.inverse(intrinsics)[0, :3, :3]
     x_ref = pts_sdf0 @ r0 - (c0 @ r0)[None, None, :]              # (B,1,3) point in the reference camera
     proj = x_ref @ k0.t()                                         # (B,1,3)
     disp = (gradients_sdf0 * x_ref).sum(-1, keepdim=True)         # n . X  (B,1,1)

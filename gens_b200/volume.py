@@ -34,12 +34,12 @@ def voxel_axis(d: int, device) -> torch.Tensor:
 
 
 def pack_feature_maps(feat: torch.Tensor) -> torch.Tensor:
-    """(n,4,h,w) NCHW -> zero-padded channels-last (n,h+1,w+1,4) with our own kernel."""
+    """(n,4,h,w) NCHW -> pixel pairs (n,h+1,w,8): texel (x,y) = [f(x,y,:), f(x+1,y,:)], zero row below."""
     return pack_feature_pyramid([feat])[0]
 
 
 def pack_feature_pyramid(features: Sequence[torch.Tensor]) -> List[torch.Tensor]:
-    """All scales with one C call (gens_pack_feature_maps_multi)."""
+    """All scales with ONE kernel launch (gens_pack_feature_maps_multi)."""
     feats = []
     for f in features:
         _lib.require_cuda(f)
@@ -50,7 +50,7 @@ def pack_feature_pyramid(features: Sequence[torch.Tensor]) -> List[torch.Tensor]
         feats.append(f)
     n = feats[0].shape[0]
     dev = feats[0].device
-    outs = [torch.empty((n, f.shape[2] + 1, f.shape[3] + 1, 4), device=dev, dtype=torch.float32) for f in feats]
+    outs = [torch.empty((n, f.shape[2] + 1, f.shape[3], 8), device=dev, dtype=torch.float32) for f in feats]
     k = len(feats)
     src = (ctypes.c_void_p * k)(*[f.data_ptr() for f in feats])
     dst = (ctypes.c_void_p * k)(*[o.data_ptr() for o in outs])
@@ -123,7 +123,7 @@ class _AggMeanVar(torch.autograd.Function):
             g_vol = _lib.f32c(g_vol)
             nv, _, h, w = shapes[i]
             a0, a1 = slabs[i]
-            g_pad = torch.zeros_like(packed[i])
+            g_pad = torch.zeros((nv, h + 1, w + 1, 4), device=dev, dtype=torch.float32)
             _lib.check(_lib.lib().gens_volume_agg_bwd(
                 _lib.ptr(packed[i]), nv, h, w, _lib.ptr(w2c), _lib.ptr(intrs), 0.5 ** i, _lib.ptr(voxel_axis(d, dev)),
                 d, a0, a1, a0, (a1 - a0) * d * d, int(div_mode), _lib.ptr(g_vol), _lib.ptr(g_pad),
@@ -143,7 +143,9 @@ def agg_mean_var(features, intrs, c2ws, dims, min_vis_view: int = 1,
     (contiguous, fp32) output buffers, e.g. views into an all-gather send buffer.
     Returns (volumes, mask_volumes) as the reference."""
     _lib.require_cuda(intrs, c2ws, *features[:len(dims)])
-    w2c = _lib.f32c(torch.inverse(c2ws))  # same op as the reference (volume.py:34): bit-identical matrices
+    # the reference's torch.inverse (volume.py:34) minus its host-synchronising singularity check: same LU
+    # kernels, bit-identical matrices, and the build stays asynchronous
+    w2c = _lib.f32c(_lib.inverse(c2ws))
     k = _lib.f32c(intrs)
     slabs = [(0, d) for d in dims] if slabs is None else list(slabs)
     out = _AggMeanVar.apply(w2c, k, tuple(dims), tuple(slabs), min_vis_view, div_mode, outs,
@@ -157,7 +159,7 @@ def agg_mean_var_scale(feat, intrs, c2ws, scale: int, d: int, min_vis_view: int 
     """One scale only (tests, slab experiments): same kernels, k_row_scale = 0.5**scale."""
     _lib.require_cuda(feat, intrs, c2ws)
     dev = feat.device
-    w2c, k = _lib.f32c(torch.inverse(c2ws)), _lib.f32c(intrs)
+    w2c, k = _lib.f32c(_lib.inverse(c2ws)), _lib.f32c(intrs)
     a0, a1 = (0, d) if slab is None else slab
 
     class _One(torch.autograd.Function):
@@ -181,7 +183,7 @@ def agg_mean_var_scale(feat, intrs, c2ws, scale: int, d: int, min_vis_view: int 
             (packed,) = ctx.saved_tensors
             nv, _, h, w = ctx.shape
             g_vol = _lib.f32c(g_vol)
-            g_pad = torch.zeros_like(packed)
+            g_pad = torch.zeros((nv, h + 1, w + 1, 4), device=dev, dtype=torch.float32)
             _lib.check(_lib.lib().gens_volume_agg_bwd(
                 _lib.ptr(packed), nv, h, w, _lib.ptr(w2c), _lib.ptr(k), 0.5 ** scale, _lib.ptr(voxel_axis(d, dev)), d,
                 a0, a1, a0, (a1 - a0) * d * d, int(div_mode), _lib.ptr(g_vol), _lib.ptr(g_pad),

@@ -39,9 +39,10 @@ int gens_abi_version(void);
 const char *gens_error_string(int code);
 
 /* ---- layout helpers ---------------------------------------------------------------- */
-/* (n,4,h,w) NCHW -> zero-padded channels-last (n, h+1, w+1, 4): one bilinear corner is a
- * single 16-byte load and the +1 corners of every valid sample exist in memory. */
-int gens_pack_feature_maps(const float *src_nchw, float *dst_padded_nhwc, int n, int h, int w,
+/* (n,4,h,w) NCHW -> "pixel pairs" (n, h+1, w, 8): texel (x,y) = [f(x,y,0..3), f(x+1,y,0..3)],
+ * zeros for y == h and x+1 == w.  A bilinear footprint is two 256-bit loads (top / bottom pair)
+ * and the +1 corners of every valid sample exist in memory. */
+int gens_pack_feature_maps(const float *src_nchw, float *dst_pairs, int n, int h, int w,
                            void *stream);
 /* inverse for gradients: padded channels-last (n, h+1, w+1, 4) -> (n,4,h,w) NCHW */
 int gens_unpack_feature_grads(const float *src_padded_nhwc, float *dst_nchw, int n, int h, int w,
@@ -58,7 +59,7 @@ int gens_unpack_feature_grads(const float *src_padded_nhwc, float *dst_nchw, int
  *                  the kernel, exactly like `intrs_stage[:, :2] *= 0.5**i` (volume.py:24-25)
  * One scale: */
 typedef struct gens_volume_scale {
-    const float *feat_padded; /* (nv,H+1,W+1,4) from gens_pack_feature_maps                 */
+    const float *feat_padded; /* (nv,H+1,W,8) pixel pairs from gens_pack_feature_maps          */
     int H, W;                 /* feature-map size of this scale                              */
     int D;                    /* volume_dims[scale]                                          */
     int a0, a1;               /* planes [a0,a1) of tensor dim 2 (world x) to build (slab)    */
@@ -81,8 +82,8 @@ int gens_volume_agg_fwd(const float *feat_padded, int nv, int H, int W, const fl
                         const float *intrs, float k_row_scale, const float *grid, int D, int a0,
                         int a1, int a_base, long long channel_stride, int min_vis_view,
                         int div_mode, float *volume, float *mask_volume, void *stream);
-/* Pack every scale's (n,4,h_i,w_i) map with one host call. */
-int gens_pack_feature_maps_multi(const float *const *src_nchw, float *const *dst_padded,
+/* Pack every scale's (n,4,h_i,w_i) map with ONE kernel launch. */
+int gens_pack_feature_maps_multi(const float *const *src_nchw, float *const *dst_pairs,
                                  const int *h, const int *w, int n_scales, int n, void *stream);
 
 /* Multi-GPU assembly: after ONE all-gather of the per-rank slab buffers (rank-major, `rank_stride`
@@ -99,8 +100,9 @@ int gens_volume_project_debug(int nv, int H, int W, const float *w2c, const floa
                               int32_t *ix0, int32_t *iy0, uint8_t *valid, void *stream);
 
 /* Backward of K1 w.r.t. the feature maps (the voxel grid is under no_grad in the
- * reference, volume.py:27-44).  grad_volume addressed like `volume` above; grad_feat_padded
- * (nv,H+1,W+1,4) must be zero-initialised by the caller (atomic scatter). */
+ * reference, volume.py:27-44).  feat_padded = the forward's pixel-pair maps; grad_volume addressed
+ * like `volume` above; grad_feat_padded is padded channels-last (nv,H+1,W+1,4), zero-initialised
+ * by the caller (atomic scatter), and goes back to NCHW with gens_unpack_feature_grads. */
 int gens_volume_agg_bwd(const float *feat_padded, int nv, int H, int W, const float *w2c,
                         const float *intrs, float k_row_scale, const float *grid, int D, int a0,
                         int a1, int a_base, long long channel_stride, int div_mode,
