@@ -1,0 +1,408 @@
+// K4: the SDF MLP as ONE persistent tcgen05 kernel (value pass), error-compensated 3xTF32.
+//
+// Replaces, for value-only evaluations (the hierarchical up-sampling loop, SDFNetwork.sdf, the
+// mesh lattice of extract_geometry; reference models/modules/sdf_network.py:98-126), the chain
+//   7 x (cuBLAS SGEMM over all points + bias/softplus kernel)
+// whose (n,128) activations travel through HBM between every two launches, with a kernel that
+// keeps a 128-point tile on chip from the encodings to the SDF value:
+//
+//   * activations h_l live in TENSOR MEMORY as the A operand of the next layer (lane = point,
+//     column = channel), split into a TF32-exact high part and the fp32 remainder;
+//   * the encodings every layer re-reads (position encoding P, 27 ch; volume-feature encoding F,
+//     100 ch) sit in shared memory in the canonical K-major no-swizzle UMMA layout
+//     ([K/4][128 rows][16 B]), also split hi/lo;
+//   * weights stream through a ring of 8 KB shared-memory slots with cp.async.bulk (one k-step =
+//     N x 8 weights, hi and lo, pre-packed on the host in exactly the slot image);
+//   * per k-step three tcgen05.mma.kind::tf32 accumulate  Ah.Bh + Al.Bh + Ah.Bl  into a fp32
+//     accumulator in TMEM: the products dropped (Al.Bl) and the truncation of the low parts are
+//     below 2^-21 relative, so the result matches an fp32 SGEMM to ~1e-6 -- plain TF32 (2^-11)
+//     would not survive softplus(beta = 100) at the stated 1e-4 tolerance;
+//   * 8 epilogue warps pull the accumulator with tcgen05.ld, add the bias, apply softplus, split and
+//     write h_{l+1} back with tcgen05.st; the accumulator is double-buffered so the F/P k-steps of
+//     layer l+1 (which do not depend on h_l) run on the tensor core while layer l's epilogue runs.
+//
+// TMEM columns: [0,128) h hi | [128,256) h lo | [256,384) acc 0 | [384,512) acc 1.
+// Warp roles: 0-7 epilogue / input staging (thread t <-> point t & 127, column half t >> 7),
+//             8 weight producer (+ TMEM allocation), 9 MMA issuer (one elected lane).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kEpiThreads = 256;
+constexpr int kProducerWarp = 8;
+constexpr int kMmaWarp = 9;
+constexpr int kThreads = 320;
+constexpr int kWSlotBytes = 8192;
+constexpr int kWStages = 6;
+constexpr int kFChunks = 26;              // feature encoding: K = 104 (100 + 4 zero columns)
+constexpr int kPChunks = 8;               // position encoding: K = 32 (27 + 5 zero columns)
+constexpr int kChunkBytes = kTileM * 16;  // one 16-byte K chunk of all 128 rows
+constexpr int kMaxLayers = 8;
+constexpr int kMaxKSteps = 256;
+
+// shared-memory map (bytes)
+constexpr int kOffFhi = 0;
+constexpr int kOffFlo = kOffFhi + kFChunks * kChunkBytes;
+constexpr int kOffPhi = kOffFlo + kFChunks * kChunkBytes;
+constexpr int kOffPlo = kOffPhi + kPChunks * kChunkBytes;
+constexpr int kOffW = kOffPlo + kPChunks * kChunkBytes;
+constexpr int kOffBias = kOffW + kWStages * kWSlotBytes;
+constexpr int kOffBar = kOffBias + kMaxLayers * 128 * 4;
+constexpr int kNumBars = 2 * kWStages + 4;  // full[], empty[], acc_full[2], h_ready, in_ready
+constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
+constexpr int kSmemBytes = kOffTmemPtr + 16;
+
+constexpr uint32_t kColHhi = 0, kColHlo = 128, kColAcc = 256;
+
+struct KStep {
+    uint32_t w_off;    // byte offset of this k-step's [hi | lo] weight block in the stream
+    uint32_t w_bytes;  // N * 64
+    uint32_t a;        // bits 0-7: A source (0 = F smem, 1 = P smem, 2 = h TMEM); bits 8-15: k-step inside it
+    uint32_t flags;    // bit 0 first of layer, bit 1 last of layer, bit 2 first k-step that needs h; bits 16-24 N
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, M = 128, kind::tf32
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// same with A from tensor memory
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+// K-major, no swizzle: element (row r, 16-byte chunk c) at start + (r % 8) * 16 + (r / 8) * SBO + c * LBO
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3ffff) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+    return d;                // base offset 0, layout type 0 (no swizzle)
+}
+// instruction descriptor: D fp32, A/B tf32, both K-major, M = 128
+__device__ __forceinline__ uint32_t instr_desc(uint32_t n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+#define TC_REGS32(v)                                                                                             \
+    v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15], v[16], \
+        v[17], v[18], v[19], v[20], v[21], v[22], v[23], v[24], v[25], v[26], v[27], v[28], v[29], v[30], v[31]
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// TF32-exact high part (round to nearest on the 13 dropped bits) and the exact fp32 remainder
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    const uint32_t h = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    hi = h;
+    lo = __float_as_uint(x - __uint_as_float(h));
+}
+
+// torch.nn.Softplus(beta = 100, threshold = 20) (reference sdf_network.py:95): a if 100 a > 20 else
+// log1p(exp(100 a)) / 100, in the overflow-free form max(t,0) + log(1 + exp(-|t|)).  ex2/lg2.approx are
+// exact to ~2^-22, which after the division by beta is ~1e-9 absolute on activations of order 0.1 - 1.
+__device__ __forceinline__ float softplus100(float a) {
+    const float t = a * 100.0f;
+    float e, l;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(t) * 1.4426950408889634f));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
+    const float sp = (fmaxf(t, 0.0f) + l * 0.6931471805599453f) * 0.01f;
+    return t > 20.0f ? a : sp;
+}
+
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+sdf_mlp_value_kernel(const float* __restrict__ pos,   // (n, 27) position encoding
+                     const float* __restrict__ fe,    // (n, 100) volume-feature encoding
+                     long long n, const float* __restrict__ wstream, const KStep* __restrict__ ksteps, int n_ksteps,
+                     const float* __restrict__ bias,  // (n_layers, 128)
+                     int n_layers, float scale, float* __restrict__ sdf_out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t s_base = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = s_base + kOffBar;
+    auto bar_full = [&](int s) { return bar0 + 8u * s; };
+    auto bar_empty = [&](int s) { return bar0 + 8u * (kWStages + s); };
+    const uint32_t bar_acc0 = bar0 + 8u * (2 * kWStages), bar_acc1 = bar_acc0 + 8, bar_h = bar_acc0 + 16,
+                   bar_in = bar_acc0 + 24;
+    float* s_bias = reinterpret_cast<float*>(smem + kOffBias);
+    volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
+
+    // ---- one-time setup ------------------------------------------------------------------------------
+    for (int i = threadIdx.x; i < n_layers * 128; i += kThreads) s_bias[i] = bias[i];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kWStages; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_empty(s), 1);
+        }
+        mbar_init(bar_acc0, 1);
+        mbar_init(bar_acc1, 1);
+        mbar_init(bar_h, kEpiThreads);
+        mbar_init(bar_in, kEpiThreads);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kProducerWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_base + kOffTmemPtr),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+
+    const long long n_tiles = (n + kTileM - 1) / kTileM;
+
+    if (warp == kProducerWarp) {
+        // ===== weight producer: the same k-step stream for every tile ==================================
+        if (lane == 0) {
+            uint32_t slot = 0, phase = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int ks = 0; ks < n_ksteps; ++ks) {
+                    const KStep st = ksteps[ks];
+                    mbar_wait(bar_empty(slot), phase ^ 1);
+                    mbar_arrive_expect_tx(bar_full(slot), st.w_bytes);
+                    bulk_g2s(s_base + kOffW + slot * kWSlotBytes, reinterpret_cast<const uint8_t*>(wstream) + st.w_off,
+                             st.w_bytes, bar_full(slot));
+                    if (++slot == kWStages) {
+                        slot = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ===== MMA issuer ==============================================================================
+        if (lane == 0) {
+            uint32_t slot = 0, phase = 0, in_phase = 0, h_phase = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                mbar_wait(bar_in, in_phase);
+                in_phase ^= 1;
+                tc_fence_after();
+                int layer = 0;
+                uint32_t acc_on = 0;
+                for (int ks = 0; ks < n_ksteps; ++ks) {
+                    const KStep st = ksteps[ks];
+                    const uint32_t nn = (st.flags >> 16) & 0x1ff;
+                    const uint32_t idesc = instr_desc(nn);
+                    const uint32_t d_tmem = tmem + kColAcc + (layer & 1) * 128;
+                    if (st.flags & 1u) acc_on = 0;
+                    if (st.flags & 4u) {  // h of the previous layer must be in tensor memory
+                        mbar_wait(bar_h, h_phase);
+                        h_phase ^= 1;
+                        tc_fence_after();
+                    }
+                    mbar_wait(bar_full(slot), phase);
+                    tc_fence_after();
+                    const uint32_t w_hi = s_base + kOffW + slot * kWSlotBytes, w_lo = w_hi + nn * 32;
+                    const uint64_t b_hi = smem_desc(w_hi, nn * 16, 128), b_lo = smem_desc(w_lo, nn * 16, 128);
+                    const uint32_t kind = st.a & 0xff, kidx = (st.a >> 8) & 0xff;
+                    if (kind == 2) {
+                        const uint32_t a_hi = tmem + kColHhi + kidx * 8, a_lo = tmem + kColHlo + kidx * 8;
+                        mma_ts(d_tmem, a_hi, b_hi, idesc, acc_on);
+                        mma_ts(d_tmem, a_lo, b_hi, idesc, 1);
+                        mma_ts(d_tmem, a_hi, b_lo, idesc, 1);
+                    } else {
+                        const uint32_t off_hi = kind == 0 ? kOffFhi : kOffPhi, off_lo = kind == 0 ? kOffFlo : kOffPlo;
+                        const uint64_t a_hi = smem_desc(s_base + off_hi + kidx * 2 * kChunkBytes, kChunkBytes, 128);
+                        const uint64_t a_lo = smem_desc(s_base + off_lo + kidx * 2 * kChunkBytes, kChunkBytes, 128);
+                        mma_ss(d_tmem, a_hi, b_hi, idesc, acc_on);
+                        mma_ss(d_tmem, a_lo, b_hi, idesc, 1);
+                        mma_ss(d_tmem, a_hi, b_lo, idesc, 1);
+                    }
+                    acc_on = 1;
+                    tc_commit(bar_empty(slot));  // slot free once these MMAs have read it
+                    if (st.flags & 2u) {
+                        tc_commit((layer & 1) ? bar_acc1 : bar_acc0);
+                        ++layer;
+                    }
+                    if (++slot == kWStages) {
+                        slot = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else {
+        // ===== input staging + epilogue (threads 0..255) =================================================
+        const int row = threadIdx.x & 127, half = threadIdx.x >> 7;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        uint32_t acc_phase[2] = {0, 0};
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            // -- encodings of this tile -> shared memory, split hi/lo (the previous tile's MMAs are done:
+            //    this thread has already waited for its last accumulator)
+            const long long p = tile * kTileM + row;
+            const bool live = p < n;
+            {
+                const float* src = fe + p * 100;
+                for (int c = half * 13; c < half * 13 + 13; ++c) {
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[e] = (live && 4 * c + e < 100) ? __ldg(src + 4 * c + e) : 0.0f;
+                    uint4 hi, lo;
+                    split_tf32(v[0], hi.x, lo.x);
+                    split_tf32(v[1], hi.y, lo.y);
+                    split_tf32(v[2], hi.z, lo.z);
+                    split_tf32(v[3], hi.w, lo.w);
+                    *reinterpret_cast<uint4*>(smem + kOffFhi + c * kChunkBytes + row * 16) = hi;
+                    *reinterpret_cast<uint4*>(smem + kOffFlo + c * kChunkBytes + row * 16) = lo;
+                }
+                const float* psrc = pos + p * 27;
+                for (int c = half * 4; c < half * 4 + 4; ++c) {
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[e] = (live && 4 * c + e < 27) ? __ldg(psrc + 4 * c + e) : 0.0f;
+                    uint4 hi, lo;
+                    split_tf32(v[0], hi.x, lo.x);
+                    split_tf32(v[1], hi.y, lo.y);
+                    split_tf32(v[2], hi.z, lo.z);
+                    split_tf32(v[3], hi.w, lo.w);
+                    *reinterpret_cast<uint4*>(smem + kOffPhi + c * kChunkBytes + row * 16) = hi;
+                    *reinterpret_cast<uint4*>(smem + kOffPlo + c * kChunkBytes + row * 16) = lo;
+                }
+            }
+            fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
+            tc_fence_before();    // orders this thread's earlier tcgen05.ld of the accumulators
+            mbar_arrive(bar_in);
+
+            for (int layer = 0; layer < n_layers; ++layer) {
+                const int st = layer & 1;
+                mbar_wait(st ? bar_acc1 : bar_acc0, acc_phase[st]);
+                acc_phase[st] ^= 1;
+                tc_fence_after();
+                const uint32_t acc = tmem + lane_base + kColAcc + st * 128;
+                if (layer + 1 < n_layers) {
+                    const float* b = s_bias + layer * 128;
+#pragma unroll 1
+                    for (int blk = 0; blk < 2; ++blk) {
+                        const int col0 = half * 64 + blk * 32;
+                        uint32_t v[32], hi[32], lo[32];
+                        tmem_ld32(acc + col0, v);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float h = softplus100(__uint_as_float(v[j]) + b[col0 + j]);
+                            split_tf32(h, hi[j], lo[j]);
+                        }
+                        tmem_st32(tmem + lane_base + kColHhi + col0, hi);
+                        tmem_st32(tmem + lane_base + kColHlo + col0, lo);
+                    }
+                    tmem_wait_st();
+                    tc_fence_before();
+                    mbar_arrive(bar_h);
+                } else {
+                    if (half == 0) {
+                        const uint32_t v = tmem_ld1(acc);
+                        tmem_wait_ld();
+                        if (live) sdf_out[p] = __fdiv_rn(__uint_as_float(v) + s_bias[layer * 128], scale);
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- teardown --------------------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kProducerWarp) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+}  // namespace
+
+// Value pass of the SDF MLP on the tensor cores.  pos (n,27) / fe (n,100): the encodings produced by
+// gens_sdf_encode; wstream / ksteps / bias: the packed network (gens_b200/mlp_tc.py documents the format);
+// sdf_out (n).  n_sm = number of CTAs to launch (<= SM count; one persistent CTA per SM).
+extern "C" int gens_sdf_mlp_value_tc(const float* pos, const float* fe, long long n, const float* wstream,
+                                     const void* ksteps, int n_ksteps, const float* bias, int n_layers, float scale,
+                                     int n_sm, float* sdf_out, void* stream) {
+    GENS_CHECK_ARG(pos && fe && wstream && ksteps && bias && sdf_out && n >= 0 && n_sm > 0);
+    if (n_ksteps <= 0 || n_ksteps > kMaxKSteps || n_layers <= 0 || n_layers > kMaxLayers || scale == 0.f)
+        return GENS_E_UNSUPPORTED;
+    if (n == 0) return 0;
+    cudaError_t e = cudaFuncSetAttribute(sdf_mlp_value_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    const long long tiles = (n + kTileM - 1) / kTileM;
+    const int grid = (int)(tiles < n_sm ? tiles : n_sm);
+    sdf_mlp_value_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
+        pos, fe, n, wstream, reinterpret_cast<const KStep*>(ksteps), n_ksteps, bias, n_layers, scale, sdf_out);
+    return gens_launch_status();
+}

@@ -1,0 +1,153 @@
+"""Tensor-core (tcgen05, 3xTF32) value pass of the SDF MLP -- host side of csrc/sdf_mlp_tc.cu.
+
+The network of reference models/modules/sdf_network.py:98-123 is re-expressed as a stream of "k-steps":
+one k-step = 8 input channels of one layer, i.e. an (N_l x 8) weight block that the kernel multiplies
+with a (128 x 8) slice of one of three resident A operands,
+
+    F  the 100-channel volume-feature encoding (shared memory, same for every layer >= 1),
+    P  the 27-channel position encoding        (shared memory; layer 0 and the skip layer),
+    H  the previous layer's activations        (tensor memory),
+
+and accumulates into that layer's fp32 accumulator.  Per layer the F and P k-steps come first (they do not
+depend on the previous layer, so they overlap its epilogue), the H k-steps last.
+
+Packed format (what gens_sdf_mlp_value_tc expects):
+  wstream  float32: per k-step [hi block | lo block]; a block is the (N_l x 8) weights as [2][N_l][4]
+           (two 16-byte K chunks, rows contiguous inside a chunk: the canonical K-major no-swizzle UMMA
+           layout with LBO = 16 N_l bytes, SBO = 128 bytes); hi = weights rounded to TF32, lo = w - hi.
+  ksteps   uint32 (n,4): byte offset, byte count (64 N_l), A source | index << 8,
+           flags (1 first of layer, 2 last of layer, 4 first H k-step) | N_l << 16.
+  bias     float32 (n_layers, 128), zero padded.
+Fan-outs are padded to multiples of 16 with zero rows (101 -> 112, the single SDF row -> 16), fan-ins to
+multiples of 8 with zero columns; the 1/sqrt(2) of the skip connection is folded into that layer's weights.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Tuple
+
+import torch
+
+from . import _lib
+
+A_F, A_P, A_H = 0, 1, 2
+F_K, P_K = 104, 32  # padded widths of the resident encodings (csrc/sdf_mlp_tc.cu kFChunks / kPChunks)
+
+
+def _split_tf32(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    hi = ((w.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+    return hi, w - hi
+
+
+def _blocks(w: torch.Tensor, n_pad: int) -> torch.Tensor:
+    """(fo, k) weights -> (k_pad/8, 2 [hi, lo], 2 chunks, n_pad rows, 4) blocks."""
+    fo, k = w.shape
+    k_pad = (k + 7) // 8 * 8
+    full = w.new_zeros((n_pad, k_pad))
+    full[:fo, :k] = w
+    hi, lo = _split_tf32(full)
+    tiles = [t.reshape(n_pad, k_pad // 8, 2, 4).permute(1, 2, 0, 3) for t in (hi, lo)]
+    return torch.stack(tiles, dim=1).contiguous()
+
+
+class PackedSDF:
+    """The folded SDF network in the kernel's streaming format (built once per weight version)."""
+
+    def __init__(self, fw):
+        """`fw` is a sdf_analytic.FoldedSDF."""
+        if fw.pe_in > P_K or fw.pe_feat > F_K:
+            raise RuntimeError("gens_b200 tensor-core SDF kernel: encodings wider than the resident operands")
+        dev = fw.wx[0].device
+        last = fw.n_layers - 1
+        inv_sqrt2 = 1.0 / math.sqrt(2.0)
+        chunks: List[torch.Tensor] = []
+        steps: List[List[int]] = []
+        off = 0
+        bias = torch.zeros((fw.n_layers, 128), device=dev, dtype=torch.float32)
+        for l in range(fw.n_layers):
+            fo = fw.fo[l]
+            n_pad = (fo + 15) // 16 * 16
+            if n_pad > 128:
+                raise RuntimeError("gens_b200 tensor-core SDF kernel: layers wider than 128 are not supported")
+            bias[l, :fo] = fw.bias[l]
+            segs = []
+            wx = fw.wx[l]
+            if l >= 1:
+                segs.append((A_F, fw.wf[fw.off[l - 1]: fw.off[l - 1] + fo]))
+            if l == 0:
+                segs.append((A_P, wx))
+            elif l in fw.skip_in:
+                h_in = fw.fo[l - 1]
+                segs.append((A_P, wx[:, h_in:] * inv_sqrt2))
+                segs.append((A_H, wx[:, :h_in] * inv_sqrt2))
+            else:
+                segs.append((A_H, wx))
+            first = True
+            for si, (kind, w) in enumerate(segs):
+                blk = _blocks(w.float(), n_pad)
+                nb = blk.shape[0]
+                nbytes = n_pad * 64
+                for j in range(nb):
+                    flags = n_pad << 16
+                    if first:
+                        flags |= 1
+                        first = False
+                    if kind == A_H and j == 0:
+                        flags |= 4
+                    if si == len(segs) - 1 and j == nb - 1:
+                        flags |= 2
+                    steps.append([off, nbytes, kind | (j << 8), flags])
+                    off += nbytes
+                chunks.append(blk.reshape(-1))
+        self.wstream = torch.cat(chunks).contiguous()
+        assert self.wstream.numel() * 4 == off
+        self.ksteps = torch.tensor(steps, dtype=torch.int64, device="cpu").to(torch.int32).to(dev).contiguous()
+        self.n_ksteps = len(steps)
+        self.bias = bias.contiguous()
+        self.n_layers = fw.n_layers
+        self.scale = float(fw.scale)
+        self.n_sm = torch.cuda.get_device_properties(dev).multi_processor_count if dev.type == "cuda" else 0
+
+
+def sdf_values(packed: PackedSDF, pos: torch.Tensor, fe: torch.Tensor) -> torch.Tensor:
+    """(n,27) position encoding, (n,100) feature encoding -> (n,1) SDF values."""
+    _lib.require_cuda(pos, fe)
+    n = pos.shape[0]
+    out = torch.empty((n, 1), device=pos.device, dtype=torch.float32)
+    _lib.check(_lib.lib().gens_sdf_mlp_value_tc(
+        _lib.ptr(pos), _lib.ptr(fe), n, _lib.ptr(packed.wstream), _lib.ptr(packed.ksteps), packed.n_ksteps,
+        _lib.ptr(packed.bias), packed.n_layers, packed.scale, packed.n_sm, _lib.ptr(out),
+        _lib.stream_ptr(pos.device)), "gens_sdf_mlp_value_tc")
+    return out
+
+
+def emulate(packed: PackedSDF, pos: torch.Tensor, fe: torch.Tensor) -> torch.Tensor:
+    """Host restatement of the kernel's k-step machine in float64 (tests only: checks the packing, not the
+    tensor-core arithmetic).  Same inputs and result as sdf_values."""
+    n = pos.shape[0]
+    srcs = {A_F: torch.zeros((n, F_K), dtype=torch.float64), A_P: torch.zeros((n, P_K), dtype=torch.float64),
+            A_H: torch.zeros((n, 128), dtype=torch.float64)}
+    srcs[A_F][:, :fe.shape[1]] = fe.double().cpu()
+    srcs[A_P][:, :pos.shape[1]] = pos.double().cpu()
+    stream = packed.wstream.double().cpu()
+    acc = None
+    layer = 0
+    for off, nbytes, a, flags in packed.ksteps.cpu().tolist():
+        n_pad = (flags >> 16) & 0x1ff
+        assert nbytes == n_pad * 64 and off % 16 == 0
+        blk = stream[off // 4: off // 4 + nbytes // 4].reshape(2, 2, n_pad, 4)
+        w = (blk[0] + blk[1]).permute(1, 0, 2).reshape(n_pad, 8)          # hi + lo, (N, 8)
+        kind, j = a & 0xff, (a >> 8) & 0xff
+        if flags & 1:
+            acc = torch.zeros((n, n_pad), dtype=torch.float64)
+        acc = acc + srcs[kind][:, 8 * j: 8 * j + 8] @ w.t()
+        if flags & 2:
+            y = acc + packed.bias[layer, :n_pad].double().cpu()
+            if layer + 1 < packed.n_layers:
+                t = y * 100.0
+                srcs[A_H] = torch.zeros((n, 128), dtype=torch.float64)
+                srcs[A_H][:, :n_pad] = torch.where(t > 20.0, y, torch.log1p(torch.exp(t.clamp(max=20.0))) / 100.0)
+            else:
+                return (y[:, :1] / packed.scale).float()
+            layer += 1
+    raise RuntimeError("k-step stream ended without an output layer")

@@ -227,6 +227,16 @@ int gens_sdf_decode(const float *pts, const float *feats, const float *dfeats, c
                     int feat_multires, int n_feat, float *g_f, float *dg_f, float *grad, float *smooth,
                     void *stream);
 
+/* K4 on the tensor cores: value pass of the whole SDF MLP (reference models/modules/sdf_network.py:98-126,
+ * SDFNetwork.forward(...)[:, :1] / .sdf) as ONE persistent tcgen05 kernel, error-compensated 3xTF32
+ * (fp32-level accuracy), activations resident in tensor memory, weights streamed through shared memory.
+ * pos (n,27) / fe (n,100) = the encodings written by gens_sdf_encode (primal rows); wstream / ksteps /
+ * bias = the network packed as gens_b200/mlp_tc.py documents (ksteps: n_ksteps x 4 uint32); n_sm = number
+ * of persistent CTAs (<= SMs of the device); sdf_out (n). */
+int gens_sdf_mlp_value_tc(const float *pos, const float *fe, long long n, const float *wstream,
+                          const void *ksteps, int n_ksteps, const float *bias, int n_layers, float scale,
+                          int n_sm, float *sdf_out, void *stream);
+
 /* Tuning knob for profiling sessions: selects among compiled-in launch configurations of K1
  * (0 = the shipped one).  Results are identical for every variant. */
 int gens_debug_set_variant(int variant);

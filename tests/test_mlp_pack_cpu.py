@@ -1,0 +1,40 @@
+"""Packing of the SDF network for the tcgen05 kernel (gens_b200/mlp_tc.py), checked on the host: the
+k-step stream, replayed by a float64 emulator of the kernel's schedule, must reproduce SDFNetwork.sdf."""
+import torch
+
+from gens_b200 import mlp_tc
+from gens_b200.config import gens_model_conf
+from gens_b200.implicit_surface import ImplicitSurface
+from gens_b200.networks import positional_encoding
+from gens_b200.sdf_analytic import FoldedSDF
+from oracle.torch_oracle import CpuOps
+
+
+def test_kstep_stream_reproduces_the_network():
+    torch.manual_seed(0)
+    surf = ImplicitSurface(gens_model_conf(perturb=0.0)["implicit_surface"], ops=CpuOps)
+    net = surf.sdf_network
+    with torch.no_grad():
+        for p in net.parameters():          # leave the geometric init: exercise every weight
+            p.add_(torch.randn_like(p) * 0.05)
+    packed = mlp_tc.PackedSDF(FoldedSDF(net))
+    dims = [16, 8, 4, 2, 2]
+    vols = [torch.randn(1, 4, d, d, d) * 0.5 for d in dims]
+    pts = torch.rand(300, 3) * 2 - 1
+    with torch.no_grad():
+        ref = net.sdf(pts, vols)
+        fe = positional_encoding(CpuOps.lookup_volume(pts, vols), net.feat_multires)
+        pos = positional_encoding(pts * net.scale, net.multires)
+    out = mlp_tc.emulate(packed, pos, fe)
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+
+    # structure: every block is 16-byte aligned, hi parts are TF32-exact, flags are consistent
+    ks = packed.ksteps.cpu()
+    assert ks.shape == (packed.n_ksteps, 4) and packed.n_ksteps <= 256
+    assert int((ks[:, 3] & 1).ne(0).sum()) == packed.n_layers and int((ks[:, 3] & 2).ne(0).sum()) == packed.n_layers
+    assert int((ks[:, 3] & 4).ne(0).sum()) == packed.n_layers - 1
+    assert bool(((ks[:, 0] % 16) == 0).all()) and int(ks[:, 1].max()) <= 8192
+    off, nbytes = int(ks[0, 0]), int(ks[0, 1])
+    hi = packed.wstream[off // 4: off // 4 + nbytes // 8]
+    assert bool(((hi.view(torch.int32) & 0x1fff) == 0).all())
