@@ -11,9 +11,9 @@
 //   * the encodings every layer re-reads (position encoding P, 27 ch; volume-feature encoding F,
 //     100 ch) sit in shared memory in the canonical K-major no-swizzle UMMA layout
 //     ([K/4][128 rows][16 B]), also split hi/lo;
-//   * weights stream through a ring of 8 KB shared-memory slots with cp.async.bulk (one k-step =
-//     N x 8 weights, hi and lo, pre-packed on the host in exactly the slot image);
-//   * per k-step three tcgen05.mma.kind::tf32 accumulate  Ah.Bh + Al.Bh + Ah.Bl  into a fp32
+//   * weights stream through a ring of 16 KB shared-memory slots with cp.async.bulk (one k-step =
+//     N x 16 weights, hi and lo, pre-packed on the host in exactly the slot image);
+//   * per 8 channels three tcgen05.mma.kind::tf32 accumulate  Ah.Bh + Al.Bh + Ah.Bl  into a fp32
 //     accumulator in TMEM: the products dropped (Al.Bl) and the truncation of the low parts are
 //     below 2^-21 relative, so the result matches an fp32 SGEMM to ~1e-6 -- plain TF32 (2^-11)
 //     would not survive softplus(beta = 100) at the stated 1e-4 tolerance;
@@ -33,13 +33,13 @@ constexpr int kEpiThreads = 256;
 constexpr int kProducerWarp = 8;
 constexpr int kMmaWarp = 9;
 constexpr int kThreads = 320;
-constexpr int kWSlotBytes = 8192;
-constexpr int kWStages = 6;
-constexpr int kFChunks = 26;              // feature encoding: K = 104 (100 + 4 zero columns)
+constexpr int kWSlotBytes = 16384;        // one k-step = 16 input channels: N x 16 weights, hi and lo
+constexpr int kWStages = 4;
+constexpr int kFChunks = 28;              // feature encoding: K = 112 (100 + 12 zero columns)
 constexpr int kPChunks = 8;               // position encoding: K = 32 (27 + 5 zero columns)
 constexpr int kChunkBytes = kTileM * 16;  // one 16-byte K chunk of all 128 rows
 constexpr int kMaxLayers = 8;
-constexpr int kMaxKSteps = 256;
+constexpr int kMaxKSteps = 128;
 
 // shared-memory map (bytes)
 constexpr int kOffFhi = 0;
@@ -48,7 +48,8 @@ constexpr int kOffPhi = kOffFlo + kFChunks * kChunkBytes;
 constexpr int kOffPlo = kOffPhi + kPChunks * kChunkBytes;
 constexpr int kOffW = kOffPlo + kPChunks * kChunkBytes;
 constexpr int kOffBias = kOffW + kWStages * kWSlotBytes;
-constexpr int kOffBar = kOffBias + kMaxLayers * 128 * 4;
+constexpr int kOffSteps = kOffBias + kMaxLayers * 128 * 4;  // per k-step issue records (uint4)
+constexpr int kOffBar = kOffSteps + kMaxKSteps * 16;
 constexpr int kNumBars = 2 * kWStages + 4;  // full[], empty[], acc_full[2], h_ready, in_ready
 constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
@@ -57,8 +58,8 @@ constexpr uint32_t kColHhi = 0, kColHlo = 128, kColAcc = 256;
 
 struct KStep {
     uint32_t w_off;    // byte offset of this k-step's [hi | lo] weight block in the stream
-    uint32_t w_bytes;  // N * 64
-    uint32_t a;        // bits 0-7: A source (0 = F smem, 1 = P smem, 2 = h TMEM); bits 8-15: k-step inside it
+    uint32_t w_bytes;  // N * 128
+    uint32_t a;        // bits 0-7: A source (0 = F smem, 1 = P smem, 2 = h TMEM); bits 8-15: k-step inside it (K / 16)
     uint32_t flags;    // bit 0 first of layer, bit 1 last of layer, bit 2 first k-step that needs h; bits 16-24 N
 };
 
@@ -96,6 +97,16 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred;
 }
 
 // D[tmem] (+)= A[smem desc] . B[smem desc]^T, M = 128, kind::tf32
@@ -205,6 +216,24 @@ sdf_mlp_value_kernel(const float* __restrict__ pos,   // (n, 27) position encodi
 
     // ---- one-time setup ------------------------------------------------------------------------------
     for (int i = threadIdx.x; i < n_layers * 128; i += kThreads) s_bias[i] = bias[i];
+    // issue records: x = A hi (descriptor low word, or TMEM column), y = A lo, z = flags | N << 16, w = bytes
+    uint4* s_steps = reinterpret_cast<uint4*>(smem + kOffSteps);
+    for (int i = threadIdx.x; i < n_ksteps; i += kThreads) {
+        const KStep st = ksteps[i];
+        const uint32_t kind = st.a & 0xff, kidx = (st.a >> 8) & 0xff;
+        uint4 r;
+        if (kind == 2) {
+            r.x = kColHhi + kidx * 16;
+            r.y = kColHlo + kidx * 16;
+        } else {
+            const uint32_t off_hi = kind == 0 ? kOffFhi : kOffPhi, off_lo = kind == 0 ? kOffFlo : kOffPlo;
+            r.x = (uint32_t)smem_desc(s_base + off_hi + kidx * 4 * kChunkBytes, kChunkBytes, 128);
+            r.y = (uint32_t)smem_desc(s_base + off_lo + kidx * 4 * kChunkBytes, kChunkBytes, 128);
+        }
+        r.z = st.flags | (kind == 2 ? 8u : 0u);
+        r.w = st.w_bytes;
+        s_steps[i] = r;
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < kWStages; ++s) {
             mbar_init(bar_full(s), 1);
@@ -234,12 +263,14 @@ sdf_mlp_value_kernel(const float* __restrict__ pos,   // (n, 27) position encodi
         if (lane == 0) {
             uint32_t slot = 0, phase = 0;
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                uint32_t w_off = 0;  // the blocks are contiguous in the stream
                 for (int ks = 0; ks < n_ksteps; ++ks) {
-                    const KStep st = ksteps[ks];
+                    const uint32_t w_bytes = s_steps[ks].w;
                     mbar_wait(bar_empty(slot), phase ^ 1);
-                    mbar_arrive_expect_tx(bar_full(slot), st.w_bytes);
-                    bulk_g2s(s_base + kOffW + slot * kWSlotBytes, reinterpret_cast<const uint8_t*>(wstream) + st.w_off,
-                             st.w_bytes, bar_full(slot));
+                    mbar_arrive_expect_tx(bar_full(slot), w_bytes);
+                    bulk_g2s(s_base + kOffW + slot * kWSlotBytes, reinterpret_cast<const uint8_t*>(wstream) + w_off,
+                             w_bytes, bar_full(slot));
+                    w_off += w_bytes;
                     if (++slot == kWStages) {
                         slot = 0;
                         phase ^= 1;
@@ -248,54 +279,62 @@ sdf_mlp_value_kernel(const float* __restrict__ pos,   // (n, 27) position encodi
             }
         }
     } else if (warp == kMmaWarp) {
-        // ===== MMA issuer ==============================================================================
-        if (lane == 0) {
-            uint32_t slot = 0, phase = 0, in_phase = 0, h_phase = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                mbar_wait(bar_in, in_phase);
-                in_phase ^= 1;
+        // ===== MMA issuer: the whole warp walks the k-steps (uniform control flow and addresses), one elected
+        // lane issues.  Per k-step: 2 x (Ah.Bh + Al.Bh + Ah.Bl) over 8 channels each.
+        const uint32_t elected = elect_one();
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1 (bits 32-47)
+        uint32_t slot = 0, phase = 0, in_phase = 0, h_phase = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(bar_in, in_phase);
+            in_phase ^= 1;
+            tc_fence_after();
+            uint32_t layer = 0, acc_on = 0;
+            uint4 rec = s_steps[0];
+            for (int ks = 0; ks < n_ksteps; ++ks) {
+                const uint4 cur = rec;
+                if (ks + 1 < n_ksteps) rec = s_steps[ks + 1];
+                const uint32_t flags = cur.z, nn = (flags >> 16) & 0x1ff;
+                const uint32_t idesc = instr_desc(nn);
+                const uint32_t d_tmem = tmem + kColAcc + (layer & 1) * 128;
+                if (flags & 1u) acc_on = 0;
+                if (flags & 4u) {  // h of the previous layer must be in tensor memory
+                    mbar_wait(bar_h, h_phase);
+                    h_phase ^= 1;
+                }
+                mbar_wait(bar_full(slot), phase);
                 tc_fence_after();
-                int layer = 0;
-                uint32_t acc_on = 0;
-                for (int ks = 0; ks < n_ksteps; ++ks) {
-                    const KStep st = ksteps[ks];
-                    const uint32_t nn = (st.flags >> 16) & 0x1ff;
-                    const uint32_t idesc = instr_desc(nn);
-                    const uint32_t d_tmem = tmem + kColAcc + (layer & 1) * 128;
-                    if (st.flags & 1u) acc_on = 0;
-                    if (st.flags & 4u) {  // h of the previous layer must be in tensor memory
-                        mbar_wait(bar_h, h_phase);
-                        h_phase ^= 1;
-                        tc_fence_after();
+                // B: [hi: 4 chunks][lo: 4 chunks], chunk = N rows x 16 B
+                const uint32_t w_addr = s_base + kOffW + slot * kWSlotBytes;
+                const uint32_t b_lo32 = ((w_addr & 0x3ffff) >> 4) | (nn << 16);  // LBO = 16 N bytes
+                const uint32_t b_step = 2 * nn, b_lopart = 4 * nn;               // in 16-byte units
+                if (elected) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const uint64_t b_hi = ((uint64_t)desc_hi << 32) | (b_lo32 + j * b_step);
+                        const uint64_t b_lo = ((uint64_t)desc_hi << 32) | (b_lo32 + b_lopart + j * b_step);
+                        if (flags & 8u) {
+                            const uint32_t a_hi = tmem + cur.x + j * 8, a_lo = tmem + cur.y + j * 8;
+                            mma_ts(d_tmem, a_hi, b_hi, idesc, acc_on);
+                            mma_ts(d_tmem, a_lo, b_hi, idesc, 1);
+                            mma_ts(d_tmem, a_hi, b_lo, idesc, 1);
+                        } else {
+                            const uint64_t a_hi = ((uint64_t)desc_hi << 32) | (cur.x + j * (2 * kChunkBytes >> 4));
+                            const uint64_t a_lo = ((uint64_t)desc_hi << 32) | (cur.y + j * (2 * kChunkBytes >> 4));
+                            mma_ss(d_tmem, a_hi, b_hi, idesc, acc_on);
+                            mma_ss(d_tmem, a_lo, b_hi, idesc, 1);
+                            mma_ss(d_tmem, a_hi, b_lo, idesc, 1);
+                        }
+                        acc_on = 1;
                     }
-                    mbar_wait(bar_full(slot), phase);
-                    tc_fence_after();
-                    const uint32_t w_hi = s_base + kOffW + slot * kWSlotBytes, w_lo = w_hi + nn * 32;
-                    const uint64_t b_hi = smem_desc(w_hi, nn * 16, 128), b_lo = smem_desc(w_lo, nn * 16, 128);
-                    const uint32_t kind = st.a & 0xff, kidx = (st.a >> 8) & 0xff;
-                    if (kind == 2) {
-                        const uint32_t a_hi = tmem + kColHhi + kidx * 8, a_lo = tmem + kColHlo + kidx * 8;
-                        mma_ts(d_tmem, a_hi, b_hi, idesc, acc_on);
-                        mma_ts(d_tmem, a_lo, b_hi, idesc, 1);
-                        mma_ts(d_tmem, a_hi, b_lo, idesc, 1);
-                    } else {
-                        const uint32_t off_hi = kind == 0 ? kOffFhi : kOffPhi, off_lo = kind == 0 ? kOffFlo : kOffPlo;
-                        const uint64_t a_hi = smem_desc(s_base + off_hi + kidx * 2 * kChunkBytes, kChunkBytes, 128);
-                        const uint64_t a_lo = smem_desc(s_base + off_lo + kidx * 2 * kChunkBytes, kChunkBytes, 128);
-                        mma_ss(d_tmem, a_hi, b_hi, idesc, acc_on);
-                        mma_ss(d_tmem, a_lo, b_hi, idesc, 1);
-                        mma_ss(d_tmem, a_hi, b_lo, idesc, 1);
-                    }
-                    acc_on = 1;
                     tc_commit(bar_empty(slot));  // slot free once these MMAs have read it
-                    if (st.flags & 2u) {
-                        tc_commit((layer & 1) ? bar_acc1 : bar_acc0);
-                        ++layer;
-                    }
-                    if (++slot == kWStages) {
-                        slot = 0;
-                        phase ^= 1;
-                    }
+                    if (flags & 2u) tc_commit((layer & 1) ? bar_acc1 : bar_acc0);
+                }
+                acc_on = 1;
+                if (flags & 2u) ++layer;
+                __syncwarp();
+                if (++slot == kWStages) {
+                    slot = 0;
+                    phase ^= 1;
                 }
             }
         }
@@ -311,7 +350,7 @@ sdf_mlp_value_kernel(const float* __restrict__ pos,   // (n, 27) position encodi
             const bool live = p < n;
             {
                 const float* src = fe + p * 100;
-                for (int c = half * 13; c < half * 13 + 13; ++c) {
+                for (int c = half * (kFChunks / 2); c < (half + 1) * (kFChunks / 2); ++c) {
                     float v[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) v[e] = (live && 4 * c + e < 100) ? __ldg(src + 4 * c + e) : 0.0f;
@@ -324,7 +363,7 @@ sdf_mlp_value_kernel(const float* __restrict__ pos,   // (n, 27) position encodi
                     *reinterpret_cast<uint4*>(smem + kOffFlo + c * kChunkBytes + row * 16) = lo;
                 }
                 const float* psrc = pos + p * 27;
-                for (int c = half * 4; c < half * 4 + 4; ++c) {
+                for (int c = half * (kPChunks / 2); c < (half + 1) * (kPChunks / 2); ++c) {
                     float v[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) v[e] = (live && 4 * c + e < 27) ? __ldg(psrc + 4 * c + e) : 0.0f;

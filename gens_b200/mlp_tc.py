@@ -1,8 +1,8 @@
 """Tensor-core (tcgen05, 3xTF32) value pass of the SDF MLP -- host side of csrc/sdf_mlp_tc.cu.
 
 The network of reference models/modules/sdf_network.py:98-123 is re-expressed as a stream of "k-steps":
-one k-step = 8 input channels of one layer, i.e. an (N_l x 8) weight block that the kernel multiplies
-with a (128 x 8) slice of one of three resident A operands,
+one k-step = 16 input channels of one layer, i.e. an (N_l x 16) weight block that the kernel multiplies
+with a (128 x 16) slice of one of three resident A operands (two tcgen05 K = 8 instructions per term),
 
     F  the 100-channel volume-feature encoding (shared memory, same for every layer >= 1),
     P  the 27-channel position encoding        (shared memory; layer 0 and the skip layer),
@@ -12,14 +12,14 @@ and accumulates into that layer's fp32 accumulator.  Per layer the F and P k-ste
 depend on the previous layer, so they overlap its epilogue), the H k-steps last.
 
 Packed format (what gens_sdf_mlp_value_tc expects):
-  wstream  float32: per k-step [hi block | lo block]; a block is the (N_l x 8) weights as [2][N_l][4]
-           (two 16-byte K chunks, rows contiguous inside a chunk: the canonical K-major no-swizzle UMMA
+  wstream  float32: per k-step [hi block | lo block]; a block is the (N_l x 16) weights as [4][N_l][4]
+           (four 16-byte K chunks, rows contiguous inside a chunk: the canonical K-major no-swizzle UMMA
            layout with LBO = 16 N_l bytes, SBO = 128 bytes); hi = weights rounded to TF32, lo = w - hi.
-  ksteps   uint32 (n,4): byte offset, byte count (64 N_l), A source | index << 8,
+  ksteps   uint32 (n,4): byte offset, byte count (128 N_l), A source | index << 8,
            flags (1 first of layer, 2 last of layer, 4 first H k-step) | N_l << 16.
   bias     float32 (n_layers, 128), zero padded.
 Fan-outs are padded to multiples of 16 with zero rows (101 -> 112, the single SDF row -> 16), fan-ins to
-multiples of 8 with zero columns; the 1/sqrt(2) of the skip connection is folded into that layer's weights.
+multiples of 16 with zero columns; the 1/sqrt(2) of the skip connection is folded into that layer's weights.
 """
 from __future__ import annotations
 
@@ -31,7 +31,7 @@ import torch
 from . import _lib
 
 A_F, A_P, A_H = 0, 1, 2
-F_K, P_K = 104, 32  # padded widths of the resident encodings (csrc/sdf_mlp_tc.cu kFChunks / kPChunks)
+F_K, P_K = 112, 32  # padded widths of the resident encodings (csrc/sdf_mlp_tc.cu kFChunks / kPChunks)
 
 
 def _split_tf32(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -40,13 +40,13 @@ def _split_tf32(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 def _blocks(w: torch.Tensor, n_pad: int) -> torch.Tensor:
-    """(fo, k) weights -> (k_pad/8, 2 [hi, lo], 2 chunks, n_pad rows, 4) blocks."""
+    """(fo, k) weights -> (k_pad/16, 2 [hi, lo], 4 chunks, n_pad rows, 4) blocks."""
     fo, k = w.shape
-    k_pad = (k + 7) // 8 * 8
+    k_pad = (k + 15) // 16 * 16
     full = w.new_zeros((n_pad, k_pad))
     full[:fo, :k] = w
     hi, lo = _split_tf32(full)
-    tiles = [t.reshape(n_pad, k_pad // 8, 2, 4).permute(1, 2, 0, 3) for t in (hi, lo)]
+    tiles = [t.reshape(n_pad, k_pad // 16, 4, 4).permute(1, 2, 0, 3) for t in (hi, lo)]
     return torch.stack(tiles, dim=1).contiguous()
 
 
@@ -86,7 +86,7 @@ class PackedSDF:
             for si, (kind, w) in enumerate(segs):
                 blk = _blocks(w.float(), n_pad)
                 nb = blk.shape[0]
-                nbytes = n_pad * 64
+                nbytes = n_pad * 128
                 for j in range(nb):
                     flags = n_pad << 16
                     if first:
@@ -114,6 +114,8 @@ def sdf_values(packed: PackedSDF, pos: torch.Tensor, fe: torch.Tensor) -> torch.
     _lib.require_cuda(pos, fe)
     n = pos.shape[0]
     out = torch.empty((n, 1), device=pos.device, dtype=torch.float32)
+    if n == 0:
+        return out
     _lib.check(_lib.lib().gens_sdf_mlp_value_tc(
         _lib.ptr(pos), _lib.ptr(fe), n, _lib.ptr(packed.wstream), _lib.ptr(packed.ksteps), packed.n_ksteps,
         _lib.ptr(packed.bias), packed.n_layers, packed.scale, packed.n_sm, _lib.ptr(out),
@@ -134,13 +136,13 @@ def emulate(packed: PackedSDF, pos: torch.Tensor, fe: torch.Tensor) -> torch.Ten
     layer = 0
     for off, nbytes, a, flags in packed.ksteps.cpu().tolist():
         n_pad = (flags >> 16) & 0x1ff
-        assert nbytes == n_pad * 64 and off % 16 == 0
-        blk = stream[off // 4: off // 4 + nbytes // 4].reshape(2, 2, n_pad, 4)
-        w = (blk[0] + blk[1]).permute(1, 0, 2).reshape(n_pad, 8)          # hi + lo, (N, 8)
+        assert nbytes == n_pad * 128 and off % 16 == 0
+        blk = stream[off // 4: off // 4 + nbytes // 4].reshape(2, 4, n_pad, 4)
+        w = (blk[0] + blk[1]).permute(1, 0, 2).reshape(n_pad, 16)         # hi + lo, (N, 16)
         kind, j = a & 0xff, (a >> 8) & 0xff
         if flags & 1:
             acc = torch.zeros((n, n_pad), dtype=torch.float64)
-        acc = acc + srcs[kind][:, 8 * j: 8 * j + 8] @ w.t()
+        acc = acc + srcs[kind][:, 16 * j: 16 * j + 16] @ w.t()
         if flags & 2:
             y = acc + packed.bias[layer, :n_pad].double().cpu()
             if layer + 1 < packed.n_layers:

@@ -26,6 +26,10 @@ from .projector import packed_volume
 
 _U = (ctypes.c_float * 3)(1.0, 1.0, 1.0)
 
+# value-only SDF evaluations run the whole MLP as one tcgen05 kernel (csrc/sdf_mlp_tc.cu, 3xTF32 with fp32
+# accumulation, ~1e-5 of the fp32 path); False = per-layer cuBLAS SGEMMs + fused bias/softplus kernels.
+USE_TC = True
+
 
 class FoldedSDF:
     """Weight-normalised layers folded and split once per call: x-part / feature-part per layer."""
@@ -59,6 +63,14 @@ class FoldedSDF:
         self.off = [0]
         for l in range(1, self.n_layers):
             self.off.append(self.off[-1] + self.fo[l])  # off[l-1] = column of layer l in the feature part
+        self._packed = None
+
+    def packed(self):
+        """The same weights in the streaming format of the tensor-core kernel (built on first use)."""
+        if self._packed is None:
+            from .mlp_tc import PackedSDF
+            self._packed = PackedSDF(self)
+        return self._packed
 
 
 def _c(code, what):
@@ -178,6 +190,9 @@ def value_only(net, pts: torch.Tensor, volumes, folded: Optional[FoldedSDF] = No
     pos, fe = new(n, fw.pe_in), new(n, fw.pe_feat)
     _c(L.gens_sdf_encode(P(pts), P(feats), None, n, fw.scale, _U, fw.multires, fw.feat_multires, nf, P(pos), P(fe), st),
        "gens_sdf_encode")
+    if USE_TC:
+        from . import mlp_tc
+        return mlp_tc.sdf_values(fw.packed(), pos, fe)
     featpart = fe @ fw.wf_t
     ldfp = featpart.shape[1]
     last = fw.n_layers - 1

@@ -36,6 +36,9 @@ for n in [128, 1000, 128 * 148 * 3 + 77, 1 << 21]:
     torch.cuda.synchronize()
     err = (out - ref).abs().max().item()
     print(f'n={n}: max abs err {err:.3e}  (ref range {ref.min().item():.3f}..{ref.max().item():.3f}) nan={bool(out.isnan().any())}', flush=True)
+    if n == 1000:
+        ex = mlp_tc.emulate(packed, pos, fe).to(dev)   # float64 replay of the same network
+        print(f'   vs float64: tcgen05 {float((out - ex).abs().max()):.3e}   fp32 cuBLAS path {float((ref - ex).abs().max()):.3e}', flush=True)
     if n >= 1 << 20:
         for fn, name in ((lambda: mlp_tc.sdf_values(packed, pos, fe), 'tcgen05 MLP only'),
                          (lambda: sdf_analytic.value_only(net, pts, vols, fw), 'fp32 value_only (incl. lookup+encode)')):
