@@ -88,6 +88,8 @@ _SIGNATURES = {
     "gens_sdf_act_bwd": ([_vp, _i, _f, _vp, _vp, _ll, _i, _vp, _i, _vp], _i),
     "gens_sdf_decode": ([_vp, _vp, _vp, _vp, _vp, _ll, _f, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "gens_sdf_mlp_value_tc": ([_vp, _vp, _ll, _vp, _vp, _i, _vp, _i, _f, _i, _vp, _vp], _i),
+    "gens_sdf_mlp_jvp_tc": ([_vp, _vp, _ll, _vp, _vp, _i, _vp, _i, _f, _i, _vp, _vp, _vp, _vp], _i),
+    "gens_sdf_mlp_rev_tc": ([_vp, _vp, _ll, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp], _i),
     "gens_pack_nhwc4": ([_vp, _vp, _i, _i, _i, _i, _vp], _i),
     "gens_unpack_nhwc4": ([_vp, _vp, _i, _i, _i, _i, _vp], _i),
     "gens_lookup_feature_fwd": ([_vp, _ll, _i, _vp, _vp, _vp, _vp, _IP, _vp, _i, _vp, _vp, _vp, _vp], _i),

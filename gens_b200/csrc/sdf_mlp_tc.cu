@@ -1,38 +1,43 @@
-// K4: the SDF MLP as ONE persistent tcgen05 kernel (value pass), error-compensated 3xTF32.
+// K4: the SDF MLP on tcgen05 tensor cores -- persistent kernels, error-compensated 3xTF32.
 //
-// Replaces, for value-only evaluations (the hierarchical up-sampling loop, SDFNetwork.sdf, the
-// mesh lattice of extract_geometry; reference models/modules/sdf_network.py:98-126), the chain
-//   7 x (cuBLAS SGEMM over all points + bias/softplus kernel)
-// whose (n,128) activations travel through HBM between every two launches, with a kernel that
-// keeps a 128-point tile on chip from the encodings to the SDF value:
+// Three kernels replace, for inference (torch.no_grad), the per-layer cuBLAS SGEMM + glue-kernel chains of
+// gens_b200/sdf_analytic.py whose (n,128) activations travel through HBM between every two launches
+// (reference models/modules/sdf_network.py:98-153: forward, .sdf and .gradient):
 //
-//   * activations h_l live in TENSOR MEMORY as the A operand of the next layer (lane = point,
-//     column = channel), split into a TF32-exact high part and the fp32 remainder;
-//   * the encodings every layer re-reads (position encoding P, 27 ch; volume-feature encoding F,
-//     100 ch) sit in shared memory in the canonical K-major no-swizzle UMMA layout
-//     ([K/4][128 rows][16 B]), also split hi/lo;
-//   * weights stream through a ring of 16 KB shared-memory slots with cp.async.bulk (one k-step =
-//     N x 16 weights, hi and lo, pre-packed on the host in exactly the slot image);
-//   * per 8 channels three tcgen05.mma.kind::tf32 accumulate  Ah.Bh + Al.Bh + Ah.Bl  into a fp32
-//     accumulator in TMEM: the products dropped (Al.Bl) and the truncation of the low parts are
-//     below 2^-21 relative, so the result matches an fp32 SGEMM to ~1e-6 -- plain TF32 (2^-11)
-//     would not survive softplus(beta = 100) at the stated 1e-4 tolerance;
-//   * 8 epilogue warps pull the accumulator with tcgen05.ld, add the bias, apply softplus, split and
-//     write h_{l+1} back with tcgen05.st; the accumulator is double-buffered so the F/P k-steps of
-//     layer l+1 (which do not depend on h_l) run on the tensor core while layer l's epilogue runs.
+//   sdf_mlp_fwd_kernel<false>   value pass: encodings -> SDF, 128 points per tile
+//   sdf_mlp_fwd_kernel<true>    value + directional-derivative pass (rows 2i / 2i+1 of a tile = primal /
+//                               tangent of point i, 64 points per tile); also stores sp'(a) and sp''(a) da
+//   sdf_mlp_rev_kernel          reverse sweep over the same 64-point tiles: cotangents of the encodings
+//                               (and their tangents) for grad sdf and the second-order "smooth" term
 //
-// TMEM columns: [0,128) h hi | [128,256) h lo | [256,384) acc 0 | [384,512) acc 1.
-// Warp roles: 0-7 epilogue / input staging (thread t <-> point t & 127, column half t >> 7),
-//             8 weight producer (+ TMEM allocation), 9 MMA issuer (one elected lane).
+// Common design:
+//   * the running activations (A operand of the next GEMM) live in TENSOR MEMORY (lane = row, column =
+//     channel), split into a TF32-exact high part and the fp32 remainder;
+//   * the encodings every forward layer re-reads (position encoding P, 27 ch; volume-feature encoding F,
+//     100 ch) sit in shared memory in the canonical K-major no-swizzle UMMA layout ([K/4][128 rows][16 B]),
+//     also split hi/lo;
+//   * weights stream through a ring of 16 KB shared-memory slots with cp.async.bulk (one k-step = N x 16
+//     weights, hi and lo, pre-packed on the host in exactly the slot image, gens_b200/mlp_tc.py);
+//   * per 8 channels three tcgen05.mma.kind::tf32 accumulate  Ah.Bh + Al.Bh + Ah.Bl  into fp32 accumulators
+//     in TMEM: what is dropped (Al.Bl, the truncation of the low parts) is below 2^-21 relative, i.e. the
+//     result matches an fp32 SGEMM to ~1e-5 after seven layers -- plain TF32 (2^-11) would not survive
+//     softplus(beta = 100) at the stated 1e-4 tolerance;
+//   * 16 epilogue warps pull the accumulators with tcgen05.ld, apply bias / softplus (and its derivatives),
+//     split and write the next A operand back with tcgen05.st; in the forward kernels the accumulator is
+//     double-buffered so the F/P k-steps of layer l+1 (independent of h_l) overlap layer l's epilogue.
+//
+// TMEM columns: [0,128) A hi | [128,256) A lo | [256,384) accumulator 0 | [384,512) accumulator 1.
+// Warp roles: 0-15 epilogue / input staging (thread t <-> row t & 127, column quarter t >> 7),
+//             16 weight producer (+ TMEM allocation), 17 MMA issuer (whole warp walks, one elected lane issues).
 #include "common.cuh"
 
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kEpiThreads = 256;
-constexpr int kProducerWarp = 8;
-constexpr int kMmaWarp = 9;
-constexpr int kThreads = 320;
+constexpr int kEpiThreads = 512;
+constexpr int kProducerWarp = 16;
+constexpr int kMmaWarp = 17;
+constexpr int kThreads = 576;
 constexpr int kWSlotBytes = 16384;        // one k-step = 16 input channels: N x 16 weights, hi and lo
 constexpr int kWStages = 4;
 constexpr int kFChunks = 28;              // feature encoding: K = 112 (100 + 12 zero columns)
@@ -40,6 +45,7 @@ constexpr int kPChunks = 8;               // position encoding: K = 32 (27 + 5 z
 constexpr int kChunkBytes = kTileM * 16;  // one 16-byte K chunk of all 128 rows
 constexpr int kMaxLayers = 8;
 constexpr int kMaxKSteps = 128;
+constexpr int kNF = 100, kNP = 27;        // real widths of the encodings
 
 // shared-memory map (bytes)
 constexpr int kOffFhi = 0;
@@ -50,17 +56,21 @@ constexpr int kOffW = kOffPlo + kPChunks * kChunkBytes;
 constexpr int kOffBias = kOffW + kWStages * kWSlotBytes;
 constexpr int kOffSteps = kOffBias + kMaxLayers * 128 * 4;  // per k-step issue records (uint4)
 constexpr int kOffBar = kOffSteps + kMaxKSteps * 16;
-constexpr int kNumBars = 2 * kWStages + 4;  // full[], empty[], acc_full[2], h_ready, in_ready
+constexpr int kNumBars = 2 * kWStages + 4;  // full[], empty[], acc[2], a_ready, in_ready
 constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
+// the reverse kernel keeps no encodings in shared memory: the ring starts at 0
+constexpr int kRevOffW = 0;
 
-constexpr uint32_t kColHhi = 0, kColHlo = 128, kColAcc = 256;
+constexpr uint32_t kColAhi = 0, kColAlo = 128, kColAcc0 = 256, kColAcc1 = 384;
 
 struct KStep {
-    uint32_t w_off;    // byte offset of this k-step's [hi | lo] weight block in the stream
+    uint32_t w_off;    // byte offset of this k-step's [hi | lo] weight block in the stream (blocks are contiguous)
     uint32_t w_bytes;  // N * 128
-    uint32_t a;        // bits 0-7: A source (0 = F smem, 1 = P smem, 2 = h TMEM); bits 8-15: k-step inside it (K / 16)
-    uint32_t flags;    // bit 0 first of layer, bit 1 last of layer, bit 2 first k-step that needs h; bits 16-24 N
+    uint32_t a;        // bits 0-7: A source (0 = F smem, 1 = P smem, 2 = TMEM); bits 8-15: k-step inside it (K / 16);
+                       // bits 16-27: accumulator column in TMEM
+    uint32_t flags;    // bit 0 overwrite the accumulator, bit 1 commit after this k-step (bit 4: to barrier acc1),
+                       // bit 2 wait for the epilogue's A operand first; bits 16-24 N
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
@@ -142,33 +152,6 @@ __device__ __forceinline__ uint32_t instr_desc(uint32_t n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
-#define TC_REGS32(v)                                                                                             \
-    v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15], v[16], \
-        v[17], v[18], v[19], v[20], v[21], v[22], v[23], v[24], v[25], v[26], v[27], v[28], v[29], v[30], v[31]
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
-        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
-        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
-        : "memory");
-}
 __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
     uint32_t v;
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
@@ -184,69 +167,116 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
     lo = __float_as_uint(x - __uint_as_float(h));
 }
 
-// torch.nn.Softplus(beta = 100, threshold = 20) (reference sdf_network.py:95): a if 100 a > 20 else
-// log1p(exp(100 a)) / 100, in the overflow-free form max(t,0) + log(1 + exp(-|t|)).  ex2/lg2.approx are
-// exact to ~2^-22, which after the division by beta is ~1e-9 absolute on activations of order 0.1 - 1.
-__device__ __forceinline__ float softplus100(float a) {
-    const float t = a * 100.0f;
-    float e, l;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(t) * 1.4426950408889634f));
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
-    const float sp = (fmaxf(t, 0.0f) + l * 0.6931471805599453f) * 0.01f;
-    return t > 20.0f ? a : sp;
+
+#define TC_LIST16(v) v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
 }
 
-// ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1)
-sdf_mlp_value_kernel(const float* __restrict__ pos,   // (n, 27) position encoding
-                     const float* __restrict__ fe,    // (n, 100) volume-feature encoding
-                     long long n, const float* __restrict__ wstream, const KStep* __restrict__ ksteps, int n_ksteps,
-                     const float* __restrict__ bias,  // (n_layers, 128)
-                     int n_layers, float scale, float* __restrict__ sdf_out) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t s_base = smem_u32(smem);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bar0 = s_base + kOffBar;
-    auto bar_full = [&](int s) { return bar0 + 8u * s; };
-    auto bar_empty = [&](int s) { return bar0 + 8u * (kWStages + s); };
-    const uint32_t bar_acc0 = bar0 + 8u * (2 * kWStages), bar_acc1 = bar_acc0 + 8, bar_h = bar_acc0 + 16,
-                   bar_in = bar_acc0 + 24;
-    float* s_bias = reinterpret_cast<float*>(smem + kOffBias);
-    volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
+// log1p(x) on [0,1], degree-8 minimax fit (abs. error 2e-7 in fp32) -- the softplus tail, FMA pipe only
+__device__ __forceinline__ float log1p_unit(float x) {
+    float p = -0.006151470821350813f;
+    p = fmaf(p, x, 0.03484971076250076f);
+    p = fmaf(p, x, -0.0932520404458046f);
+    p = fmaf(p, x, 0.16582275927066803f);
+    p = fmaf(p, x, -0.23982615768909454f);
+    p = fmaf(p, x, 0.33154863119125366f);
+    p = fmaf(p, x, -0.49983856081962585f);
+    p = fmaf(p, x, 0.9999942779541016f);
+    return fmaf(p, x, 3.3869653748297424e-08f);
+}
+__device__ __forceinline__ float exp_neg_abs(float t) {  // exp(-|t|)
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(t) * 1.4426950408889634f));
+    return e;
+}
+// torch.nn.Softplus(beta = 100, threshold = 20) (reference sdf_network.py:95): a if 100 a > 20 else
+// log1p(exp(100 a)) / 100, in the overflow-free form max(t,0) + log1p(exp(-|t|)).  Absolute error ~2e-9.
+__device__ __forceinline__ float softplus100(float a) {
+    const float t = a * 100.0f;
+    const float sp = (fmaxf(t, 0.0f) + log1p_unit(exp_neg_abs(t))) * 0.01f;
+    return t > 20.0f ? a : sp;
+}
+// sp'(a) = sigmoid(100 a) and sp''(a) = 100 sp' (1 - sp'), torch's linear region (100 a > 20) has (1, 0)
+__device__ __forceinline__ void softplus100_d12(float a, float& d1, float& d2) {
+    const float t = a * 100.0f;
+    const float e = exp_neg_abs(t);
+    const float r = __frcp_rn(1.0f + e);
+    const float er = e * r;
+    d1 = t > 0.0f ? r : er;
+    d2 = 100.0f * er * r;
+    if (t > 20.0f) {
+        d1 = 1.0f;
+        d2 = 0.0f;
+    }
+}
 
-    // ---- one-time setup ------------------------------------------------------------------------------
-    for (int i = threadIdx.x; i < n_layers * 128; i += kThreads) s_bias[i] = bias[i];
-    // issue records: x = A hi (descriptor low word, or TMEM column), y = A lo, z = flags | N << 16, w = bytes
+struct Ctx {
+    uint8_t* smem;
+    uint32_t s_base, bar0, tmem;
+    __device__ __forceinline__ uint32_t bar_full(int s) const { return bar0 + 8u * s; }
+    __device__ __forceinline__ uint32_t bar_empty(int s) const { return bar0 + 8u * (kWStages + s); }
+    __device__ __forceinline__ uint32_t bar_acc(int i) const { return bar0 + 8u * (2 * kWStages + i); }
+    __device__ __forceinline__ uint32_t bar_a() const { return bar0 + 8u * (2 * kWStages + 2); }
+    __device__ __forceinline__ uint32_t bar_in() const { return bar0 + 8u * (2 * kWStages + 3); }
+};
+
+// One-time setup shared by the kernels: bias / constant rows and the k-step issue records to shared memory,
+// barriers, TMEM allocation.  Issue record: x = A hi (descriptor low word, or TMEM column), y = A lo,
+// z = flags (bit 3 added: A in TMEM) | N << 16, w = bytes | accumulator column << 16.
+__device__ __forceinline__ Ctx setup(uint8_t* smem, const KStep* __restrict__ ksteps, int n_ksteps,
+                                     const float* __restrict__ bias, int n_bias_rows) {
+    Ctx c;
+    c.smem = smem;
+    c.s_base = smem_u32(smem);
+    c.bar0 = c.s_base + kOffBar;
+    float* s_bias = reinterpret_cast<float*>(smem + kOffBias);
+    for (int i = threadIdx.x; i < n_bias_rows * 128; i += kThreads) s_bias[i] = bias[i];
     uint4* s_steps = reinterpret_cast<uint4*>(smem + kOffSteps);
     for (int i = threadIdx.x; i < n_ksteps; i += kThreads) {
         const KStep st = ksteps[i];
-        const uint32_t kind = st.a & 0xff, kidx = (st.a >> 8) & 0xff;
+        const uint32_t kind = st.a & 0xff, kidx = (st.a >> 8) & 0xff, acc_col = (st.a >> 16) & 0xfff;
         uint4 r;
         if (kind == 2) {
-            r.x = kColHhi + kidx * 16;
-            r.y = kColHlo + kidx * 16;
+            r.x = kColAhi + kidx * 16;
+            r.y = kColAlo + kidx * 16;
         } else {
             const uint32_t off_hi = kind == 0 ? kOffFhi : kOffPhi, off_lo = kind == 0 ? kOffFlo : kOffPlo;
-            r.x = (uint32_t)smem_desc(s_base + off_hi + kidx * 4 * kChunkBytes, kChunkBytes, 128);
-            r.y = (uint32_t)smem_desc(s_base + off_lo + kidx * 4 * kChunkBytes, kChunkBytes, 128);
+            r.x = (uint32_t)smem_desc(c.s_base + off_hi + kidx * 4 * kChunkBytes, kChunkBytes, 128);
+            r.y = (uint32_t)smem_desc(c.s_base + off_lo + kidx * 4 * kChunkBytes, kChunkBytes, 128);
         }
         r.z = st.flags | (kind == 2 ? 8u : 0u);
-        r.w = st.w_bytes;
+        r.w = st.w_bytes | (acc_col << 16);
         s_steps[i] = r;
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < kWStages; ++s) {
-            mbar_init(bar_full(s), 1);
-            mbar_init(bar_empty(s), 1);
+            mbar_init(c.bar_full(s), 1);
+            mbar_init(c.bar_empty(s), 1);
         }
-        mbar_init(bar_acc0, 1);
-        mbar_init(bar_acc1, 1);
-        mbar_init(bar_h, kEpiThreads);
-        mbar_init(bar_in, kEpiThreads);
+        mbar_init(c.bar_acc(0), 1);
+        mbar_init(c.bar_acc(1), 1);
+        mbar_init(c.bar_a(), kEpiThreads);
+        mbar_init(c.bar_in(), kEpiThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == kProducerWarp) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_base + kOffTmemPtr),
+    if ((threadIdx.x >> 5) == kProducerWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(c.s_base + kOffTmemPtr),
                      "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -254,177 +284,361 @@ sdf_mlp_value_kernel(const float* __restrict__ pos,   // (n, 27) position encodi
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *s_tmem;
+    c.tmem = *reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
+    return c;
+}
 
-    const long long n_tiles = (n + kTileM - 1) / kTileM;
+__device__ __forceinline__ void teardown(const Ctx& c) {
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == kProducerWarp) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "r"(512u) : "memory");
+    }
+}
 
-    if (warp == kProducerWarp) {
-        // ===== weight producer: the same k-step stream for every tile ==================================
-        if (lane == 0) {
-            uint32_t slot = 0, phase = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                uint32_t w_off = 0;  // the blocks are contiguous in the stream
-                for (int ks = 0; ks < n_ksteps; ++ks) {
-                    const uint32_t w_bytes = s_steps[ks].w;
-                    mbar_wait(bar_empty(slot), phase ^ 1);
-                    mbar_arrive_expect_tx(bar_full(slot), w_bytes);
-                    bulk_g2s(s_base + kOffW + slot * kWSlotBytes, reinterpret_cast<const uint8_t*>(wstream) + w_off,
-                             w_bytes, bar_full(slot));
-                    w_off += w_bytes;
-                    if (++slot == kWStages) {
-                        slot = 0;
-                        phase ^= 1;
-                    }
-                }
+// ===== weight producer (one lane): the same k-step stream for every tile ===================================
+__device__ __forceinline__ void produce_weights(const Ctx& c, const float* __restrict__ wstream, int n_ksteps,
+                                                long long n_tiles, uint32_t w_ring) {
+    const uint4* s_steps = reinterpret_cast<const uint4*>(c.smem + kOffSteps);
+    uint32_t slot = 0, phase = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint32_t w_off = 0;
+        for (int ks = 0; ks < n_ksteps; ++ks) {
+            const uint32_t w_bytes = s_steps[ks].w & 0xffffu;
+            mbar_wait(c.bar_empty(slot), phase ^ 1);
+            mbar_arrive_expect_tx(c.bar_full(slot), w_bytes);
+            bulk_g2s(c.s_base + w_ring + slot * kWSlotBytes, reinterpret_cast<const uint8_t*>(wstream) + w_off, w_bytes,
+                     c.bar_full(slot));
+            w_off += w_bytes;
+            if (++slot == kWStages) {
+                slot = 0;
+                phase ^= 1;
             }
         }
-    } else if (warp == kMmaWarp) {
-        // ===== MMA issuer: the whole warp walks the k-steps (uniform control flow and addresses), one elected
-        // lane issues.  Per k-step: 2 x (Ah.Bh + Al.Bh + Ah.Bl) over 8 channels each.
-        const uint32_t elected = elect_one();
-        const uint32_t desc_hi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1 (bits 32-47)
-        uint32_t slot = 0, phase = 0, in_phase = 0, h_phase = 0;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            mbar_wait(bar_in, in_phase);
+    }
+}
+
+// ===== MMA issuer: the whole warp walks the k-steps (uniform control flow and addresses), one elected lane
+// issues.  Per k-step: 2 x (Ah.Bh + Al.Bh + Ah.Bl) over 8 channels each.  WAIT_IN: a tile starts when the
+// epilogue warps have staged its encodings (forward kernels).
+template <bool WAIT_IN>
+__device__ __forceinline__ void issue_mmas(const Ctx& c, int n_ksteps, long long n_tiles, uint32_t w_ring) {
+    const uint4* s_steps = reinterpret_cast<const uint4*>(c.smem + kOffSteps);
+    const uint32_t elected = elect_one();
+    const uint32_t desc_hi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1 (bits 32-47)
+    uint32_t slot = 0, phase = 0, in_phase = 0, a_phase = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (WAIT_IN) {
+            mbar_wait(c.bar_in(), in_phase);
             in_phase ^= 1;
             tc_fence_after();
-            uint32_t layer = 0, acc_on = 0;
-            uint4 rec = s_steps[0];
-            for (int ks = 0; ks < n_ksteps; ++ks) {
-                const uint4 cur = rec;
-                if (ks + 1 < n_ksteps) rec = s_steps[ks + 1];
-                const uint32_t flags = cur.z, nn = (flags >> 16) & 0x1ff;
-                const uint32_t idesc = instr_desc(nn);
-                const uint32_t d_tmem = tmem + kColAcc + (layer & 1) * 128;
-                if (flags & 1u) acc_on = 0;
-                if (flags & 4u) {  // h of the previous layer must be in tensor memory
-                    mbar_wait(bar_h, h_phase);
-                    h_phase ^= 1;
-                }
-                mbar_wait(bar_full(slot), phase);
-                tc_fence_after();
-                // B: [hi: 4 chunks][lo: 4 chunks], chunk = N rows x 16 B
-                const uint32_t w_addr = s_base + kOffW + slot * kWSlotBytes;
-                const uint32_t b_lo32 = ((w_addr & 0x3ffff) >> 4) | (nn << 16);  // LBO = 16 N bytes
-                const uint32_t b_step = 2 * nn, b_lopart = 4 * nn;               // in 16-byte units
-                if (elected) {
+        }
+        uint32_t acc_on = 0;
+        uint4 rec = s_steps[0];
+        for (int ks = 0; ks < n_ksteps; ++ks) {
+            const uint4 cur = rec;
+            if (ks + 1 < n_ksteps) rec = s_steps[ks + 1];
+            const uint32_t flags = cur.z, nn = (flags >> 16) & 0x1ff;
+            const uint32_t idesc = instr_desc(nn);
+            const uint32_t d_tmem = c.tmem + (cur.w >> 16);
+            if (flags & 1u) acc_on = 0;
+            if (flags & 4u) {  // the epilogue's A operand must be in tensor memory
+                mbar_wait(c.bar_a(), a_phase);
+                a_phase ^= 1;
+            }
+            mbar_wait(c.bar_full(slot), phase);
+            tc_fence_after();
+            // B: [hi: 4 chunks][lo: 4 chunks], chunk = N rows x 16 B
+            const uint32_t w_addr = c.s_base + w_ring + slot * kWSlotBytes;
+            const uint32_t b_lo32 = ((w_addr & 0x3ffff) >> 4) | (nn << 16);  // LBO = 16 N bytes
+            const uint32_t b_step = 2 * nn, b_lopart = 4 * nn;               // in 16-byte units
+            if (elected) {
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const uint64_t b_hi = ((uint64_t)desc_hi << 32) | (b_lo32 + j * b_step);
-                        const uint64_t b_lo = ((uint64_t)desc_hi << 32) | (b_lo32 + b_lopart + j * b_step);
-                        if (flags & 8u) {
-                            const uint32_t a_hi = tmem + cur.x + j * 8, a_lo = tmem + cur.y + j * 8;
-                            mma_ts(d_tmem, a_hi, b_hi, idesc, acc_on);
-                            mma_ts(d_tmem, a_lo, b_hi, idesc, 1);
-                            mma_ts(d_tmem, a_hi, b_lo, idesc, 1);
-                        } else {
-                            const uint64_t a_hi = ((uint64_t)desc_hi << 32) | (cur.x + j * (2 * kChunkBytes >> 4));
-                            const uint64_t a_lo = ((uint64_t)desc_hi << 32) | (cur.y + j * (2 * kChunkBytes >> 4));
-                            mma_ss(d_tmem, a_hi, b_hi, idesc, acc_on);
-                            mma_ss(d_tmem, a_lo, b_hi, idesc, 1);
-                            mma_ss(d_tmem, a_hi, b_lo, idesc, 1);
-                        }
-                        acc_on = 1;
+                for (int j = 0; j < 2; ++j) {
+                    const uint64_t b_hi = ((uint64_t)desc_hi << 32) | (b_lo32 + j * b_step);
+                    const uint64_t b_lo = ((uint64_t)desc_hi << 32) | (b_lo32 + b_lopart + j * b_step);
+                    if (flags & 8u) {
+                        const uint32_t a_hi = c.tmem + cur.x + j * 8, a_lo = c.tmem + cur.y + j * 8;
+                        mma_ts(d_tmem, a_hi, b_hi, idesc, acc_on);
+                        mma_ts(d_tmem, a_lo, b_hi, idesc, 1);
+                        mma_ts(d_tmem, a_hi, b_lo, idesc, 1);
+                    } else {
+                        const uint64_t a_hi = ((uint64_t)desc_hi << 32) | (cur.x + j * (2 * kChunkBytes >> 4));
+                        const uint64_t a_lo = ((uint64_t)desc_hi << 32) | (cur.y + j * (2 * kChunkBytes >> 4));
+                        mma_ss(d_tmem, a_hi, b_hi, idesc, acc_on);
+                        mma_ss(d_tmem, a_lo, b_hi, idesc, 1);
+                        mma_ss(d_tmem, a_hi, b_lo, idesc, 1);
                     }
-                    tc_commit(bar_empty(slot));  // slot free once these MMAs have read it
-                    if (flags & 2u) tc_commit((layer & 1) ? bar_acc1 : bar_acc0);
+                    acc_on = 1;
                 }
-                acc_on = 1;
-                if (flags & 2u) ++layer;
-                __syncwarp();
-                if (++slot == kWStages) {
-                    slot = 0;
-                    phase ^= 1;
-                }
+                tc_commit(c.bar_empty(slot));  // slot free once these MMAs have read it
+                if (flags & 2u) tc_commit(c.bar_acc((flags >> 4) & 1));
+            }
+            acc_on = 1;
+            __syncwarp();
+            if (++slot == kWStages) {
+                slot = 0;
+                phase ^= 1;
             }
         }
+    }
+}
+
+// 16 floats of one row of an encoding -> hi / lo chunks in the canonical layout
+__device__ __forceinline__ void stage_chunk(uint8_t* smem, int off_hi, int off_lo, int chunk, int row,
+                                            const float* __restrict__ src, int width, bool live) {
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = (live && 4 * chunk + e < width) ? __ldg(src + 4 * chunk + e) : 0.0f;
+    uint4 hi, lo;
+    split_tf32(v[0], hi.x, lo.x);
+    split_tf32(v[1], hi.y, lo.y);
+    split_tf32(v[2], hi.z, lo.z);
+    split_tf32(v[3], hi.w, lo.w);
+    *reinterpret_cast<uint4*>(smem + off_hi + chunk * kChunkBytes + row * 16) = hi;
+    *reinterpret_cast<uint4*>(smem + off_lo + chunk * kChunkBytes + row * 16) = lo;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Forward kernels.  JVP = false: rows are points, pos (n,27), fe (n,100) -> sdf (n).
+// JVP = true: row 2i / 2i+1 = primal / tangent of point i; pos (2n,27) and fe (2n,100) hold the primal rows
+// [0,n) and the tangent rows [n,2n) (gens_sdf_encode); additionally stores, per hidden layer l and point p,
+// s1[l][p][c] = sp'(a) and t2[l][p][c] = sp''(a) da for the reverse sweep.
+template <bool JVP>
+__global__ void __launch_bounds__(kThreads, 1)
+sdf_mlp_fwd_kernel(const float* __restrict__ pos, const float* __restrict__ fe, long long n,
+                   const float* __restrict__ wstream, const KStep* __restrict__ ksteps, int n_ksteps,
+                   const float* __restrict__ bias, int n_layers, float scale, float* __restrict__ sdf_out,
+                   float* __restrict__ s1_out, float* __restrict__ t2_out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const Ctx c = setup(smem, ksteps, n_ksteps, bias, n_layers);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kPts = JVP ? kTileM / 2 : kTileM;  // points per tile
+    const long long n_tiles = (n + kPts - 1) / kPts;
+
+    if (warp == kProducerWarp) {
+        if (lane == 0) produce_weights(c, wstream, n_ksteps, n_tiles, kOffW);
+    } else if (warp == kMmaWarp) {
+        issue_mmas<true>(c, n_ksteps, n_tiles, kOffW);
     } else {
-        // ===== input staging + epilogue (threads 0..255) =================================================
-        const int row = threadIdx.x & 127, half = threadIdx.x >> 7;
+        // ===== input staging + epilogue (threads 0..511) ===================================================
+        const float* s_bias = reinterpret_cast<const float*>(smem + kOffBias);
+        const int row = threadIdx.x & 127, cq = threadIdx.x >> 7;  // column quarter: 32 columns
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const bool tangent = JVP && (row & 1);
         uint32_t acc_phase[2] = {0, 0};
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            // -- encodings of this tile -> shared memory, split hi/lo (the previous tile's MMAs are done:
-            //    this thread has already waited for its last accumulator)
-            const long long p = tile * kTileM + row;
+            // -- encodings of this tile -> shared memory, split hi/lo (the previous tile's MMAs are done: this
+            //    thread has already waited for its last accumulator)
+            const long long p = JVP ? tile * kPts + (row >> 1) : tile * kPts + row;
             const bool live = p < n;
-            {
-                const float* src = fe + p * 100;
-                for (int c = half * (kFChunks / 2); c < (half + 1) * (kFChunks / 2); ++c) {
-                    float v[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) v[e] = (live && 4 * c + e < 100) ? __ldg(src + 4 * c + e) : 0.0f;
-                    uint4 hi, lo;
-                    split_tf32(v[0], hi.x, lo.x);
-                    split_tf32(v[1], hi.y, lo.y);
-                    split_tf32(v[2], hi.z, lo.z);
-                    split_tf32(v[3], hi.w, lo.w);
-                    *reinterpret_cast<uint4*>(smem + kOffFhi + c * kChunkBytes + row * 16) = hi;
-                    *reinterpret_cast<uint4*>(smem + kOffFlo + c * kChunkBytes + row * 16) = lo;
-                }
-                const float* psrc = pos + p * 27;
-                for (int c = half * (kPChunks / 2); c < (half + 1) * (kPChunks / 2); ++c) {
-                    float v[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) v[e] = (live && 4 * c + e < 27) ? __ldg(psrc + 4 * c + e) : 0.0f;
-                    uint4 hi, lo;
-                    split_tf32(v[0], hi.x, lo.x);
-                    split_tf32(v[1], hi.y, lo.y);
-                    split_tf32(v[2], hi.z, lo.z);
-                    split_tf32(v[3], hi.w, lo.w);
-                    *reinterpret_cast<uint4*>(smem + kOffPhi + c * kChunkBytes + row * 16) = hi;
-                    *reinterpret_cast<uint4*>(smem + kOffPlo + c * kChunkBytes + row * 16) = lo;
-                }
-            }
+            const long long in_row = tangent ? n + p : p;
+            for (int ch = cq * (kFChunks / 4); ch < (cq + 1) * (kFChunks / 4); ++ch)
+                stage_chunk(smem, kOffFhi, kOffFlo, ch, row, fe + in_row * kNF, kNF, live);
+            for (int ch = cq * (kPChunks / 4); ch < (cq + 1) * (kPChunks / 4); ++ch)
+                stage_chunk(smem, kOffPhi, kOffPlo, ch, row, pos + in_row * kNP, kNP, live);
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
             tc_fence_before();    // orders this thread's earlier tcgen05.ld of the accumulators
-            mbar_arrive(bar_in);
+            mbar_arrive(c.bar_in());
 
             for (int layer = 0; layer < n_layers; ++layer) {
                 const int st = layer & 1;
-                mbar_wait(st ? bar_acc1 : bar_acc0, acc_phase[st]);
+                mbar_wait(c.bar_acc(st), acc_phase[st]);
                 acc_phase[st] ^= 1;
                 tc_fence_after();
-                const uint32_t acc = tmem + lane_base + kColAcc + st * 128;
+                const uint32_t acc = c.tmem + lane_base + (st ? kColAcc1 : kColAcc0);
                 if (layer + 1 < n_layers) {
                     const float* b = s_bias + layer * 128;
 #pragma unroll 1
                     for (int blk = 0; blk < 2; ++blk) {
-                        const int col0 = half * 64 + blk * 32;
-                        uint32_t v[32], hi[32], lo[32];
-                        tmem_ld32(acc + col0, v);
+                        const int col0 = cq * 32 + blk * 16;
+                        uint32_t v[16], hi[16], lo[16];
+                        tmem_ld16(acc + col0, v);
                         tmem_wait_ld();
+                        if (!JVP) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float h = softplus100(__uint_as_float(v[j]) + b[col0 + j]);
-                            split_tf32(h, hi[j], lo[j]);
+                            for (int j = 0; j < 16; ++j)
+                                split_tf32(softplus100(__uint_as_float(v[j]) + b[col0 + j]), hi[j], lo[j]);
+                        } else {
+                            float d1[16], d2[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float mine = __uint_as_float(v[j]);
+                                const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+                                const float a = (tangent ? other : mine) + b[col0 + j];  // pre-activation of the point
+                                float out;
+                                if (tangent) {
+                                    softplus100_d12(a, d1[j], d2[j]);
+                                    out = d1[j] * mine;   // dh = sp'(a) da
+                                    d2[j] *= mine;        // sp''(a) da
+                                } else {
+                                    out = softplus100(a);
+                                }
+                                split_tf32(out, hi[j], lo[j]);
+                            }
+                            if (tangent && live) {
+                                float4* o1 = reinterpret_cast<float4*>(s1_out + ((long long)layer * n + p) * 128 + col0);
+                                float4* o2 = reinterpret_cast<float4*>(t2_out + ((long long)layer * n + p) * 128 + col0);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    __stcs(o1 + q, make_float4(d1[4 * q], d1[4 * q + 1], d1[4 * q + 2], d1[4 * q + 3]));
+                                    __stcs(o2 + q, make_float4(d2[4 * q], d2[4 * q + 1], d2[4 * q + 2], d2[4 * q + 3]));
+                                }
+                            }
                         }
-                        tmem_st32(tmem + lane_base + kColHhi + col0, hi);
-                        tmem_st32(tmem + lane_base + kColHlo + col0, lo);
+                        tmem_st16(c.tmem + lane_base + kColAhi + col0, hi);
+                        tmem_st16(c.tmem + lane_base + kColAlo + col0, lo);
                     }
                     tmem_wait_st();
                     tc_fence_before();
-                    mbar_arrive(bar_h);
+                    mbar_arrive(c.bar_a());
                 } else {
-                    if (half == 0) {
+                    if (cq == 0) {
                         const uint32_t v = tmem_ld1(acc);
                         tmem_wait_ld();
-                        if (live) sdf_out[p] = __fdiv_rn(__uint_as_float(v) + s_bias[layer * 128], scale);
+                        if (live && !tangent) sdf_out[p] = __fdiv_rn(__uint_as_float(v) + s_bias[layer * 128], scale);
                     }
                 }
             }
         }
     }
-
-    // ---- teardown --------------------------------------------------------------------------------------
-    tc_fence_before();
-    __syncthreads();
-    if (warp == kProducerWarp) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
-    }
+    teardown(c);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Reverse sweep (forward-over-reverse along u): for hidden layers l = L-1 .. 0
+//     ga = sp' g_h ,  dga = sp''(a) da g_h + sp' dg_h            (epilogue, rows 2i / 2i+1 of a 64-point tile)
+//     [g_h ; dg_h]_{l-1} = [ga ; dga] Wx_l        -> accumulator 0 (overwritten per layer)
+//     [g_fe ; dg_fe]    += [ga ; dga] Wf_l        -> accumulator 1 (running sum over layers, l >= 1)
+// with g_h of the last hidden layer = w_out / scale (consts row 0) and the output layer's own feature part
+// (consts row 1) added to the primal rows of g_fe at the end.  The skip layer returns its position part in
+// columns [skip_col, skip_col + 27) of accumulator 0; together with layer 0's result it forms g_pos.
+// Outputs (sdf_analytic's layout, primal rows [0,n), tangent rows [n,2n)): g_pos (2n,27), g_fe (2n,100).
+__global__ void __launch_bounds__(kThreads, 1)
+sdf_mlp_rev_kernel(const float* __restrict__ s1, const float* __restrict__ t2, long long n,
+                   const float* __restrict__ wstream, const KStep* __restrict__ ksteps, int n_ksteps,
+                   const float* __restrict__ consts, int n_hidden, int skip_layer, int skip_col,
+                   float* __restrict__ g_pos, float* __restrict__ g_fe) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const Ctx c = setup(smem, ksteps, n_ksteps, consts, 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kPts = kTileM / 2;
+    const long long n_tiles = (n + kPts - 1) / kPts;
+
+    if (warp == kProducerWarp) {
+        if (lane == 0) produce_weights(c, wstream, n_ksteps, n_tiles, kRevOffW);
+    } else if (warp == kMmaWarp) {
+        issue_mmas<false>(c, n_ksteps, n_tiles, kRevOffW);
+    } else {
+        const float* s_const = reinterpret_cast<const float*>(smem + kOffBias);
+        const int row = threadIdx.x & 127, cq = threadIdx.x >> 7;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const bool tangent = row & 1;
+        uint32_t acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const long long p = tile * kPts + (row >> 1);
+            const bool live = p < n;
+            const long long out_row = tangent ? n + p : p;
+            float pos_part[16];  // the skip layer's position cotangents (threads owning those columns)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pos_part[j] = 0.0f;
+            for (int layer = n_hidden - 1; layer >= 0; --layer) {
+                const bool top = layer == n_hidden - 1;
+                if (!top) {
+                    mbar_wait(c.bar_acc(0), acc_phase);
+                    acc_phase ^= 1;
+                    tc_fence_after();
+                }
+#pragma unroll 1
+                for (int blk = 0; blk < 2; ++blk) {
+                    const int col0 = cq * 32 + blk * 16;
+                    uint32_t v[16], hi[16], lo[16];
+                    if (top) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(tangent ? 0.0f : s_const[col0 + j]);
+                    } else {
+                        tmem_ld16(c.tmem + lane_base + kColAcc0 + col0, v);
+                    }
+                    float d1[16], d2[16];
+                    {
+                        const float4* i1 = reinterpret_cast<const float4*>(s1 + ((long long)layer * n + p) * 128 + col0);
+                        const float4* i2 = reinterpret_cast<const float4*>(t2 + ((long long)layer * n + p) * 128 + col0);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 a = live ? __ldcs(i1 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            d1[4 * q] = a.x; d1[4 * q + 1] = a.y; d1[4 * q + 2] = a.z; d1[4 * q + 3] = a.w;
+                            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (live && tangent) b = __ldcs(i2 + q);
+                            d2[4 * q] = b.x; d2[4 * q + 1] = b.y; d2[4 * q + 2] = b.z; d2[4 * q + 3] = b.w;
+                        }
+                    }
+                    if (!top) tmem_wait_ld();
+                    // the skip layer's x-part covers [h | pos]: keep the pos columns, they are not activations
+                    if (layer == skip_layer - 1 && col0 + 16 > skip_col) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int cc = col0 + j - skip_col;
+                            if (cc >= 0 && cc < kNP && live) g_pos[out_row * kNP + cc] = __uint_as_float(v[j]);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float mine = __uint_as_float(v[j]);                    // g_h (primal) / dg_h (tangent)
+                        const float other = __shfl_xor_sync(0xffffffffu, mine, 1);  // the pair's other row
+                        const float out = tangent ? fmaf(d2[j], other, d1[j] * mine) : d1[j] * mine;
+                        split_tf32(out, hi[j], lo[j]);
+                    }
+                    tmem_st16(c.tmem + lane_base + kColAhi + col0, hi);
+                    tmem_st16(c.tmem + lane_base + kColAlo + col0, lo);
+                }
+                (void)pos_part;
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(c.bar_a());
+            }
+            // -- results: accumulator 0 = layer 0's position cotangents, accumulator 1 = feature cotangents
+            mbar_wait(c.bar_acc(0), acc_phase);
+            acc_phase ^= 1;
+            tc_fence_after();
+#pragma unroll 1
+            for (int blk = 0; blk < 2; ++blk) {
+                const int col0 = cq * 32 + blk * 16;
+                uint32_t v[16];
+                if (col0 < kNP) {  // warp-uniform
+                    tmem_ld16(c.tmem + lane_base + kColAcc0 + col0, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (col0 + j < kNP && live) {
+                            float* o = g_pos + out_row * kNP + col0 + j;
+                            *o = __uint_as_float(v[j]) + (skip_layer > 0 ? *o : 0.0f);
+                        }
+                }
+                if (col0 < kNF) {
+                    tmem_ld16(c.tmem + lane_base + kColAcc1 + col0, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (col0 + j < kNF && live)
+                            g_fe[out_row * kNF + col0 + j] =
+                                __uint_as_float(v[j]) + (tangent ? 0.0f : s_const[128 + col0 + j]);
+                }
+            }
+            tc_fence_before();  // accumulator reads done before the next tile's MMAs may overwrite them
+        }
+    }
+    teardown(c);
+}
+
+}  // namespace
+
+namespace {
+template <typename K>
+int set_smem(K kernel) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    return e == cudaSuccess ? 0 : (int)e;
+}
 }  // namespace
 
 // Value pass of the SDF MLP on the tensor cores.  pos (n,27) / fe (n,100): the encodings produced by
@@ -437,11 +651,50 @@ extern "C" int gens_sdf_mlp_value_tc(const float* pos, const float* fe, long lon
     if (n_ksteps <= 0 || n_ksteps > kMaxKSteps || n_layers <= 0 || n_layers > kMaxLayers || scale == 0.f)
         return GENS_E_UNSUPPORTED;
     if (n == 0) return 0;
-    cudaError_t e = cudaFuncSetAttribute(sdf_mlp_value_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return (int)e;
+    if (int rc = set_smem(sdf_mlp_fwd_kernel<false>)) return rc;
     const long long tiles = (n + kTileM - 1) / kTileM;
     const int grid = (int)(tiles < n_sm ? tiles : n_sm);
-    sdf_mlp_value_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
-        pos, fe, n, wstream, reinterpret_cast<const KStep*>(ksteps), n_ksteps, bias, n_layers, scale, sdf_out);
+    sdf_mlp_fwd_kernel<false><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
+        pos, fe, n, wstream, reinterpret_cast<const KStep*>(ksteps), n_ksteps, bias, n_layers, scale, sdf_out, nullptr,
+        nullptr);
+    return gens_launch_status();
+}
+
+// Value + tangent pass: pos (2n,27) / fe (2n,100) with the tangent rows (directional derivative of the
+// encodings along u) in [n,2n); sdf_out (n); s1_out / t2_out (n_layers-1, n, 128) = sp'(a), sp''(a) da.
+extern "C" int gens_sdf_mlp_jvp_tc(const float* pos, const float* fe, long long n, const float* wstream,
+                                   const void* ksteps, int n_ksteps, const float* bias, int n_layers, float scale,
+                                   int n_sm, float* sdf_out, float* s1_out, float* t2_out, void* stream) {
+    GENS_CHECK_ARG(pos && fe && wstream && ksteps && bias && sdf_out && s1_out && t2_out && n >= 0 && n_sm > 0);
+    if (n_ksteps <= 0 || n_ksteps > kMaxKSteps || n_layers <= 0 || n_layers > kMaxLayers || scale == 0.f)
+        return GENS_E_UNSUPPORTED;
+    if (n == 0) return 0;
+    if (int rc = set_smem(sdf_mlp_fwd_kernel<true>)) return rc;
+    const long long tiles = (n + kTileM / 2 - 1) / (kTileM / 2);
+    const int grid = (int)(tiles < n_sm ? tiles : n_sm);
+    sdf_mlp_fwd_kernel<true><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
+        pos, fe, n, wstream, reinterpret_cast<const KStep*>(ksteps), n_ksteps, bias, n_layers, scale, sdf_out, s1_out,
+        t2_out);
+    return gens_launch_status();
+}
+
+// Reverse sweep: s1 / t2 from gens_sdf_mlp_jvp_tc; wstream / ksteps = the transposed network
+// (mlp_tc.PackedSDFReverse); consts (2,128): row 0 = output-layer weights of the last hidden activations /
+// scale, row 1 = output-layer weights of the feature encoding / scale.  skip_layer / skip_col: the layer whose
+// input concatenates the position encoding and the column where it starts.  g_pos (2n,27), g_fe (2n,100).
+extern "C" int gens_sdf_mlp_rev_tc(const float* s1, const float* t2, long long n, const float* wstream,
+                                   const void* ksteps, int n_ksteps, const float* consts, int n_hidden, int skip_layer,
+                                   int skip_col, int n_sm, float* g_pos, float* g_fe, void* stream) {
+    GENS_CHECK_ARG(s1 && t2 && wstream && ksteps && consts && g_pos && g_fe && n >= 0 && n_sm > 0);
+    if (n_ksteps <= 0 || n_ksteps > kMaxKSteps || n_hidden <= 0 || n_hidden >= kMaxLayers || skip_col < 0 ||
+        skip_col + kNP > 128)
+        return GENS_E_UNSUPPORTED;
+    if (n == 0) return 0;
+    if (int rc = set_smem(sdf_mlp_rev_kernel)) return rc;
+    const long long tiles = (n + kTileM / 2 - 1) / (kTileM / 2);
+    const int grid = (int)(tiles < n_sm ? tiles : n_sm);
+    sdf_mlp_rev_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
+        s1, t2, n, wstream, reinterpret_cast<const KStep*>(ksteps), n_ksteps, consts, n_hidden, skip_layer, skip_col,
+        g_pos, g_fe);
     return gens_launch_status();
 }

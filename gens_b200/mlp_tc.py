@@ -15,8 +15,9 @@ Packed format (what gens_sdf_mlp_value_tc expects):
   wstream  float32: per k-step [hi block | lo block]; a block is the (N_l x 16) weights as [4][N_l][4]
            (four 16-byte K chunks, rows contiguous inside a chunk: the canonical K-major no-swizzle UMMA
            layout with LBO = 16 N_l bytes, SBO = 128 bytes); hi = weights rounded to TF32, lo = w - hi.
-  ksteps   uint32 (n,4): byte offset, byte count (128 N_l), A source | index << 8,
-           flags (1 first of layer, 2 last of layer, 4 first H k-step) | N_l << 16.
+  ksteps   uint32 (n,4): byte offset, byte count (128 N_l), A source | index << 8 | accumulator column << 16,
+           flags (1 overwrite the accumulator, 2 commit after this k-step [16: to barrier 1], 4 wait for the
+           epilogue's A operand) | N_l << 16.
   bias     float32 (n_layers, 128), zero padded.
 Fan-outs are padded to multiples of 16 with zero rows (101 -> 112, the single SDF row -> 16), fan-ins to
 multiples of 16 with zero columns; the 1/sqrt(2) of the skip connection is folded into that layer's weights.
@@ -31,6 +32,7 @@ import torch
 from . import _lib
 
 A_F, A_P, A_H = 0, 1, 2
+ACC0, ACC1 = 256, 384  # TMEM columns of the two accumulators (csrc/sdf_mlp_tc.cu)
 F_K, P_K = 112, 32  # padded widths of the resident encodings (csrc/sdf_mlp_tc.cu kFChunks / kPChunks)
 
 
@@ -95,8 +97,8 @@ class PackedSDF:
                     if kind == A_H and j == 0:
                         flags |= 4
                     if si == len(segs) - 1 and j == nb - 1:
-                        flags |= 2
-                    steps.append([off, nbytes, kind | (j << 8), flags])
+                        flags |= 2 | (16 if l & 1 else 0)
+                    steps.append([off, nbytes, kind | (j << 8) | ((ACC1 if l & 1 else ACC0) << 16), flags])
                     off += nbytes
                 chunks.append(blk.reshape(-1))
         self.wstream = torch.cat(chunks).contiguous()
@@ -106,6 +108,56 @@ class PackedSDF:
         self.bias = bias.contiguous()
         self.n_layers = fw.n_layers
         self.scale = float(fw.scale)
+        self.n_sm = torch.cuda.get_device_properties(dev).multi_processor_count if dev.type == "cuda" else 0
+
+
+class PackedSDFReverse:
+    """The transposed network for the reverse sweep (gens_sdf_mlp_rev_tc): per hidden layer l = L-1..0 the
+    x-part W_x^T (cotangent of the layer input, accumulator 0, overwritten per layer) and, for l >= 1, the
+    feature part W_f^T (cotangent of the feature encoding, accumulator 1, summed over the layers)."""
+
+    def __init__(self, fw):
+        dev = fw.wx[0].device
+        last = fw.n_layers - 1
+        inv_sqrt2 = 1.0 / math.sqrt(2.0)
+        chunks: List[torch.Tensor] = []
+        steps: List[List[int]] = []
+        off = 0
+        self.skip_layer, self.skip_col = 0, 0
+        for l in range(last - 1, -1, -1):
+            wx = fw.wx[l].float()
+            if l in fw.skip_in:
+                wx = wx * inv_sqrt2
+                self.skip_layer, self.skip_col = l, fw.fo[l - 1]
+            segs = [(ACC0, wx.t().contiguous())]
+            if l >= 1:
+                segs.append((ACC1, fw.wf[fw.off[l - 1]: fw.off[l - 1] + fw.fo[l]].float().t().contiguous()))
+            for si, (acc, w) in enumerate(segs):
+                n_pad = (w.shape[0] + 15) // 16 * 16
+                if n_pad > 128:
+                    raise RuntimeError("gens_b200 tensor-core SDF kernel: layer inputs wider than 128 are not supported")
+                blk = _blocks(w, n_pad)
+                nb = blk.shape[0]
+                nbytes = n_pad * 128
+                for j in range(nb):
+                    flags = n_pad << 16
+                    if j == 0 and (acc == ACC0 or l == last - 1):
+                        flags |= 1
+                    if j == 0 and si == 0:
+                        flags |= 4
+                    if si == len(segs) - 1 and j == nb - 1:
+                        flags |= 2
+                    steps.append([off, nbytes, A_H | (j << 8) | (acc << 16), flags])
+                    off += nbytes
+                chunks.append(blk.reshape(-1))
+        self.wstream = torch.cat(chunks).contiguous()
+        self.ksteps = torch.tensor(steps, dtype=torch.int64, device="cpu").to(torch.int32).to(dev).contiguous()
+        self.n_ksteps = len(steps)
+        consts = torch.zeros((2, 128), device=dev, dtype=torch.float32)
+        consts[0, : fw.wx[last].shape[1]] = fw.wx[last][0] / fw.scale
+        consts[1, : fw.pe_feat] = fw.wf[fw.off[last - 1]] / fw.scale
+        self.consts = consts.contiguous()
+        self.n_hidden = last
         self.n_sm = torch.cuda.get_device_properties(dev).multi_processor_count if dev.type == "cuda" else 0
 
 
@@ -123,33 +175,134 @@ def sdf_values(packed: PackedSDF, pos: torch.Tensor, fe: torch.Tensor) -> torch.
     return out
 
 
+def sdf_jvp(packed: PackedSDF, pos: torch.Tensor, fe: torch.Tensor, n: int):
+    """pos (2n,27) / fe (2n,100) with tangent rows in [n,2n) -> (sdf (n,1), s1, t2 (n_layers-1, n, 128))."""
+    _lib.require_cuda(pos, fe)
+    dev = pos.device
+    sdf = torch.empty((n, 1), device=dev, dtype=torch.float32)
+    s1 = torch.empty((packed.n_layers - 1, n, 128), device=dev, dtype=torch.float32)
+    t2 = torch.empty((packed.n_layers - 1, n, 128), device=dev, dtype=torch.float32)
+    if n == 0:
+        return sdf, s1, t2
+    _lib.check(_lib.lib().gens_sdf_mlp_jvp_tc(
+        _lib.ptr(pos), _lib.ptr(fe), n, _lib.ptr(packed.wstream), _lib.ptr(packed.ksteps), packed.n_ksteps,
+        _lib.ptr(packed.bias), packed.n_layers, packed.scale, packed.n_sm, _lib.ptr(sdf), _lib.ptr(s1), _lib.ptr(t2),
+        _lib.stream_ptr(dev)), "gens_sdf_mlp_jvp_tc")
+    return sdf, s1, t2
+
+
+def sdf_reverse(rev: PackedSDFReverse, s1: torch.Tensor, t2: torch.Tensor, n: int):
+    """Reverse sweep -> (g_pos (2n,27), g_fe (2n,100)), primal rows first."""
+    dev = s1.device
+    g_pos = torch.empty((2 * n, 27), device=dev, dtype=torch.float32)
+    g_fe = torch.empty((2 * n, 100), device=dev, dtype=torch.float32)
+    if n == 0:
+        return g_pos, g_fe
+    _lib.check(_lib.lib().gens_sdf_mlp_rev_tc(
+        _lib.ptr(s1), _lib.ptr(t2), n, _lib.ptr(rev.wstream), _lib.ptr(rev.ksteps), rev.n_ksteps, _lib.ptr(rev.consts),
+        rev.n_hidden, rev.skip_layer, rev.skip_col, rev.n_sm, _lib.ptr(g_pos), _lib.ptr(g_fe), _lib.stream_ptr(dev)),
+        "gens_sdf_mlp_rev_tc")
+    return g_pos, g_fe
+
+
+def _replay(ksteps, stream, srcs, n_rows, on_commit):
+    """Walks a k-step stream in float64; `on_commit(acc)` is called at every commit with the accumulators
+    ({column: tensor}) and may replace srcs[A_H]."""
+    acc = {}
+    for off, nbytes, a, flags in ksteps:
+        n_pad = (flags >> 16) & 0x1ff
+        assert nbytes == n_pad * 128 and off % 16 == 0
+        blk = stream[off // 4: off // 4 + nbytes // 4].reshape(2, 4, n_pad, 4)
+        w = (blk[0] + blk[1]).permute(1, 0, 2).reshape(n_pad, 16)         # hi + lo, (N, 16)
+        kind, j, col = a & 0xff, (a >> 8) & 0xff, (a >> 16) & 0xfff
+        if flags & 1:
+            acc[col] = torch.zeros((n_rows, 128), dtype=torch.float64)
+        acc[col][:, :n_pad] += srcs[kind][:, 16 * j: 16 * j + 16] @ w.t()
+        if flags & 2:
+            on_commit(acc, col)
+
+
+def _sp(y):
+    t = y * 100.0
+    return torch.where(t > 20.0, y, torch.log1p(torch.exp(t.clamp(max=20.0))) / 100.0)
+
+
+def emulate_grad(packed: PackedSDF, rev: PackedSDFReverse, pos: torch.Tensor, fe: torch.Tensor, n: int):
+    """Float64 replay of the JVP forward and the reverse sweep (tests only).  pos (2n,27), fe (2n,100) ->
+    (sdf (n,1), g_pos (2n,27), g_fe (2n,100))."""
+    rows = 2 * n
+    srcs = {A_F: torch.zeros((rows, F_K), dtype=torch.float64), A_P: torch.zeros((rows, P_K), dtype=torch.float64),
+            A_H: torch.zeros((rows, 128), dtype=torch.float64)}
+    srcs[A_F][:, :fe.shape[1]] = fe.double().cpu()
+    srcs[A_P][:, :pos.shape[1]] = pos.double().cpu()
+    bias = packed.bias.double().cpu()
+    state = {"layer": 0, "s1": [], "t2": [], "sdf": None}
+
+    def fwd_commit(acc, col):
+        l = state["layer"]
+        y = acc[col]
+        if l + 1 < packed.n_layers:
+            a = y[:n] + bias[l]
+            da = y[n:]
+            sig = torch.where(a * 100.0 > 20.0, torch.ones_like(a), torch.sigmoid(a * 100.0))
+            s2 = torch.where(a * 100.0 > 20.0, torch.zeros_like(a), 100.0 * sig * (1.0 - sig))
+            state["s1"].append(sig)
+            state["t2"].append(s2 * da)
+            srcs[A_H] = torch.cat([_sp(a), sig * da], 0)
+        else:
+            state["sdf"] = ((y[:n, :1] + bias[l, :1]) / packed.scale).float()
+        state["layer"] = l + 1
+
+    _replay(packed.ksteps.cpu().tolist(), packed.wstream.double().cpu(), srcs, rows, fwd_commit)
+
+    consts = rev.consts.double().cpu()
+    rstate = {"layer": rev.n_hidden - 1, "g_pos": torch.zeros((rows, 27), dtype=torch.float64), "g_fe": None}
+
+    def load_a(l, g):
+        s1, t2 = state["s1"][l], state["t2"][l]
+        return torch.cat([s1 * g[:n], t2 * g[:n] + s1 * g[n:]], 0)
+
+    g_top = torch.zeros((rows, 128), dtype=torch.float64)
+    g_top[:n] = consts[0]
+    rsrcs = {A_H: load_a(rev.n_hidden - 1, g_top)}
+
+    def rev_commit(acc, col):
+        l = rstate["layer"]          # the layer whose MMAs just finished
+        g = acc[ACC0]
+        if l == rev.skip_layer and l > 0:
+            rstate["g_pos"] += g[:, rev.skip_col: rev.skip_col + 27]
+        if l > 0:
+            rsrcs[A_H] = load_a(l - 1, g)
+        else:
+            rstate["g_pos"] += g[:, :27]
+            gfe = acc[ACC1][:, :100].clone()
+            gfe[:n] += consts[1, :100]
+            rstate["g_fe"] = gfe
+        rstate["layer"] = l - 1
+
+    _replay(rev.ksteps.cpu().tolist(), rev.wstream.double().cpu(), rsrcs, rows, rev_commit)
+    return state["sdf"], rstate["g_pos"].float(), rstate["g_fe"].float()
+
+
 def emulate(packed: PackedSDF, pos: torch.Tensor, fe: torch.Tensor) -> torch.Tensor:
-    """Host restatement of the kernel's k-step machine in float64 (tests only: checks the packing, not the
-    tensor-core arithmetic).  Same inputs and result as sdf_values."""
+    """Host restatement of the value kernel's k-step machine in float64 (tests only: checks the packing, not
+    the tensor-core arithmetic).  Same inputs and result as sdf_values."""
     n = pos.shape[0]
     srcs = {A_F: torch.zeros((n, F_K), dtype=torch.float64), A_P: torch.zeros((n, P_K), dtype=torch.float64),
             A_H: torch.zeros((n, 128), dtype=torch.float64)}
     srcs[A_F][:, :fe.shape[1]] = fe.double().cpu()
     srcs[A_P][:, :pos.shape[1]] = pos.double().cpu()
-    stream = packed.wstream.double().cpu()
-    acc = None
-    layer = 0
-    for off, nbytes, a, flags in packed.ksteps.cpu().tolist():
-        n_pad = (flags >> 16) & 0x1ff
-        assert nbytes == n_pad * 128 and off % 16 == 0
-        blk = stream[off // 4: off // 4 + nbytes // 4].reshape(2, 4, n_pad, 4)
-        w = (blk[0] + blk[1]).permute(1, 0, 2).reshape(n_pad, 16)         # hi + lo, (N, 16)
-        kind, j = a & 0xff, (a >> 8) & 0xff
-        if flags & 1:
-            acc = torch.zeros((n, n_pad), dtype=torch.float64)
-        acc = acc + srcs[kind][:, 16 * j: 16 * j + 16] @ w.t()
-        if flags & 2:
-            y = acc + packed.bias[layer, :n_pad].double().cpu()
-            if layer + 1 < packed.n_layers:
-                t = y * 100.0
-                srcs[A_H] = torch.zeros((n, 128), dtype=torch.float64)
-                srcs[A_H][:, :n_pad] = torch.where(t > 20.0, y, torch.log1p(torch.exp(t.clamp(max=20.0))) / 100.0)
-            else:
-                return (y[:, :1] / packed.scale).float()
-            layer += 1
-    raise RuntimeError("k-step stream ended without an output layer")
+    bias = packed.bias.double().cpu()
+    state = {"layer": 0, "sdf": None}
+
+    def commit(acc, col):
+        l = state["layer"]
+        y = acc[col] + bias[l]
+        if l + 1 < packed.n_layers:
+            srcs[A_H] = _sp(y)
+        else:
+            state["sdf"] = (y[:, :1] / packed.scale).float()
+        state["layer"] = l + 1
+
+    _replay(packed.ksteps.cpu().tolist(), packed.wstream.double().cpu(), srcs, n, commit)
+    return state["sdf"]

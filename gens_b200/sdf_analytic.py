@@ -64,6 +64,14 @@ class FoldedSDF:
         for l in range(1, self.n_layers):
             self.off.append(self.off[-1] + self.fo[l])  # off[l-1] = column of layer l in the feature part
         self._packed = None
+        self._packed_rev = None
+
+    def packed_rev(self):
+        """The transposed network for the tensor-core reverse sweep (built on first use)."""
+        if self._packed_rev is None:
+            from .mlp_tc import PackedSDFReverse
+            self._packed_rev = PackedSDFReverse(self)
+        return self._packed_rev
 
     def packed(self):
         """The same weights in the streaming format of the tensor-core kernel (built on first use)."""
@@ -102,6 +110,19 @@ def value_grad_smooth(net, pts: torch.Tensor, volumes, folded: Optional[FoldedSD
     pos, fe = new(2 * n, fw.pe_in), new(2 * n, fw.pe_feat)
     _c(L.gens_sdf_encode(P(pts), P(feats), P(dfeats), n, fw.scale, _U, fw.multires, fw.feat_multires, nf, P(pos),
                          P(fe), st), "gens_sdf_encode")
+    if USE_TC:
+        # whole MLP on the tensor cores: one persistent kernel forward (value + tangent), one in reverse
+        from . import mlp_tc
+        sdf, s1, t2 = mlp_tc.sdf_jvp(fw.packed(), pos, fe, n)
+        g_pos, g_fe = mlp_tc.sdf_reverse(fw.packed_rev(), s1, t2, n)
+        del s1, t2
+        grad, smooth = new(n, 3), new(n, 3)
+        g_f, dg_f = new(n, nf), new(n, nf)
+        _c(L.gens_sdf_decode(P(pts), P(feats), P(dfeats), P(g_pos), P(g_fe), n, fw.scale, _U, fw.multires,
+                             fw.feat_multires, nf, P(g_f), P(dg_f), P(grad), P(smooth), st), "gens_sdf_decode")
+        _c(L.gens_trilinear_vjp2(P(pts), n, pyr, _U, P(g_f), P(dg_f), P(grad), P(smooth) if need_smooth else None, st),
+           "gens_trilinear_vjp2")
+        return sdf, grad, (smooth if need_smooth else None)
     featpart = fe @ fw.wf_t                                   # (2n, sum fan_out)
     ldfp = featpart.shape[1]
     last = fw.n_layers - 1

@@ -47,3 +47,31 @@ for n in [128, 1000, 128 * 148 * 3 + 77, 1 << 21]:
             for _ in range(5): fn()
             torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5
             print(f'  {name}: {dt*1e3:.2f} ms  ({n/dt/1e6:.1f} Mpts/s)', flush=True)
+
+# ---- value + gradient + second-order term: tensor-core sweep vs the fp32 cuBLAS sweep ----------------------
+def cmp(name, a, b):
+    err = (a - b).abs()
+    tol = 1e-5 * max(1.0, float(b.abs().max())) + 1e-4 * b.abs()
+    bad = int((err > tol).sum())
+    print(f'   {name}: max abs err {float(err.max()):.3e} (scale {float(b.abs().max()):.3f}), beyond 1e-4 tolerance: {bad}/{b.numel()}', flush=True)
+
+for n in [64, 1000, 64 * 148 * 2 + 13, 1 << 20]:
+    pts = torch.rand(n, 3, device=dev, generator=g) * 2 - 1
+    sdf_analytic.USE_TC = False
+    r = sdf_analytic.value_grad_smooth(net, pts, vols, fw)
+    sdf_analytic.USE_TC = True
+    o = sdf_analytic.value_grad_smooth(net, pts, vols, fw)
+    torch.cuda.synchronize()
+    print(f'n={n}: nan={any(bool(t.isnan().any()) for t in o)}', flush=True)
+    for nm, a, b in zip(('sdf', 'grad', 'smooth'), o, r):
+        cmp(nm, a, b)
+    if n >= 1 << 20:
+        for flag, name in ((True, 'tcgen05 sweep'), (False, 'fp32 cuBLAS sweep')):
+            sdf_analytic.USE_TC = flag
+            fn = lambda: sdf_analytic.value_grad_smooth(net, pts, vols, fw)
+            for _ in range(2): fn()
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            for _ in range(3): fn()
+            torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 3
+            print(f'  {name}: {dt*1e3:.2f} ms  ({n/dt/1e6:.1f} Mpts/s)', flush=True)
+sdf_analytic.USE_TC = True
