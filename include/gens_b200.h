@@ -236,6 +236,21 @@ int gens_sdf_decode(const float *pts, const float *feats, const float *dfeats, c
 int gens_sdf_mlp_value_tc(const float *pos, const float *fe, long long n, const float *wstream,
                           const void *ksteps, int n_ksteps, const float *bias, int n_layers, float scale,
                           int n_sm, float *sdf_out, void *stream);
+/* Value + tangent pass of the same network (forward half of SDFNetwork.gradient, sdf_network.py:131-153):
+ * pos (2n,27) / fe (2n,100) carry the directional derivative of the encodings along u in rows [n,2n);
+ * sdf_out (n); s1_out / t2_out (n_layers-1, n, 128) = softplus'(a) and softplus''(a)*da per hidden layer,
+ * kept for the reverse sweep. */
+int gens_sdf_mlp_jvp_tc(const float *pos, const float *fe, long long n, const float *wstream,
+                        const void *ksteps, int n_ksteps, const float *bias, int n_layers, float scale,
+                        int n_sm, float *sdf_out, float *s1_out, float *t2_out, void *stream);
+/* Reverse sweep through value and tangent (the two nested autograd.grad calls of sdf_network.py:139-152):
+ * s1 / t2 from gens_sdf_mlp_jvp_tc; wstream / ksteps = the transposed network (mlp_tc.PackedSDFReverse);
+ * consts (2,128): output-layer weights of the last hidden activations and of the feature encoding, / scale;
+ * skip_layer / skip_col: the layer whose input concatenates the position encoding and its first column.
+ * Writes the cotangents of the encodings g_pos (2n,27), g_fe (2n,100) for gens_sdf_decode. */
+int gens_sdf_mlp_rev_tc(const float *s1, const float *t2, long long n, const float *wstream,
+                        const void *ksteps, int n_ksteps, const float *consts, int n_hidden, int skip_layer,
+                        int skip_col, int n_sm, float *g_pos, float *g_fe, void *stream);
 
 /* Tuning knob for profiling sessions: selects among compiled-in launch configurations of K1
  * (0 = the shipped one).  Results are identical for every variant. */
