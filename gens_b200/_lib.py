@@ -96,6 +96,7 @@ _SIGNATURES = {
     "gens_lookup_feature_bwd": ([_vp, _ll, _i, _vp, _vp, _IP, _i, _vp, _IP, _vp], _i),
     "gens_upsample_rays": ([_vp, _vp, _vp, _vp, _i, _i, _PP, _i, _f, _i, _vp, _vp], _i),
     "gens_merge_samples": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp], _i),
+    "gens_tv_reduce": ([_PP, _PP, _i, _i, _vp, _vp], _i),
     "gens_debug_set_variant": ([_i], _i),
     "gens_selftest_division": ([_i, ctypes.c_ulonglong, _vp, _vp], _i),
 }

@@ -133,6 +133,10 @@ class ImplicitSurface(nn.Module):
     def tv_regularization(self, volume_feat_cas, volume_mask_cas=None):
         """Masked total variation over the pyramid (reference :135-150, incl. its mx.sum() normaliser
         for all three axes)."""
+        needs_graph = torch.is_grad_enabled() and any(v.requires_grad for v in volume_feat_cas)
+        if self.ops is _cuda_ops and not needs_graph:
+            # K9: one fused pass over the pyramid, cached per volume version (csrc/tv_reg.cu)
+            return self.ops.tv_regularization(volume_feat_cas, volume_mask_cas)
         if volume_mask_cas is None:
             volume_mask_cas = [torch.ones_like(v[:, :1]) for v in volume_feat_cas]
         total = 0

@@ -252,6 +252,15 @@ int gens_sdf_mlp_rev_tc(const float *s1, const float *t2, long long n, const flo
                         const void *ksteps, int n_ksteps, const float *consts, int n_hidden, int skip_layer,
                         int skip_col, int n_sm, float *g_pos, float *g_fe, void *stream);
 
+/* K9: masked total variation of the volume pyramid in one pass -- the reduction behind
+ * ImplicitSurface.tv_regularization (reference models/modules/implicit_surface.py:135-150, called from
+ * render_core :260).  vols->vol[s] = (channels,D,D,D) NCDHW, masks->vol[s] = (D,D,D) (masks or an entry NULL =
+ * all ones).  out (n_scales,4) fp64, ACCUMULATED (caller zeroes): sums over channels and voxels of the
+ * squared forward differences along tensor dims 2,3,4 where mask*mask[+1] > 0, and the number of such pairs
+ * along dim 2 (the reference normalises all three axes by that count).  n_blocks = CTAs per scale. */
+int gens_tv_reduce(const gens_pyramid_t *vols, const gens_pyramid_t *masks, int channels, int n_blocks,
+                   double *out, void *stream);
+
 /* Tuning knob for profiling sessions: selects among compiled-in launch configurations of K1
  * (0 = the shipped one).  Results are identical for every variant. */
 int gens_debug_set_variant(int variant);
