@@ -60,6 +60,17 @@ def make_image_pyramid(tensors, sizes):
     return p
 
 
+class CompositeArgs(ctypes.Structure):
+    """Mirror of gens_composite_args_t."""
+    _fields_ = ([("n_rays", _i), ("n_samples", _i), ("n_src", _i), ("cos_anneal_ratio", _f), ("sample_dist", _f)]
+                + [(k, _vp) for k in (
+                    "rays_o", "rays_d", "z_vals", "pts", "sdf_raw", "grad_raw", "smooth_raw", "colour_raw",
+                    "voxel_mask", "evaluated", "mask_views", "inv_s", "z_max", "rot",
+                    "weights_out", "weight_sum_out", "weight_max_out", "depth_out", "color_out", "normal_out",
+                    "inside_out", "valid_out", "sdf_out", "gradients_out", "mid_inside_out", "sdf_depth_out",
+                    "pts_sdf0_out", "ge_num_out", "ge_den_out", "smooth_norm_out")])
+
+
 _PP = ctypes.POINTER(Pyramid)
 _IP = ctypes.POINTER(ImagePyramid)
 
@@ -96,6 +107,7 @@ _SIGNATURES = {
     "gens_lookup_feature_bwd": ([_vp, _ll, _i, _vp, _vp, _IP, _i, _vp, _IP, _vp], _i),
     "gens_upsample_rays": ([_vp, _vp, _vp, _vp, _i, _i, _PP, _i, _f, _i, _vp, _vp], _i),
     "gens_merge_samples": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp], _i),
+    "gens_composite_rays": ([ctypes.POINTER(CompositeArgs), _vp], _i),
     "gens_tv_reduce": ([_PP, _PP, _i, _i, _vp, _vp], _i),
     "gens_debug_set_variant": ([_i], _i),
     "gens_selftest_division": ([_i, ctypes.c_ulonglong, _vp, _vp], _i),

@@ -73,6 +73,7 @@ class ImplicitSurface(nn.Module):
         self.deviation_network = SingleVarianceNetwork(**confs["variance_network"])
         self.val_chunk = 256  # rays per render() call in validate(); 256 = the reference's split
         self.analytic_nograd = True  # under torch.no_grad(): hand-differentiated SDF sweep instead of autograd
+        self.fused_composite = True  # K7 warp-per-ray compositing kernel for the no-grad render_core tail
         self.fused_upsample = True   # K5 warp-per-ray kernels for up_sample / cat_z_vals (CUDA tensors)
 
     def _fold_sdf(self):
@@ -151,6 +152,65 @@ class ImplicitSurface(nn.Module):
             total = total + torch.sqrt(tx + ty + tz) * 0.5 ** i
         return total
 
+    def _patch_warp(self, pts_sdf0, g_sdf0, features, match_features, intrs, c2ws, step):
+        """Feature-metric consistency patches around the surface points (reference :303-328)."""
+        src = features if (step is None or step < 5) else match_features
+        f0 = src[0].detach()
+        ups = [F.interpolate(src[k].detach(), size=f0.shape[-2:], mode="bilinear") for k in (1, 2)]
+        warp_feats = torch.cat([f0] + ups, dim=1).detach()
+        return self.ops.surface_patch_warp(pts_sdf0, g_sdf0, warp_feats, intrs, c2ws)
+
+    def _surface_normal(self, pts_sdf0, volumes, c2ws, analytic):
+        """Unit SDF gradient at the zero-crossing points, in the reference camera frame (reference :300-302)."""
+        b = pts_sdf0.shape[0]
+        if analytic:
+            _, g_sdf0, _ = self.sdf_network.value_grad_smooth_nograd(pts_sdf0.reshape(-1, 3), volumes, False)
+        else:
+            g_sdf0, _ = self.sdf_network.gradient(pts_sdf0.reshape(-1, 3), volumes)
+        g_sdf0 = g_sdf0.reshape(b, 1, 3)
+        g_norm = torch.linalg.norm(g_sdf0, ord=2, dim=-1, keepdim=True)
+        g_norm = torch.where(g_norm <= 0, torch.ones_like(g_norm) * 1e-8, g_norm)
+        return ((g_sdf0 / g_norm) @ c2ws[0, :3, :3]).detach()
+
+    def _render_core_fused(self, rays_o, rays_d, z_vals, sample_dist, pts, voxel_mask, evaluated, sdf_val, grad_all,
+                           smooth_all, volumes, mask_volumes, features, match_features, imgs, intrs, c2ws,
+                           cos_anneal_ratio, step):
+        """Inference tail of render_core on K7 (csrc/composite.cu): one launch for the masking, alphas,
+        transmittance, every per-ray reduction and the zero-crossing search."""
+        b, n = z_vals.shape
+        feat_views, ray_diff, mask_views = self.ops.lookup_feature(pts, imgs, intrs, c2ws, features)
+        mask_views = mask_views & evaluated[:, None]
+        colour = self.color_network(feat_views, ray_diff, mask_views)
+        inv_s_raw = self.deviation_network(torch.zeros([1, 3]).type_as(rays_o))[:, :1]
+        c = self.ops.composite_rays(rays_o, rays_d, z_vals, pts, sdf_val, grad_all, smooth_all, colour, voxel_mask,
+                                    evaluated, mask_views, inv_s_raw, _inverse(c2ws[0, :3, :3]), cos_anneal_ratio,
+                                    sample_dist)
+        pts_random = torch.rand([1024, 3]).type_as(rays_o) * 2 - 1
+        sdf_random = self.sdf_network.sdf(pts_random, volumes)
+        g_sdf0 = self._surface_normal(c["pts_sdf0"], volumes, c2ws, True)
+        ref_gray_val, sampled_gray_val = self._patch_warp(c["pts_sdf0"], g_sdf0, features, match_features, intrs, c2ws,
+                                                          step)
+        return {
+            'ref_gray_val': ref_gray_val,
+            'sampled_gray_val': sampled_gray_val,
+            'mid_inside_sphere': c["mid_inside_sphere"],
+            'smooth_error': c["smooth_norm"].mean(),
+            'tv_reg': self.tv_regularization(volumes, mask_volumes),
+            'color_fine': c["color_fine"],
+            'render_depth': c["render_depth"],
+            'valid_mask': c["valid_mask"],
+            'sparse_sdf': torch.cat([sdf_random, c["sdf"]]),
+            'gradients': c["gradients"],
+            'normal': c["normal"],
+            's_val': (1.0 / inv_s_raw.clip(1e-6, 1e6)).expand(b * n, 1),
+            'weights': c["weights"],
+            'weight_sum': c["weight_sum"],
+            'weight_max': c["weight_max"],
+            'gradient_error': c["ge_num"].sum() / (c["ge_den"].sum() + 1e-5),
+            'inside_sphere': c["inside_sphere"],
+            'sdf_depth': c["sdf_depth"],
+        }
+
     # ------------------------------------------------------------------------------ rendering
     def render_core(self, rays_o, rays_d, z_vals, sample_dist, volumes, mask_volumes, features, match_features,
                     imgs, intrs, c2ws, cos_anneal_ratio, step):
@@ -175,6 +235,10 @@ class ImplicitSurface(nn.Module):
         else:
             sdf_val = self.sdf_network(pts, volumes)[:, :1]
             grad_all, smooth_all = self.sdf_network.gradient(pts.clone(), volumes)
+        if analytic and self.fused_composite:
+            return self._render_core_fused(rays_o, rays_d, z_vals, sample_dist, pts, voxel_mask, evaluated, sdf_val,
+                                           grad_all, smooth_all, volumes, mask_volumes, features, match_features,
+                                           imgs, intrs, c2ws, cos_anneal_ratio, step)
         sdf = torch.where(ev, sdf_val, torch.full_like(sdf_val, FAR_SDF))
         gradients = torch.where(ev, grad_all, torch.zeros_like(grad_all))
         smooth = torch.where(ev, smooth_all, torch.zeros_like(smooth_all))
@@ -243,20 +307,8 @@ class ImplicitSurface(nn.Module):
         z_sdf0 = torch.where(z_sdf0 < 0, torch.zeros_like(z_sdf0), z_sdf0)
         z_sdf0 = torch.where(z_sdf0 > torch.max(z_vals), torch.zeros_like(z_sdf0), z_sdf0)
         pts_sdf0 = rays_o[:, None, :] + rays_d[:, None, :] * z_sdf0[..., :, None]
-        if analytic:
-            _, g_sdf0, _ = self.sdf_network.value_grad_smooth_nograd(pts_sdf0.reshape(-1, 3), volumes, False)
-        else:
-            g_sdf0, _ = self.sdf_network.gradient(pts_sdf0.reshape(-1, 3), volumes)
-        g_sdf0 = g_sdf0.reshape(b, 1, 3)
-        g_norm = torch.linalg.norm(g_sdf0, ord=2, dim=-1, keepdim=True)
-        g_norm = torch.where(g_norm <= 0, torch.ones_like(g_norm) * 1e-8, g_norm)
-        g_sdf0 = ((g_sdf0 / g_norm) @ c2ws[0, :3, :3]).detach()  # normal in the reference camera frame
-
-        src = features if (step is None or step < 5) else match_features
-        f0 = src[0].detach()
-        ups = [F.interpolate(src[k].detach(), size=f0.shape[-2:], mode="bilinear") for k in (1, 2)]
-        warp_feats = torch.cat([f0] + ups, dim=1).detach()
-        ref_gray_val, sampled_gray_val = self.ops.surface_patch_warp(pts_sdf0, g_sdf0, warp_feats, intrs, c2ws)
+        g_sdf0 = self._surface_normal(pts_sdf0, volumes, c2ws, analytic)
+        ref_gray_val, sampled_gray_val = self._patch_warp(pts_sdf0, g_sdf0, features, match_features, intrs, c2ws, step)
 
         return {
             'ref_gray_val': ref_gray_val,

@@ -374,3 +374,42 @@ def tv_regularization(volume_feat_cas, volume_mask_cas=None) -> torch.Tensor:
     _TV_CACHE.clear()  # one pyramid at a time
     _TV_CACHE[key] = ([weakref.ref(t) for t in every], total)
     return total
+
+
+# ---- K7: alpha compositing, one warp per ray (reference implicit_surface.py:179-326) ----------------
+def composite_rays(rays_o, rays_d, z_vals, pts, sdf_raw, grad_raw, smooth_raw, colour_raw, voxel_mask, evaluated,
+                   mask_views, inv_s, rot, cos_anneal_ratio: float, sample_dist: float) -> Dict[str, torch.Tensor]:
+    """Everything render_core computes between the network evaluations and its output dictionary, for
+    inference (no autograd graph), in one launch (csrc/composite.cu).  voxel_mask / evaluated (n,) and
+    mask_views (n,ns) are bool; inv_s is the (1,1) un-clipped deviation-network output; rot (3,3)."""
+    _lib.require_cuda(rays_o, rays_d, z_vals, pts, sdf_raw, grad_raw, smooth_raw, colour_raw, voxel_mask, evaluated,
+                      mask_views, inv_s, rot)
+    b, n = z_vals.shape
+    dev = z_vals.device
+    f, u8 = _lib.f32c, lambda t: t.contiguous().view(torch.uint8) if t.dtype == torch.bool else t.to(torch.uint8).contiguous()
+    keep = [f(rays_o), f(rays_d), f(z_vals), f(pts.reshape(-1, 3)), f(sdf_raw.reshape(-1)), f(grad_raw.reshape(-1, 3)),
+            f(smooth_raw.reshape(-1, 3)), f(colour_raw.reshape(-1, 3)), u8(voxel_mask.reshape(-1)),
+            u8(evaluated.reshape(-1)), u8(mask_views.reshape(b * n, -1)), f(inv_s.reshape(-1)),
+            f(z_vals.max().reshape(1)), f(rot)]
+    new = lambda *shape, dtype=torch.float32: torch.empty(shape, device=dev, dtype=dtype)
+    out = {"weights": new(b, n), "weight_sum": new(b, 1), "weight_max": new(b, 1), "render_depth": new(b),
+           "color_fine": new(b, 3), "normal": new(b, 3), "inside_sphere": new(b, n),
+           "valid_mask": new(b, 1, dtype=torch.uint8), "sdf": new(b * n, 1), "gradients": new(b, n, 3),
+           "mid_inside_sphere": new(b, 1), "sdf_depth": new(b, 1), "pts_sdf0": new(b, 1, 3), "ge_num": new(b),
+           "ge_den": new(b), "smooth_norm": new(b)}
+    a = _lib.CompositeArgs()
+    a.n_rays, a.n_samples, a.n_src = b, n, keep[10].shape[1]
+    a.cos_anneal_ratio, a.sample_dist = float(cos_anneal_ratio), float(sample_dist)
+    for name, t in zip(("rays_o", "rays_d", "z_vals", "pts", "sdf_raw", "grad_raw", "smooth_raw", "colour_raw",
+                        "voxel_mask", "evaluated", "mask_views", "inv_s", "z_max", "rot"), keep):
+        setattr(a, name, t.data_ptr())
+    for name, key in (("weights_out", "weights"), ("weight_sum_out", "weight_sum"), ("weight_max_out", "weight_max"),
+                      ("depth_out", "render_depth"), ("color_out", "color_fine"), ("normal_out", "normal"),
+                      ("inside_out", "inside_sphere"), ("valid_out", "valid_mask"), ("sdf_out", "sdf"),
+                      ("gradients_out", "gradients"), ("mid_inside_out", "mid_inside_sphere"),
+                      ("sdf_depth_out", "sdf_depth"), ("pts_sdf0_out", "pts_sdf0"), ("ge_num_out", "ge_num"),
+                      ("ge_den_out", "ge_den"), ("smooth_norm_out", "smooth_norm")):
+        setattr(a, name, out[key].data_ptr())
+    _lib.check(_lib.lib().gens_composite_rays(ctypes.byref(a), _lib.stream_ptr(dev)), "gens_composite_rays")
+    out["valid_mask"] = out["valid_mask"].bool()
+    return out

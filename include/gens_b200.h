@@ -252,6 +252,42 @@ int gens_sdf_mlp_rev_tc(const float *s1, const float *t2, long long n, const flo
                         const void *ksteps, int n_ksteps, const float *consts, int n_hidden, int skip_layer,
                         int skip_col, int n_sm, float *g_pos, float *g_fe, void *stream);
 
+/* ---- K7: alpha compositing, one warp per ray ------------------------------------------------
+ * The part of ImplicitSurface.render_core (reference models/modules/implicit_surface.py:179-326) between the
+ * network evaluations and the output dictionary, for inference (no autograd graph): masking of the evaluated
+ * samples, cosine annealing + NeuS section alphas (:206-226), transmittance / weights (:235-236), the weighted
+ * ray sums (colour, normal, depth :238-247), the per-ray partial sums of the eikonal and smoothness terms
+ * (:249-257), the visibility count of valid_mask (:202-203) and the first SDF zero crossing with its
+ * interpolated depth and surface point (:262-300).  n = n_rays * n_samples sample points, ray-major. */
+typedef struct gens_composite_args {
+    int n_rays, n_samples /* <= 160 */, n_src;
+    float cos_anneal_ratio, sample_dist;
+    const float *rays_o, *rays_d;       /* (n_rays,3)                                                      */
+    const float *z_vals;                /* (n_rays,n_samples) sorted sample depths                         */
+    const float *pts;                   /* (n,3) section mid-points o + d * mid_z (as fed to the networks) */
+    const float *sdf_raw;               /* (n)   SDF at pts, before masking                                */
+    const float *grad_raw, *smooth_raw; /* (n,3) SDF gradient and second-order term, before masking        */
+    const float *colour_raw;            /* (n,3) blended colour, before masking                            */
+    const uint8_t *voxel_mask;          /* (n)   nearest-mask look-up of pts                               */
+    const uint8_t *evaluated;           /* (n)   voxel_mask, or the first-10 fallback of an all-masked batch */
+    const uint8_t *mask_views;          /* (n,n_src) per-view validity of lookup_feature AND evaluated     */
+    const float *inv_s;                 /* (1)   exp(10 * variance), clipped to [1e-6,1e6] in the kernel    */
+    const float *z_max;                 /* (1)   max over the batch of z_vals (:297)                       */
+    const float *rot;                   /* (3,3) inverse(c2ws[0,:3,:3])                                    */
+    float *weights_out;                 /* (n_rays,n_samples)                                              */
+    float *weight_sum_out, *weight_max_out, *depth_out; /* (n_rays)                                        */
+    float *color_out, *normal_out;      /* (n_rays,3)                                                      */
+    float *inside_out;                  /* (n_rays,n_samples) inside_sphere                                */
+    uint8_t *valid_out;                 /* (n_rays) valid_mask                                             */
+    float *sdf_out;                     /* (n)   masked SDF (100 outside)                                  */
+    float *gradients_out;               /* (n,3) masked gradients                                          */
+    float *mid_inside_out, *sdf_depth_out; /* (n_rays)                                                     */
+    float *pts_sdf0_out;                /* (n_rays,3) surface point of the first zero crossing             */
+    float *ge_num_out, *ge_den_out;     /* (n_rays) sums of relax*(|g|-1)^2 and of relax                   */
+    float *smooth_norm_out;             /* (n_rays) | sum_j smooth_j w_j inside_j |                        */
+} gens_composite_args_t;
+int gens_composite_rays(const gens_composite_args_t *args, void *stream);
+
 /* K9: masked total variation of the volume pyramid in one pass -- the reduction behind
  * ImplicitSurface.tv_regularization (reference models/modules/implicit_surface.py:135-150, called from
  * render_core :260).  vols->vol[s] = (channels,D,D,D) NCDHW, masks->vol[s] = (D,D,D) (masks or an entry NULL =

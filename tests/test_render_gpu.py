@@ -207,3 +207,32 @@ def test_render_is_chunk_invariant_and_masks_force_far(setup):
         none = surf.render(ro[:64], rd[:64], scene.near, scene.far, volumes, empty, scene.imgs, scene.features,
                            scene.features, scene.intrs, scene.c2ws, 1.0, None)
     assert float(none["weight_sum"].abs().max()) == 0.0
+
+
+def test_k7_composite_kernel_matches_aten_tail(setup):
+    """K7 (csrc/composite.cu) against the ATen-op tail of render_core on identical network outputs: every
+    key of the output dictionary, discrete ones exactly."""
+    g, surf, scene, volumes, masks = setup
+    ro, rd = scene.rays(step=3)
+    outs = {}
+    for fused in (True, False):
+        surf.fused_composite = fused
+        torch.manual_seed(11)
+        with torch.no_grad():
+            outs[fused] = surf.render(ro, rd, scene.near, scene.far, volumes, masks, scene.imgs, scene.features,
+                                      scene.features, scene.intrs, scene.c2ws, 0.7, None)
+    surf.fused_composite = True
+    a, b = outs[True], outs[False]
+    assert sorted(a.keys()) == sorted(b.keys())
+    problems = []
+    for k in sorted(a.keys()):
+        assert a[k].shape == b[k].shape and a[k].dtype == b[k].dtype, (k, a[k].shape, b[k].shape, a[k].dtype, b[k].dtype)
+        if k in ("valid_mask", "inside_sphere", "mid_inside_sphere"):
+            assert torch.equal(a[k], b[k]), k
+            continue
+        # the surface normal / patches hang on the zero-crossing point, whose gradient jumps at voxel faces
+        problems.append(_mismatch(k, a[k], b[k].cpu().numpy(), atol_scale=2e-6,
+                                  outlier_frac=JUMPY.get(k, 0.0) if k in ("ref_gray_val", "sampled_gray_val") else 0.0))
+    problems = [p for p in problems if p]
+    assert not problems, "\n".join(problems)
+    assert float(a["weight_sum"].max()) > 0.5   # the scene has surfaces: the comparison is not vacuous
