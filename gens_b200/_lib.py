@@ -78,7 +78,8 @@ _SIGNATURES = {
     "gens_abi_version": ([], _i),
     "gens_error_string": ([_i], ctypes.c_char_p),
     "gens_pack_feature_maps": ([_vp, _vp, _i, _i, _i, _vp], _i),
-    "gens_pack_feature_maps_multi": ([_vp, _vp, _vp, _vp, _i, _i, _vp], _i),
+    "gens_pack_feature_maps_multi": ([_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp], _i),
+    "gens_invert_poses": ([_vp, _i, _vp, _vp], _i),
     "gens_unpack_feature_grads": ([_vp, _vp, _i, _i, _i, _vp], _i),
     "gens_volume_agg_fwd_multi": ([ctypes.POINTER(VolumeScale), _i, _i, _vp, _vp, _i, _i, _vp], _i),
     "gens_volume_agg_fwd": ([_vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _i, _i, _i, _ll, _i, _i, _vp, _vp, _vp], _i),
@@ -168,6 +169,18 @@ def f32c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()
+
+
+def invert_poses(t: torch.Tensor) -> torch.Tensor:
+    """inverse of (n,4,4) fp32 CUDA matrices in ONE launch, bit-identical to torch.inverse on CUDA
+    (gens_invert_poses); the reference's torch.inverse(c2ws) costs 11 library launches."""
+    require_cuda(t)
+    if t.dim() != 3 or t.shape[1:] != (4, 4):
+        raise RuntimeError(f"invert_poses expects (n,4,4), got {tuple(t.shape)}")
+    src = f32c(t)
+    out = torch.empty_like(src)
+    check(lib().gens_invert_poses(ptr(src), src.shape[0], ptr(out), stream_ptr(t.device)), "gens_invert_poses")
+    return out
 
 
 def inverse(t: torch.Tensor) -> torch.Tensor:

@@ -473,11 +473,81 @@ struct PackJobs {
     PackJob job[GENS_MAX_SCALES];
     int n_jobs, n_maps;
     long long total;
+    const float* poses;  // optional: (n_poses,4,4) matrices to invert beside the packing (world-to-camera)
+    float* poses_inv;
+    int n_poses;
 };
+
+// inverse(A) for one 4x4 matrix, rounding for rounding what torch.linalg.inv_ex / torch.inverse return on
+// CUDA (cuBLAS getrfBatched + getrsBatched on the identity): partial-pivoting LU whose multipliers are
+// a * RN(1/pivot), fused multiply-subtract updates, unit-lower forward substitution in ascending order,
+// back substitution accumulating from the last column down, true division by the diagonal.  Identified
+// offline (tools/fit_inverse.py: 20 016 of 20 016 camera matrices bit-identical) and pinned by
+// tests/test_volume_gpu.py::test_pose_inverse_is_bit_identical_to_torch.
+__device__ void invert4x4_like_torch(const float* __restrict__ A, float* __restrict__ out) {
+    float a[4][4];
+    int perm[4] = {0, 1, 2, 3};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[i][j] = A[4 * i + j];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int p = k;
+        float best = fabsf(a[k][k]);
+#pragma unroll
+        for (int i = k + 1; i < 4; ++i)
+            if (fabsf(a[i][k]) > best) { best = fabsf(a[i][k]); p = i; }
+#pragma unroll
+        for (int i = k + 1; i < 4; ++i)
+            if (i == p) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float t = a[k][j]; a[k][j] = a[i][j]; a[i][j] = t; }
+                const int t = perm[k]; perm[k] = perm[i]; perm[i] = t;
+            }
+        const float r = __frcp_rn(a[k][k]);
+#pragma unroll
+        for (int i = k + 1; i < 4; ++i) {
+            const float l = __fmul_rn(a[i][k], r);
+            a[i][k] = l;
+#pragma unroll
+            for (int j = k + 1; j < 4; ++j) a[i][j] = __fmaf_rn(-l, a[k][j], a[i][j]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {  // column c of the inverse: solve L U x = P e_c
+        float x[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float y = perm[i] == c ? 1.0f : 0.0f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < i) y = __fmaf_rn(-a[i][j], x[j], y);
+            x[i] = y;
+        }
+#pragma unroll
+        for (int i = 3; i >= 0; --i) {
+            float y = x[i];
+#pragma unroll
+            for (int j = 3; j >= 0; --j)
+                if (j > i) y = __fmaf_rn(-a[i][j], x[j], y);
+            x[i] = __fdiv_rn(y, a[i][i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) out[4 * i + c] = x[i];
+    }
+}
+
+__global__ void __launch_bounds__(64) invert_poses_kernel(const float* __restrict__ poses, float* __restrict__ inv,
+                                                          int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) invert4x4_like_torch(poses + 16 * i, inv + 16 * i);
+}
 
 __global__ void __launch_bounds__(256)
 pack_pairs_kernel(const __grid_constant__ PackJobs jobs) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < jobs.n_poses) invert4x4_like_torch(jobs.poses + 16 * i, jobs.poses_inv + 16 * i);
     if (i >= jobs.total) return;
     int s = 0;
 #pragma unroll
@@ -534,13 +604,25 @@ extern "C" int gens_debug_set_variant(int variant) {
     return 0;
 }
 
+extern "C" int gens_invert_poses(const float* poses, int n, float* poses_inv, void* stream) {
+    if (n == 0) return 0;
+    GENS_CHECK_ARG(poses && poses_inv && n > 0);
+    invert_poses_kernel<<<ceil_div_i(n, 64), 64, 0, (cudaStream_t)stream>>>(poses, poses_inv, n);
+    return gens_launch_status();
+}
+
 extern "C" int gens_pack_feature_maps_multi(const float* const* src_nchw, float* const* dst_pairs, const int* h,
-                                            const int* w, int n_scales, int n, void* stream) {
+                                            const int* w, int n_scales, int n, const float* poses,
+                                            float* poses_inv, int n_poses, void* stream) {
     GENS_CHECK_ARG(src_nchw && dst_pairs && h && w && n_scales > 0 && n > 0);
+    GENS_CHECK_ARG(n_poses == 0 || (poses && poses_inv && n_poses > 0 && n_poses <= 256));
     if (n_scales > GENS_MAX_SCALES) return GENS_E_UNSUPPORTED;
     PackJobs jobs;
     jobs.n_jobs = n_scales;
     jobs.n_maps = n;
+    jobs.poses = poses;
+    jobs.poses_inv = poses_inv;
+    jobs.n_poses = n_poses;
     long long total = 0;
     for (int i = 0; i < n_scales; ++i) {
         GENS_CHECK_ARG(src_nchw[i] && dst_pairs[i] && h[i] > 0 && w[i] > 0);
@@ -557,7 +639,7 @@ extern "C" int gens_pack_feature_maps_multi(const float* const* src_nchw, float*
 }
 
 extern "C" int gens_pack_feature_maps(const float* src_nchw, float* dst_pairs, int n, int h, int w, void* stream) {
-    return gens_pack_feature_maps_multi(&src_nchw, &dst_pairs, &h, &w, 1, n, stream);
+    return gens_pack_feature_maps_multi(&src_nchw, &dst_pairs, &h, &w, 1, n, nullptr, nullptr, 0, stream);
 }
 
 extern "C" int gens_unpack_feature_grads(const float* src_padded_nhwc, float* dst_nchw, int n, int h, int w,

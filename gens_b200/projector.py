@@ -251,7 +251,7 @@ def lookup_feature(pts, imgs, intrs, c2ws, features):
     if any(f.shape[1] != 4 for f in features) or imgs.shape[1] != 3:
         raise RuntimeError("gens_b200.lookup_feature is built for 4-channel feature maps and RGB images")
     p = _lib.f32c(pts.reshape(-1, 3))
-    w2c_src = _lib.f32c(_lib.inverse(c2ws[1:]))  # same op as the reference (projector.py:322)
+    w2c_src = _lib.invert_poses(c2ws[1:])  # torch.inverse(c2ws[1:]) of the reference (projector.py:322), one launch
     k_src = _lib.f32c(intrs[1:])
     return _LookupFeature.apply(p, w2c_src, k_src, _lib.f32c(c2ws[0]), _lib.f32c(c2ws[1:]), imgs[1:], *features)
 

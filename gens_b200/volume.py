@@ -38,8 +38,9 @@ def pack_feature_maps(feat: torch.Tensor) -> torch.Tensor:
     return pack_feature_pyramid([feat])[0]
 
 
-def pack_feature_pyramid(features: Sequence[torch.Tensor]) -> List[torch.Tensor]:
-    """All scales with ONE kernel launch (gens_pack_feature_maps_multi)."""
+def pack_feature_pyramid(features: Sequence[torch.Tensor], poses: Optional[torch.Tensor] = None):
+    """All scales with ONE kernel launch (gens_pack_feature_maps_multi).  With `poses` (n,4,4) the same
+    launch also inverts them (bit-identical to torch.inverse on CUDA) and (packed, poses_inv) is returned."""
     feats = []
     for f in features:
         _lib.require_cuda(f)
@@ -56,9 +57,18 @@ def pack_feature_pyramid(features: Sequence[torch.Tensor]) -> List[torch.Tensor]
     dst = (ctypes.c_void_p * k)(*[o.data_ptr() for o in outs])
     hs = (ctypes.c_int * k)(*[f.shape[2] for f in feats])
     ws = (ctypes.c_int * k)(*[f.shape[3] for f in feats])
-    _lib.check(_lib.lib().gens_pack_feature_maps_multi(src, dst, hs, ws, k, n, _lib.stream_ptr(dev)),
-               "gens_pack_feature_maps_multi")
-    return outs
+    inv = None
+    if poses is not None:
+        _lib.require_cuda(poses)
+        if poses.dim() != 3 or poses.shape[1:] != (4, 4):
+            raise RuntimeError(f"camera poses must be (n,4,4), got {tuple(poses.shape)}")
+        poses = _lib.f32c(poses)
+        inv = torch.empty_like(poses)
+    _lib.check(_lib.lib().gens_pack_feature_maps_multi(
+        src, dst, hs, ws, k, n, _lib.ptr(poses) if inv is not None else None,
+        _lib.ptr(inv) if inv is not None else None, poses.shape[0] if inv is not None else 0, _lib.stream_ptr(dev)),
+        "gens_pack_feature_maps_multi")
+    return outs if inv is None else (outs, inv)
 
 
 def stage_cameras(intrs: torch.Tensor, c2ws: torch.Tensor, scale: int):
@@ -74,9 +84,11 @@ class _AggMeanVar(torch.autograd.Function):
     no_grad in the reference, volume.py:27-44)."""
 
     @staticmethod
-    def forward(ctx, w2c, intrs, dims, slabs, min_vis_view, div_mode, outs, *features):
+    def forward(ctx, c2ws, intrs, dims, slabs, min_vis_view, div_mode, outs, *features):
         dev = features[0].device
-        packed = pack_feature_pyramid(features)
+        # one launch: channels-last pixel pairs of every scale + w2c = inverse(c2ws) (the reference's
+        # torch.inverse, volume.py:34, reproduced bit for bit without its 11 library launches / host sync)
+        packed, w2c = pack_feature_pyramid(features, c2ws)
         nv = features[0].shape[0]
         n = len(dims)
         scales = (_lib.VolumeScale * n)()
@@ -143,12 +155,9 @@ def agg_mean_var(features, intrs, c2ws, dims, min_vis_view: int = 1,
     (contiguous, fp32) output buffers, e.g. views into an all-gather send buffer.
     Returns (volumes, mask_volumes) as the reference."""
     _lib.require_cuda(intrs, c2ws, *features[:len(dims)])
-    # the reference's torch.inverse (volume.py:34) minus its host-synchronising singularity check: same LU
-    # kernels, bit-identical matrices, and the build stays asynchronous
-    w2c = _lib.f32c(_lib.inverse(c2ws))
     k = _lib.f32c(intrs)
     slabs = [(0, d) for d in dims] if slabs is None else list(slabs)
-    out = _AggMeanVar.apply(w2c, k, tuple(dims), tuple(slabs), min_vis_view, div_mode, outs,
+    out = _AggMeanVar.apply(_lib.f32c(c2ws), k, tuple(dims), tuple(slabs), min_vis_view, div_mode, outs,
                             *features[:len(dims)])
     n = len(dims)
     return list(out[:n]), list(out[n:])

@@ -82,9 +82,16 @@ int gens_volume_agg_fwd(const float *feat_padded, int nv, int H, int W, const fl
                         const float *intrs, float k_row_scale, const float *grid, int D, int a0,
                         int a1, int a_base, long long channel_stride, int min_vis_view,
                         int div_mode, float *volume, float *mask_volume, void *stream);
-/* Pack every scale's (n,4,h_i,w_i) map with ONE kernel launch. */
+/* Pack every scale's (n,4,h_i,w_i) map with ONE kernel launch.  The same launch can invert the camera
+ * poses: poses (n_poses,4,4) -> poses_inv, bit-identical to the reference's torch.inverse(c2ws) on CUDA
+ * (volume.py:34; see gens_invert_poses); n_poses = 0 skips it. */
 int gens_pack_feature_maps_multi(const float *const *src_nchw, float *const *dst_pairs,
-                                 const int *h, const int *w, int n_scales, int n, void *stream);
+                                 const int *h, const int *w, int n_scales, int n, const float *poses,
+                                 float *poses_inv, int n_poses, void *stream);
+/* inverse of n 4x4 matrices in one launch, rounding for rounding what torch.inverse / torch.linalg.inv_ex
+ * return on CUDA (cuBLAS batched LU + triangular solves; reference volume.py:34, projector.py:322) -- replaces
+ * the 11 library launches of that call. */
+int gens_invert_poses(const float *poses, int n, float *poses_inv, void *stream);
 
 /* Multi-GPU assembly: after ONE all-gather of the per-rank slab buffers (rank-major, `rank_stride`
  * floats per rank; at `scale_off` inside each block the 8 volume channels + mask of this scale as

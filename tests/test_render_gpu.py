@@ -128,7 +128,33 @@ def test_k5_kernels_match_torch_path(setup):
     surf.fused_upsample = True
 
 
-def test_full_render_matches_reference(setup):
+# Golden comparison of the whole render, on both MLP back-ends.  use_tc = False (fp32 cuBLAS chain): the tight
+# bounds.  use_tc = True (shipped): the SDF values of the up-sampling loop carry the tensor-core floor of 1e-5,
+# which the inverse-CDF sampling at inv_s up to 512 turns into sample depths moved by up to ~1e-4; the per-ray
+# image outputs (colour, depths, normal) still meet the tight bound, the PER-SAMPLE quantities (weights,
+# gradients at the samples) and the patches sampled from white-noise feature maps around the interpolated
+# zero crossing get the stated looser floor.
+TC_RENDER = {"weights": dict(atol_scale=2e-3), "weight_sum": dict(atol_scale=2e-3), "weight_max": dict(atol_scale=2e-3),
+             "gradients": dict(atol_scale=1e-5, outlier_frac=1e-2), "normal": dict(atol_scale=1e-5, outlier_frac=1e-2),
+             "sampled_gray_val": dict(atol_scale=1e-2), "ref_gray_val": dict(atol_scale=1e-2),
+             "s_val": dict(atol_scale=1e-5)}
+
+
+def _render_tolerances(key, use_tc):
+    if use_tc and key in TC_RENDER:
+        return dict(rtol=1e-4, **TC_RENDER[key])
+    return dict(rtol=1e-3 if key == "smooth_error" else 1e-4, atol_scale=1e-5, outlier_frac=JUMPY.get(key, 0.0))
+
+
+@pytest.fixture(params=[False, True], ids=["fp32", "tc"])
+def use_tc(request):
+    from gens_b200 import sdf_analytic
+    sdf_analytic.USE_TC = request.param
+    yield request.param
+    sdf_analytic.USE_TC = True
+
+
+def test_full_render_matches_reference(setup, use_tc):
     g, surf, scene, volumes, masks = setup
     ro, rd = torch.from_numpy(g["rays_o"]).to(DEV), torch.from_numpy(g["rays_d"]).to(DEV)
     torch.manual_seed(123)
@@ -140,23 +166,17 @@ def test_full_render_matches_reference(setup):
     assert np.array_equal(res["valid_mask"].cpu().numpy(), g["render/valid_mask"])
     assert np.array_equal(res["inside_sphere"].cpu().numpy(), g["render/inside_sphere"])
     assert np.array_equal(res["mid_inside_sphere"].cpu().numpy(), g["render/mid_inside_sphere"])
-    loose = {"smooth_error": 1e-3}
-    jumpy = JUMPY
     skip = {"valid_mask", "inside_sphere", "mid_inside_sphere", "sparse_sdf"}
-    problems = []
-    for k in ref_keys:
-        if k in skip:
-            continue
-        problems.append(_mismatch(k, res[k], g["render/" + k], rtol=loose.get(k, 1e-4), atol_scale=1e-5,
-                                  outlier_frac=jumpy.get(k, 0.0)))
+    problems = [_mismatch(k, res[k], g["render/" + k], **_render_tolerances(k, use_tc)) for k in ref_keys
+                if k not in skip]
     problems = [p for p in problems if p]
     assert not problems, "\n".join(problems)
     # sparse_sdf = [1024 SDF values at torch.rand points (device RNG stream differs from the CPU run), samples]
     _check("sparse_sdf[1024:]", res["sparse_sdf"][1024:], g["render/sparse_sdf"][1024:], atol_scale=1e-5)
 
 
-def test_full_render_nograd_analytic_path_matches_reference(setup):
-    """Same golden comparison for the inference path (torch.no_grad -> analytic SDF sweep)."""
+def test_full_render_nograd_analytic_path_matches_reference(setup, use_tc):
+    """Same golden comparison for the inference path (torch.no_grad -> analytic SDF sweep, K5 / K7 kernels)."""
     g, surf, scene, volumes, masks = setup
     ro, rd = torch.from_numpy(g["rays_o"]).to(DEV), torch.from_numpy(g["rays_d"]).to(DEV)
     torch.manual_seed(123)
@@ -178,12 +198,9 @@ def test_full_render_nograd_analytic_path_matches_reference(setup):
     _check("z_vals after up-sampling", captured["z"], g["z_vals"], atol_scale=2e-6, outlier_frac=2e-3)
     assert np.array_equal(res["valid_mask"].cpu().numpy(), g["render/valid_mask"])
     assert np.array_equal(res["mid_inside_sphere"].cpu().numpy(), g["render/mid_inside_sphere"])
-    problems = []
-    for k in sorted(k[7:] for k in g.files if k.startswith("render/")):
-        if k in {"valid_mask", "inside_sphere", "mid_inside_sphere", "sparse_sdf"}:
-            continue
-        problems.append(_mismatch(k, res[k], g["render/" + k], rtol=1e-3 if k == "smooth_error" else 1e-4,
-                                  atol_scale=1e-5, outlier_frac=JUMPY.get(k, 0.0)))
+    keys = [k[7:] for k in g.files if k.startswith("render/")]
+    problems = [_mismatch(k, res[k], g["render/" + k], **_render_tolerances(k, use_tc)) for k in sorted(keys)
+                if k not in {"valid_mask", "inside_sphere", "mid_inside_sphere", "sparse_sdf"}]
     problems = [p for p in problems if p]
     assert not problems, "\n".join(problems)
 

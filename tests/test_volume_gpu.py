@@ -178,3 +178,41 @@ def test_public_api_backward_all_scales(cuda_lib):
     for g, rg in zip(grads, rgrads):
         scale = rg.abs().max().item()
         assert torch.all((g - rg).abs() <= 1e-5 * scale + 1e-4 * rg.abs())
+
+
+def test_pose_inverse_is_bit_identical_to_torch(cuda_lib):
+    """gens_invert_poses (also folded into the pack launch of every build) must return the very bits of the
+    reference's torch.inverse(c2ws) on this GPU: the matrices decide voxel validity at frustum borders."""
+    from gens_b200 import _lib
+    from gens_b200.volume import pack_feature_pyramid
+    g = torch.Generator().manual_seed(17)
+    n = 50000
+    q, r = torch.linalg.qr(torch.randn(n, 3, 3, generator=g, dtype=torch.float64))
+    q = q * torch.sign(torch.diagonal(r, dim1=1, dim2=2))[:, None, :]
+    c2w = torch.zeros(n, 4, 4, dtype=torch.float64)
+    c2w[:, :3, :3] = q
+    c2w[:, :3, 3] = torch.randn(n, 3, generator=g, dtype=torch.float64) * 3
+    c2w[:, 3, 3] = 1
+    # a quarter of them: near-identity rotations (DTU-like rigs), where pivoting never permutes
+    small = torch.randn(n // 4, 3, generator=g, dtype=torch.float64) * 0.2
+    skew = torch.zeros(n // 4, 3, 3, dtype=torch.float64)
+    skew[:, 0, 1], skew[:, 0, 2], skew[:, 1, 2] = -small[:, 2], small[:, 1], -small[:, 0]
+    skew = skew - skew.transpose(1, 2)
+    c2w[: n // 4, :3, :3] = torch.linalg.matrix_exp(skew)
+    scenes = torch.cat([make_scene(480, 640, nv, seed=s, with_images=False).c2ws for nv in (3, 5) for s in (0, 1, 2)])
+    c2w = torch.cat([scenes, c2w.float()]).to(DEV)
+    ref = torch.inverse(c2w)
+    got = _lib.invert_poses(c2w)
+    assert torch.equal(got, ref), f"{int((got != ref).any(-1).any(-1).sum())} of {c2w.shape[0]} matrices differ"
+    assert torch.equal(_lib.invert_poses(c2w[:5]), torch.linalg.inv_ex(c2w[:5])[0])
+    # the copy folded into the pack launch
+    feats = [torch.randn(3, 4, 12, 16, device=DEV)]
+    _, inv = pack_feature_pyramid(feats, c2w[:3])
+    assert torch.equal(inv, ref[:3])
+    assert _lib.invert_poses(c2w[:0]).shape == (0, 4, 4)
+    with pytest.raises(RuntimeError):
+        _lib.invert_poses(c2w.cpu())
+    # informative only: general (non-rigid) matrices
+    rnd = torch.randn(20000, 4, 4, generator=g).to(DEV)
+    share = float((_lib.invert_poses(rnd) == torch.inverse(rnd)).all(-1).all(-1).float().mean())
+    print(f"general 4x4 matrices reproduced bit for bit: {share:.4f}")
