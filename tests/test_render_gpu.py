@@ -140,9 +140,16 @@ TC_RENDER = {"weights": dict(atol_scale=2e-3), "weight_sum": dict(atol_scale=2e-
              "s_val": dict(atol_scale=1e-5)}
 
 
+# patches are bilinear samples of WHITE-NOISE feature maps around a surface point whose depth is the cancelling
+# ratio (sa*zb - sb*za) / (sa - sb): 1e-7 differences in the SDF values move the samples by ~1e-4 of a value
+GRAY = dict(rtol=1e-4, atol_scale=1e-4, outlier_frac=2e-3)
+
+
 def _render_tolerances(key, use_tc):
     if use_tc and key in TC_RENDER:
         return dict(rtol=1e-4, **TC_RENDER[key])
+    if key in ("ref_gray_val", "sampled_gray_val"):
+        return GRAY
     return dict(rtol=1e-3 if key == "smooth_error" else 1e-4, atol_scale=1e-5, outlier_frac=JUMPY.get(key, 0.0))
 
 
@@ -248,8 +255,8 @@ def test_k7_composite_kernel_matches_aten_tail(setup):
             assert torch.equal(a[k], b[k]), k
             continue
         # the surface normal / patches hang on the zero-crossing point, whose gradient jumps at voxel faces
-        problems.append(_mismatch(k, a[k], b[k].cpu().numpy(), atol_scale=2e-6,
-                                  outlier_frac=JUMPY.get(k, 0.0) if k in ("ref_gray_val", "sampled_gray_val") else 0.0))
+        tol = GRAY if k in ("ref_gray_val", "sampled_gray_val") else dict(atol_scale=2e-6)
+        problems.append(_mismatch(k, a[k], b[k].cpu().numpy(), **tol))
     problems = [p for p in problems if p]
     assert not problems, "\n".join(problems)
     assert float(a["weight_sum"].max()) > 0.5   # the scene has surfaces: the comparison is not vacuous

@@ -1,11 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
-./gpurun_out/ubench_store > gpurun_out/ubench_store.txt 2>&1
+./tools/_bin/ubench_store > gpurun_out/ubench_store.txt 2>&1
 cat gpurun_out/ubench_store.txt
 timeout 300 ncu --metrics l1tex__data_pipe_lsu_wavefronts.sum,l1tex__data_pipe_lsu_wavefronts_mem_lg.sum,l1tex__t_requests_pipe_lsu_mem_global_op_st.sum,l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_st.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum,sm__cycles_active.avg,gpu__time_duration.sum \
-  --clock-control none --csv --log-file gpurun_out/ubench_store_ncu.csv ./gpurun_out/ubench_store > /dev/null 2>&1
+  --clock-control none --csv --log-file gpurun_out/ubench_store_ncu.csv ./tools/_bin/ubench_store > /dev/null 2>&1
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -15 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --no-cpu > gpurun_out/bench3.json 2> gpurun_out/bench3.err
-cut -c1-1800 gpurun_out/bench3.json
+echo skip bench
+

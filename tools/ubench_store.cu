@@ -1,5 +1,5 @@
 // Micro-benchmark: L1 data-pipe cost of global stores by width / cache operator on sm_100a.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gpurun_out/ubench_store tools/ubench_store.cu
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/_bin/ubench_store tools/ubench_store.cu
 // Every block rewrites its own L2-resident 64 KB window, so the rate is set by the SM's store path, not HBM.
 // Run plain for rates, and under `ncu --metrics l1tex__data_pipe_lsu_wavefronts_mem_lg.sum,...` for wavefronts.
 #include <cstdio>
