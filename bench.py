@@ -31,6 +31,9 @@ sys.path.insert(0, ROOT)
 DIMS = [256, 128, 64, 32, 16]
 HW = (480, 640)
 L2_FLUSH_BYTES = 256 << 20
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE K1 launch at 256^3, nv=3, 480x640 (ncu --set full capture of
+# this round, profiles/r01_k1_256_kernel.txt): 29.6 MB + 546.4 MB
+K1_NCU_DRAM_BYTES = 29607680 + 546436096
 
 
 def measured_peak_gbs():
@@ -420,13 +423,17 @@ def run_ours(args, rank, world, local):
                    "l2": "256 MiB memset between steps, outside the per-step event pairs",
                    "mask_fill": fill, "wall_s_timed_loop": round(wall, 4)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "volume_agg_packed_kernel @ 256^3", "ms": k1_ms,
+                     "traffic": K1_NCU_DRAM_BYTES if (nv == 3 and world == 1) else None,
+                     "traffic_source": "profiles/r01_k1_256_kernel.txt (ncu --set full: dram__bytes_read.sum + "
+                                       "dram__bytes_write.sum of one launch; the tail of the writes is still in L2 "
+                                       "when the kernel ends, hence below the algorithmic bytes)",
+                     "kernel": "volume_agg_packed_kernel @ 256^3", "ms": k1_ms,
                      "algorithmic_bytes": abytes, "peak_source": f"MEASURED_PEAKS.json ({peak_kind}, burst copy)"},
         "cpu_baseline": cpu,
         "e2e": None if e2e_ms is None else {"value": vv / (e2e_ms * 1e-3), "unit": "voxel*views/s",
                                             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                             "ms_per_step": e2e_ms},
-        "gpu_launches": 2 * len(DIMS) * args.steps,  # per step: 5 pack + 5 aggregation kernels
+        "gpu_launches": (1 + len(DIMS)) * args.steps,  # per step: 1 pack+pose-inverse kernel + 5 aggregation kernels
         "clocks": clk,
         "render": render,
     }

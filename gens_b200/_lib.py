@@ -82,6 +82,7 @@ _SIGNATURES = {
     "gens_invert_poses": ([_vp, _i, _vp, _vp], _i),
     "gens_unpack_feature_grads": ([_vp, _vp, _i, _i, _i, _vp], _i),
     "gens_volume_agg_fwd_multi": ([ctypes.POINTER(VolumeScale), _i, _i, _vp, _vp, _i, _i, _vp], _i),
+    "gens_volume_build": ([_vp, _vp, _vp, _vp, ctypes.POINTER(VolumeScale), _i, _i, _vp, _vp, _vp, _i, _i, _vp], _i),
     "gens_volume_agg_fwd": ([_vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _i, _i, _i, _ll, _i, _i, _vp, _vp, _vp], _i),
     "gens_unpack_slabs": ([_vp, _i, _ll, _ll, _i, _vp, _vp, _vp], _i),
     "gens_volume_project_debug": ([_i, _i, _i, _vp, _vp, _f, _vp, _i, _i, _vp, _vp, _vp, _vp], _i),

@@ -757,6 +757,18 @@ extern "C" int gens_volume_agg_fwd_multi(const gens_volume_scale_t* scales, int 
     return 0;
 }
 
+// One host call per build: pack every scale's maps + invert the poses (one launch), then all aggregation
+// launches.  Between the two stages the GPU waits only for this function, not for the caller's interpreter.
+extern "C" int gens_volume_build(const float* const* src_nchw, float* const* dst_pairs, const int* h, const int* w,
+                                 const gens_volume_scale_t* scales, int n_scales, int nv, const float* c2ws,
+                                 float* w2c_out, const float* intrs, int min_vis_view, int div_mode, void* stream) {
+    GENS_CHECK_ARG(scales && n_scales > 0 && c2ws && w2c_out && intrs && nv > 0);
+    if (nv > GENS_MAX_VIEWS) return GENS_E_UNSUPPORTED;
+    for (int i = 0; i < n_scales; ++i) GENS_CHECK_ARG(dst_pairs && scales[i].feat_padded == dst_pairs[i]);
+    if (int rc = gens_pack_feature_maps_multi(src_nchw, dst_pairs, h, w, n_scales, nv, c2ws, w2c_out, nv, stream)) return rc;
+    return gens_volume_agg_fwd_multi(scales, n_scales, nv, w2c_out, intrs, min_vis_view, div_mode, stream);
+}
+
 extern "C" int gens_volume_agg_fwd(const float* feat_padded, int nv, int H, int W, const float* w2c,
                                    const float* intrs, float k_row_scale, const float* grid, int D, int a0, int a1,
                                    int a_base, long long channel_stride, int min_vis_view, int div_mode,

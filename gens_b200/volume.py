@@ -79,42 +79,74 @@ def stage_cameras(intrs: torch.Tensor, c2ws: torch.Tensor, scale: int):
     return _lib.f32c(torch.inverse(c2ws)), _lib.f32c(k)
 
 
+def _check_maps(features) -> List[torch.Tensor]:
+    feats = []
+    for f in features:
+        _lib.require_cuda(f)
+        f = _lib.f32c(f)
+        if f.dim() != 4 or f.shape[1] != 4:
+            raise RuntimeError("gens_b200 volume kernels are built for 4-channel (n,4,h,w) feature maps, got "
+                               f"{tuple(f.shape)}")
+        feats.append(f)
+    return feats
+
+
+def _build(c2ws, intrs, dims, slabs, min_vis_view, div_mode, outs, features):
+    """Every allocation first, then ONE C call (gens_volume_build): pack + pose inverse launch, then the
+    aggregation launches, with no interpreter time between them.  Returns (vols, masks, packed, w2c)."""
+    feats = _check_maps(features)
+    dev = feats[0].device
+    nv = feats[0].shape[0]
+    n = len(dims)
+    if c2ws.dim() != 3 or c2ws.shape[1:] != (4, 4) or c2ws.shape[0] != nv:
+        raise RuntimeError(f"camera poses must be ({nv},4,4), got {tuple(c2ws.shape)}")
+    # one scratch allocation: w2c, then the pixel-pair maps of every scale
+    sizes = [nv * (f.shape[2] + 1) * f.shape[3] * 8 for f in feats]
+    scratch = torch.empty(16 * nv + sum(sizes), device=dev, dtype=torch.float32)
+    w2c = scratch[: 16 * nv].view(nv, 4, 4)
+    packed, off = [], 16 * nv
+    for f, sz in zip(feats, sizes):
+        packed.append(scratch[off: off + sz].view(nv, f.shape[2] + 1, f.shape[3], 8))
+        off += sz
+    scales = (_lib.VolumeScale * n)()
+    vols, masks, keep = [], [], []
+    for i, d in enumerate(dims):
+        a0, a1 = slabs[i]
+        planes = a1 - a0
+        if outs is None:
+            # the 8 feature channels and the mask of a scale share one allocation (both views are contiguous)
+            both = torch.empty((1, 9, planes, d, d), device=dev, dtype=torch.float32)
+            vol, msk = both[:, :8], both[:, 8:]
+        else:  # caller-provided slab buffers (views into the all-gather send buffer)
+            vol, msk = outs[i]
+        grid = voxel_axis(d, dev)
+        sc = scales[i]
+        sc.feat_padded = packed[i].data_ptr()
+        sc.H, sc.W, sc.D = feats[i].shape[2], feats[i].shape[3], d
+        sc.a0, sc.a1, sc.a_base = a0, a1, a0
+        sc.channel_stride = planes * d * d
+        sc.k_row_scale = 0.5 ** i
+        sc.grid, sc.volume, sc.mask_volume = grid.data_ptr(), vol.data_ptr(), msk.data_ptr()
+        vols.append(vol)
+        masks.append(msk)
+        keep.append(grid)
+    src = (ctypes.c_void_p * n)(*[f.data_ptr() for f in feats])
+    dst = (ctypes.c_void_p * n)(*[p.data_ptr() for p in packed])
+    hs = (ctypes.c_int * n)(*[f.shape[2] for f in feats])
+    ws = (ctypes.c_int * n)(*[f.shape[3] for f in feats])
+    _lib.check(_lib.lib().gens_volume_build(src, dst, hs, ws, scales, n, nv, _lib.ptr(c2ws), _lib.ptr(w2c),
+                                            _lib.ptr(intrs), int(min_vis_view), int(div_mode), _lib.stream_ptr(dev)),
+               "gens_volume_build")
+    return vols, masks, packed, w2c
+
+
 class _AggMeanVar(torch.autograd.Function):
     """All scales of one build.  Differentiable w.r.t. the feature maps only (the voxel grid is under
     no_grad in the reference, volume.py:27-44)."""
 
     @staticmethod
     def forward(ctx, c2ws, intrs, dims, slabs, min_vis_view, div_mode, outs, *features):
-        dev = features[0].device
-        # one launch: channels-last pixel pairs of every scale + w2c = inverse(c2ws) (the reference's
-        # torch.inverse, volume.py:34, reproduced bit for bit without its 11 library launches / host sync)
-        packed, w2c = pack_feature_pyramid(features, c2ws)
-        nv = features[0].shape[0]
-        n = len(dims)
-        scales = (_lib.VolumeScale * n)()
-        vols, masks, grids = [], [], []
-        for i, d in enumerate(dims):
-            a0, a1 = slabs[i]
-            planes = a1 - a0
-            if outs is None:
-                vol = torch.empty((1, 8, planes, d, d), device=dev, dtype=torch.float32)
-                msk = torch.empty((1, 1, planes, d, d), device=dev, dtype=torch.float32)
-            else:  # caller-provided slab buffers (views into the all-gather send buffer)
-                vol, msk = outs[i]
-            grid = voxel_axis(d, dev)
-            sc = scales[i]
-            sc.feat_padded = packed[i].data_ptr()
-            sc.H, sc.W, sc.D = features[i].shape[2], features[i].shape[3], d
-            sc.a0, sc.a1, sc.a_base = a0, a1, a0
-            sc.channel_stride = planes * d * d
-            sc.k_row_scale = 0.5 ** i
-            sc.grid, sc.volume, sc.mask_volume = grid.data_ptr(), vol.data_ptr(), msk.data_ptr()
-            vols.append(vol)
-            masks.append(msk)
-            grids.append(grid)
-        _lib.check(_lib.lib().gens_volume_agg_fwd_multi(scales, n, nv, _lib.ptr(w2c), _lib.ptr(intrs),
-                                                        int(min_vis_view), int(div_mode), _lib.stream_ptr(dev)),
-                   "gens_volume_agg_fwd_multi")
+        vols, masks, packed, w2c = _build(c2ws, intrs, dims, slabs, min_vis_view, div_mode, outs, features)
         ctx.save_for_backward(w2c, intrs, *packed)
         ctx.meta = (list(dims), list(slabs), div_mode, [tuple(f.shape) for f in features])
         ctx.mark_non_differentiable(*masks)
@@ -157,6 +189,10 @@ def agg_mean_var(features, intrs, c2ws, dims, min_vis_view: int = 1,
     _lib.require_cuda(intrs, c2ws, *features[:len(dims)])
     k = _lib.f32c(intrs)
     slabs = [(0, d) for d in dims] if slabs is None else list(slabs)
+    feats = features[:len(dims)]
+    if not (torch.is_grad_enabled() and any(f.requires_grad for f in feats)):
+        vols, masks, _, _ = _build(_lib.f32c(c2ws), k, tuple(dims), tuple(slabs), min_vis_view, div_mode, outs, feats)
+        return vols, masks
     out = _AggMeanVar.apply(_lib.f32c(c2ws), k, tuple(dims), tuple(slabs), min_vis_view, div_mode, outs,
                             *features[:len(dims)])
     n = len(dims)

@@ -77,6 +77,12 @@ typedef struct gens_volume_scale {
 int gens_volume_agg_fwd_multi(const gens_volume_scale_t *scales, int n_scales, int nv,
                               const float *w2c, const float *intrs, int min_vis_view,
                               int div_mode, void *stream);
+/* The whole build in ONE host call: gens_pack_feature_maps_multi (src_nchw[i] (nv,4,h[i],w[i]) -> dst_pairs[i],
+ * which scales[i].feat_padded must point at; c2ws (nv,4,4) -> w2c_out, bit-identical to torch.inverse) followed
+ * by gens_volume_agg_fwd_multi.  This is Volume.agg_mean_var (reference volume.py:13-63) end to end. */
+int gens_volume_build(const float *const *src_nchw, float *const *dst_pairs, const int *h, const int *w,
+                      const gens_volume_scale_t *scales, int n_scales, int nv, const float *c2ws,
+                      float *w2c_out, const float *intrs, int min_vis_view, int div_mode, void *stream);
 /* Single-scale convenience form of the same. */
 int gens_volume_agg_fwd(const float *feat_padded, int nv, int H, int W, const float *w2c,
                         const float *intrs, float k_row_scale, const float *grid, int D, int a0,
