@@ -1,0 +1,260 @@
+// K10: the colour-blending network over the source views as ONE kernel (sm_100a).
+//
+// Replaces, for inference, BlendingNetwork.forward (reference models/modules/blending_network.py:69-117): eleven
+// small Linear layers on (n * n_src) rows plus ~40 element-wise / concat / reduction launches, all of whose
+// activations travel through HBM (27 % of a 16 k-ray render chunk, profiles/r01_launches_bench.txt).  Here one
+// thread owns one sample point, walks its source views, and keeps every activation in registers; the 11 k
+// weights sit in shared memory in the order the loops read them, so that every weight fetch is a broadcast
+// LDS.128 feeding four FFMAs:
+//   * "A" layers (inputs in registers) produce their outputs four at a time in a rolled loop,
+//   * the following "B" layer accumulates those four activations into its statically indexed outputs,
+// which keeps the code a few thousand instructions instead of the 19 k a full unroll would need.
+// The view-independent half of base_fc's first layer ([mean, var] -> 64) is evaluated once per point and
+// parked in a per-thread shared-memory column.
+// Bound: fp32 FMA issue (18.6 kMAC per point at n_src = 2); HBM traffic is 232 B read + 12 B written per point.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kC = 23;           // 3 rgb + 20 feature channels per view
+constexpr int kThreads = 192;
+constexpr int kMaxSrc = 8;
+
+// packed-weight offsets, in floats (gens_b200/networks.py:pack_blending builds exactly this image)
+constexpr int oW1 = 0;                    // ray_dir_fc.0   A  [4 blocks][4 in] float4
+constexpr int oB1 = oW1 + 4 * 4 * 4;      //                   [16]
+constexpr int oW2 = oB1 + 16;             // ray_dir_fc.2   B  [4 blocks][23 out] float4
+constexpr int oB2 = oW2 + 4 * kC * 4;     //                   [23] (+1 pad)
+constexpr int oW3s = oB2 + 24;            // base_fc.0 (mean,var part)  A [16][46] float4
+constexpr int oB3 = oW3s + 16 * 46 * 4;   //                   [64]
+constexpr int oW3f = oB3 + 64;            // base_fc.0 (per-view part)  A [16][23] float4
+constexpr int oW4 = oW3f + 16 * kC * 4;   // base_fc.2      B  [16][32] float4
+constexpr int oB4 = oW4 + 16 * 32 * 4;    //                   [32]
+constexpr int oW5 = oB4 + 32;             // vis_fc.0       A  [8][32] float4
+constexpr int oB5 = oW5 + 8 * 32 * 4;     //                   [32]
+constexpr int oW6 = oB5 + 32;             // vis_fc.2       B  [8][33] float4
+constexpr int oB6 = oW6 + 8 * 33 * 4;     //                   [33] (+3 pad)
+constexpr int oW7 = oB6 + 36;             // vis_fc2.0      A  [8][32] float4
+constexpr int oB7 = oW7 + 8 * 32 * 4;     //                   [32]
+constexpr int oW8 = oB7 + 32;             // vis_fc2.2      B  [8][1] float4
+constexpr int oB8 = oW8 + 8 * 4;          //                   [1] (+3 pad)
+constexpr int oW9 = oB8 + 4;              // rgb_fc.0       A  [4][37] float4
+constexpr int oB9 = oW9 + 4 * 37 * 4;     //                   [16]
+constexpr int oW10 = oB9 + 16;            // rgb_fc.2       B  [4][8] float4
+constexpr int oB10 = oW10 + 4 * 8 * 4;    //                   [8]
+constexpr int oW11 = oB10 + 8;            // rgb_fc.4          [8]
+constexpr int oB11 = oW11 + 8;            //                   [1] ; then |s| of the anti-alias pooling, 2 pad
+constexpr int oS = oB11 + 1;
+constexpr int kWeightFloats = oS + 3;
+static_assert(kWeightFloats % 4 == 0, "weight image must be float4 granular");
+
+__device__ __forceinline__ float elu(float x) { return x > 0.f ? x : expf(x) - 1.0f; }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// four outputs (block ob) of an A layer whose IN inputs are in registers; w = [blocks][IN] float4
+template <int IN>
+__device__ __forceinline__ float4 a_block(const float4* __restrict__ w, int ob, const float (&x)[IN], float4 acc) {
+    const float4* p = w + ob * IN;
+#pragma unroll
+    for (int i = 0; i < IN; ++i) {
+        const float4 ww = p[i];
+        acc.x = fmaf(ww.x, x[i], acc.x);
+        acc.y = fmaf(ww.y, x[i], acc.y);
+        acc.z = fmaf(ww.z, x[i], acc.z);
+        acc.w = fmaf(ww.w, x[i], acc.w);
+    }
+    return acc;
+}
+// accumulate the four activations of block ob into the OUT outputs of a B layer; w = [blocks][OUT] float4
+template <int OUT>
+__device__ __forceinline__ void b_accum(const float4* __restrict__ w, int ob, float4 a, float (&acc)[OUT]) {
+    const float4* p = w + ob * OUT;
+#pragma unroll
+    for (int j = 0; j < OUT; ++j) {
+        const float4 ww = p[j];
+        acc[j] = fmaf(ww.x, a.x, fmaf(ww.y, a.y, fmaf(ww.z, a.z, fmaf(ww.w, a.w, acc[j]))));
+    }
+}
+__device__ __forceinline__ float4 elu4(float4 a) { return make_float4(elu(a.x), elu(a.y), elu(a.z), elu(a.w)); }
+__device__ __forceinline__ float4 ld4(const float* p, int i) { return reinterpret_cast<const float4*>(p)[i]; }
+
+// feat = rgb_feat + ray_dir_fc(ray_diff)   (blending_network.py:77-78)
+__device__ __forceinline__ void view_features(const float* __restrict__ W, const float* __restrict__ rf,
+                                              const float (&rd)[4], float (&feat)[kC]) {
+    float acc[kC];
+#pragma unroll
+    for (int j = 0; j < kC; ++j) acc[j] = W[oB2 + j];
+#pragma unroll 1
+    for (int ob = 0; ob < 4; ++ob) {
+        const float4 a = elu4(a_block<4>(reinterpret_cast<const float4*>(W + oW1), ob, rd, ld4(W + oB1, ob)));
+        b_accum<kC>(reinterpret_cast<const float4*>(W + oW2), ob, a, acc);
+    }
+#pragma unroll
+    for (int j = 0; j < kC; ++j) feat[j] = rf[j] + elu(acc[j]);
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+blend_kernel(const float* __restrict__ rgb_feat, const float* __restrict__ ray_diff, const uint8_t* __restrict__ mask,
+             long long n, int ns, const float* __restrict__ weights, float* __restrict__ rgb_out) {
+    extern __shared__ __align__(16) float smem[];
+    float* W = smem;                          // kWeightFloats
+    float* pre3 = smem + kWeightFloats;       // [64][kThreads]: view-independent half of base_fc.0, per thread
+    for (int i = threadIdx.x; i < kWeightFloats / 4; i += kThreads)
+        reinterpret_cast<float4*>(W)[i] = __ldg(reinterpret_cast<const float4*>(weights) + i);
+    __syncthreads();
+    const long long pt = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (pt >= n) return;
+    const float* rf0 = rgb_feat + pt * ns * kC;
+    const float* rd0 = ray_diff + pt * ns * 4;
+    const uint8_t* m0 = mask + pt * ns;
+
+    // anti-alias pooling weights over the views (:79-83)
+    const float s_abs = W[oS];
+    float wv[kMaxSrc];
+    {
+        float emin = 3.4e38f;
+        for (int v = 0; v < ns; ++v) {
+            wv[v] = expf(s_abs * (rd0[4 * v + 3] - 1.0f));
+            emin = fminf(emin, wv[v]);
+        }
+        float sum = 0.f;
+        for (int v = 0; v < ns; ++v) {
+            wv[v] = (wv[v] - emin) * (m0[v] ? 1.0f : 0.0f);
+            sum += wv[v];
+        }
+        for (int v = 0; v < ns; ++v) wv[v] = wv[v] / (sum + 1e-8f);
+    }
+
+    // weighted mean and variance of the per-view features (:88-89), two passes as the reference
+    float mv[2 * kC];
+#pragma unroll
+    for (int j = 0; j < 2 * kC; ++j) mv[j] = 0.f;
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll 1
+        for (int v = 0; v < ns; ++v) {
+            const float rd[4] = {rd0[4 * v], rd0[4 * v + 1], rd0[4 * v + 2], rd0[4 * v + 3]};
+            float feat[kC];
+            view_features(W, rf0 + v * kC, rd, feat);
+            const float w = wv[v];
+            if (pass == 0) {
+#pragma unroll
+                for (int j = 0; j < kC; ++j) mv[j] = fmaf(feat[j], w, mv[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < kC; ++j) {
+                    const float d = feat[j] - mv[j];
+                    mv[kC + j] = fmaf(w, d * d, mv[kC + j]);
+                }
+            }
+        }
+    }
+    // view-independent half of base_fc.0: b3 + W3[:, :46] . [mean, var]  -> shared-memory column of this thread
+#pragma unroll 1
+    for (int ob = 0; ob < 16; ++ob) {
+        const float4 a = a_block<2 * kC>(reinterpret_cast<const float4*>(W + oW3s), ob, mv, ld4(W + oB3, ob));
+        pre3[(4 * ob + 0) * kThreads + threadIdx.x] = a.x;
+        pre3[(4 * ob + 1) * kThreads + threadIdx.x] = a.y;
+        pre3[(4 * ob + 2) * kThreads + threadIdx.x] = a.z;
+        pre3[(4 * ob + 3) * kThreads + threadIdx.x] = a.w;
+    }
+
+    float logit[kMaxSrc];
+#pragma unroll 1
+    for (int v = 0; v < ns; ++v) {
+        const float rd[4] = {rd0[4 * v], rd0[4 * v + 1], rd0[4 * v + 2], rd0[4 * v + 3]};
+        const float m = m0[v] ? 1.0f : 0.0f;
+        float x[32];
+        {   // base_fc: 69 -> 64 -> 32 (:91)
+            float feat[kC];
+            view_features(W, rf0 + v * kC, rd, feat);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = W[oB4 + j];
+#pragma unroll 1
+            for (int ob = 0; ob < 16; ++ob) {
+                const float4 init = make_float4(pre3[(4 * ob + 0) * kThreads + threadIdx.x], pre3[(4 * ob + 1) * kThreads + threadIdx.x],
+                                                pre3[(4 * ob + 2) * kThreads + threadIdx.x], pre3[(4 * ob + 3) * kThreads + threadIdx.x]);
+                const float4 a = elu4(a_block<kC>(reinterpret_cast<const float4*>(W + oW3f), ob, feat, init));
+                b_accum<32>(reinterpret_cast<const float4*>(W + oW4), ob, a, x);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = elu(x[j]);
+        }
+        float vis;
+        {   // vis_fc on x * weight: 32 -> 32 -> 33; residual + visibility (:92-95)
+            float xin[32], y[33];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) xin[j] = x[j] * wv[v];
+#pragma unroll
+            for (int j = 0; j < 33; ++j) y[j] = W[oB6 + j];
+#pragma unroll 1
+            for (int ob = 0; ob < 8; ++ob) {
+                const float4 a = elu4(a_block<32>(reinterpret_cast<const float4*>(W + oW5), ob, xin, ld4(W + oB5, ob)));
+                b_accum<33>(reinterpret_cast<const float4*>(W + oW6), ob, a, y);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] += elu(y[j]);
+            vis = sigmoidf_(elu(y[32])) * m;
+        }
+        {   // vis_fc2 on x * vis: 32 -> 32 -> 1, sigmoid (:96)
+            float xin[32], y[1] = {W[oB8]};
+#pragma unroll
+            for (int j = 0; j < 32; ++j) xin[j] = x[j] * vis;
+#pragma unroll 1
+            for (int ob = 0; ob < 8; ++ob) {
+                const float4 a = elu4(a_block<32>(reinterpret_cast<const float4*>(W + oW7), ob, xin, ld4(W + oB7, ob)));
+                b_accum<1>(reinterpret_cast<const float4*>(W + oW8), ob, a, y);
+            }
+            vis = sigmoidf_(y[0]) * m;
+        }
+        {   // rgb_fc on [x, vis, ray_diff]: 37 -> 16 -> 8 -> 1 (:99-100)
+            float xin[37], y[8];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) xin[j] = x[j];
+            xin[32] = vis;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xin[33 + j] = rd[j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = W[oB10 + j];
+#pragma unroll 1
+            for (int ob = 0; ob < 4; ++ob) {
+                const float4 a = elu4(a_block<37>(reinterpret_cast<const float4*>(W + oW9), ob, xin, ld4(W + oB9, ob)));
+                b_accum<8>(reinterpret_cast<const float4*>(W + oW10), ob, a, y);
+            }
+            float l = W[oB11];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) l = fmaf(W[oW11 + j], elu(y[j]), l);
+            logit[v] = m != 0.f ? l : -1e9f;
+        }
+    }
+    // softmax over the views, blend the sampled colours (:101-103)
+    float lmax = -3.4e38f;
+    for (int v = 0; v < ns; ++v) lmax = fmaxf(lmax, logit[v]);
+    float den = 0.f, r = 0.f, g = 0.f, b = 0.f;
+    for (int v = 0; v < ns; ++v) {
+        const float e = expf(logit[v] - lmax);
+        den += e;
+        r = fmaf(rf0[v * kC], e, r);
+        g = fmaf(rf0[v * kC + 1], e, g);
+        b = fmaf(rf0[v * kC + 2], e, b);
+    }
+    rgb_out[3 * pt] = r / den;
+    rgb_out[3 * pt + 1] = g / den;
+    rgb_out[3 * pt + 2] = b / den;
+}
+
+}  // namespace
+
+extern "C" int gens_blend_weight_floats(void) { return kWeightFloats; }
+
+extern "C" int gens_blend_colour(const float* rgb_feat, const float* ray_diff, const uint8_t* mask, long long n,
+                                 int n_src, const float* weights, float* rgb_out, void* stream) {
+    if (n == 0) return 0;
+    GENS_CHECK_ARG(rgb_feat && ray_diff && mask && weights && rgb_out && n > 0 && n_src > 0);
+    if (n_src > kMaxSrc) return GENS_E_UNSUPPORTED;
+    const int smem = (kWeightFloats + 64 * kThreads) * (int)sizeof(float);
+    const cudaError_t e = cudaFuncSetAttribute(blend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    blend_kernel<<<ceil_div_i(n, kThreads), kThreads, smem, (cudaStream_t)stream>>>(rgb_feat, ray_diff, mask, n, n_src,
+                                                                                   weights, rgb_out);
+    return gens_launch_status();
+}

@@ -73,6 +73,7 @@ class ImplicitSurface(nn.Module):
         self.deviation_network = SingleVarianceNetwork(**confs["variance_network"])
         self.val_chunk = 256  # rays per render() call in validate(); 256 = the reference's split
         self.analytic_nograd = True  # under torch.no_grad(): hand-differentiated SDF sweep instead of autograd
+        self.fused_blend = True      # K10 colour-blending network as one kernel (no-grad render_core tail)
         self.fused_composite = True  # K7 warp-per-ray compositing kernel for the no-grad render_core tail
         self.fused_upsample = True   # K5 warp-per-ray kernels for up_sample / cat_z_vals (CUDA tensors)
 
@@ -180,7 +181,10 @@ class ImplicitSurface(nn.Module):
         b, n = z_vals.shape
         feat_views, ray_diff, mask_views = self.ops.lookup_feature(pts, imgs, intrs, c2ws, features)
         mask_views = mask_views & evaluated[:, None]
-        colour = self.color_network(feat_views, ray_diff, mask_views)
+        if self.fused_blend:
+            colour = self.color_network.blend_nograd(feat_views, ray_diff, mask_views)  # K10, one launch
+        else:
+            colour = self.color_network(feat_views, ray_diff, mask_views)
         inv_s_raw = self.deviation_network(torch.zeros([1, 3]).type_as(rays_o))[:, :1]
         c = self.ops.composite_rays(rays_o, rays_d, z_vals, pts, sdf_val, grad_all, smooth_all, colour, voxel_mask,
                                     evaluated, mask_views, inv_s_raw, _inverse(c2ws[0, :3, :3]), cos_anneal_ratio,

@@ -202,6 +202,66 @@ class BlendingNetwork(nn.Module):
         for net in (self.base_fc, self.vis_fc2, self.vis_fc, self.rgb_fc):
             net.apply(_kaiming)
 
+    # -- inference path: the whole network as one kernel (K10, csrc/blend.cu) -----------------------------
+    def packed_weights(self) -> torch.Tensor:
+        """The eleven Linear layers re-ordered into the shared-memory image of blend_kernel: "A" layers as
+        [out/4][in][4], the "B" layer that follows as [in/4][out][4], biases padded to float4 (offsets: the
+        constexpr table at the top of csrc/blend.cu).  Cached per parameter versions."""
+        params = list(self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if getattr(self, "_packed_key", None) == key:
+            return self._packed
+        dev = params[0].device
+
+        def a_layout(w):                      # (out, in) -> [out/4][in][4]
+            out, inp = w.shape
+            return w.reshape(out // 4, 4, inp).permute(0, 2, 1).reshape(-1)
+
+        def b_layout(w):                      # (out, in) -> [in/4][out][4]
+            out, inp = w.shape
+            return w.reshape(out, inp // 4, 4).permute(1, 0, 2).reshape(-1)
+
+        def pad4(v):
+            v = v.reshape(-1)
+            return F.pad(v, (0, (-v.numel()) % 4))
+
+        rd, base, vis, vis2, rgb = self.ray_dir_fc, self.base_fc, self.vis_fc, self.vis_fc2, self.rgb_fc
+        c = rd[2].weight.shape[0]
+        if c != 23 or base[0].weight.shape != (64, 3 * c) or rgb[0].weight.shape != (16, 37) or \
+                not self.anti_alias_pooling:
+            raise RuntimeError("gens_b200 blend kernel is built for d_feature = 20 with anti-alias pooling")
+        with torch.no_grad():
+            w3 = base[0].weight
+            pieces = [a_layout(rd[0].weight), rd[0].bias, b_layout(rd[2].weight), pad4(rd[2].bias),
+                      a_layout(w3[:, : 2 * c]), base[0].bias, a_layout(w3[:, 2 * c:]),
+                      b_layout(base[2].weight), base[2].bias,
+                      a_layout(vis[0].weight), vis[0].bias, b_layout(vis[2].weight), pad4(vis[2].bias),
+                      a_layout(vis2[0].weight), vis2[0].bias, b_layout(vis2[2].weight), pad4(vis2[2].bias),
+                      a_layout(rgb[0].weight), rgb[0].bias, b_layout(rgb[2].weight), rgb[2].bias,
+                      rgb[4].weight.reshape(-1), rgb[4].bias.reshape(-1), torch.abs(self.s).reshape(1),
+                      torch.zeros(2, device=dev)]
+            flat = torch.cat([p.reshape(-1).float() for p in pieces]).contiguous()
+        from . import _lib
+        if flat.numel() != _lib.lib().gens_blend_weight_floats():
+            raise RuntimeError(f"packed blending weights: {flat.numel()} floats, the kernel expects "
+                               f"{_lib.lib().gens_blend_weight_floats()}")
+        self._packed_key, self._packed = key, flat
+        return flat
+
+    @torch.no_grad()
+    def blend_nograd(self, rgb_feat, ray_diff, mask):
+        """forward() without autograd, one launch (CUDA only)."""
+        from . import _lib
+        _lib.require_cuda(rgb_feat, ray_diff, mask)
+        n, ns = mask.shape
+        rf, rdiff = _lib.f32c(rgb_feat), _lib.f32c(ray_diff)
+        m = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8).contiguous()
+        w = self.packed_weights()
+        out = torch.empty((n, 3), device=rf.device, dtype=torch.float32)
+        _lib.check(_lib.lib().gens_blend_colour(_lib.ptr(rf), _lib.ptr(rdiff), _lib.ptr(m), n, ns, _lib.ptr(w),
+                                                _lib.ptr(out), _lib.stream_ptr(rf.device)), "gens_blend_colour")
+        return out
+
     def forward(self, rgb_feat, ray_diff, mask):
         """rgb_feat (n,ns,3+c), ray_diff (n,ns,4), mask (n,ns) -> rgb (n,3)."""
         m = mask[:, :, None]

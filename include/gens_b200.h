@@ -301,6 +301,15 @@ typedef struct gens_composite_args {
 } gens_composite_args_t;
 int gens_composite_rays(const gens_composite_args_t *args, void *stream);
 
+/* ---- K10: colour blending over the source views ---------------------------------------------
+ * BlendingNetwork.forward (reference models/modules/blending_network.py:69-117) for inference as one kernel:
+ * rgb_feat (n,n_src,23) = [sampled rgb, 20 features] and ray_diff (n,n_src,4) as gens_lookup_feature_fwd writes
+ * them, mask (n,n_src) uint8 -> rgb_out (n,3).  weights = the eleven Linear layers + |s| re-ordered into the
+ * shared-memory image the kernel reads (gens_blend_weight_floats() floats; gens_b200/networks.py packs it). */
+int gens_blend_weight_floats(void);
+int gens_blend_colour(const float *rgb_feat, const float *ray_diff, const uint8_t *mask, long long n,
+                      int n_src, const float *weights, float *rgb_out, void *stream);
+
 /* K9: masked total variation of the volume pyramid in one pass -- the reduction behind
  * ImplicitSurface.tv_regularization (reference models/modules/implicit_surface.py:135-150, called from
  * render_core :260).  vols->vol[s] = (channels,D,D,D) NCDHW, masks->vol[s] = (D,D,D) (masks or an entry NULL =

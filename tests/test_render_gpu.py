@@ -260,3 +260,36 @@ def test_k7_composite_kernel_matches_aten_tail(setup):
     problems = [p for p in problems if p]
     assert not problems, "\n".join(problems)
     assert float(a["weight_sum"].max()) > 0.5   # the scene has surfaces: the comparison is not vacuous
+
+
+@pytest.mark.parametrize("ns", [1, 2, 4])
+def test_k10_blend_kernel_matches_module(setup, ns):
+    """K10 (csrc/blend.cu) against BlendingNetwork.forward (the state_dict-compatible mirror the golden render
+    pins) on random inputs, incl. fully masked points; colours are in [0,1]: |a-b| <= 1e-5 + 1e-4 |b|."""
+    g, surf, scene, volumes, masks = setup
+    net = surf.color_network
+    gen = torch.Generator(device=DEV).manual_seed(100 + ns)
+    n = 50_001
+    rgb_feat = torch.randn(n, ns, 23, device=DEV, generator=gen) * 0.5
+    rgb_feat[..., :3] = torch.rand(n, ns, 3, device=DEV, generator=gen)
+    ray_diff = torch.randn(n, ns, 4, device=DEV, generator=gen) * 0.3
+    ray_diff[..., 3] = torch.rand(n, ns, device=DEV, generator=gen) * 2 - 1          # cosine of the ray angle
+    mask = torch.rand(n, ns, device=DEV, generator=gen) > 0.3
+    mask[:100] = False
+    with torch.no_grad():
+        ref = net(rgb_feat, ray_diff, mask)
+        got = net.blend_nograd(rgb_feat, ray_diff, mask)
+    assert got.shape == ref.shape == (n, 3)
+    _check(f"blend ns={ns}", got, ref.cpu().numpy(), atol_scale=1e-5)
+    # weights updated in place (fine-tuning): the packed image follows
+    with torch.no_grad():
+        saved = net.base_fc[0].weight.clone()
+        net.base_fc[0].weight.mul_(1.01)
+        try:
+            _check("blend after update", net.blend_nograd(rgb_feat[:999], ray_diff[:999], mask[:999]),
+                   net(rgb_feat[:999], ray_diff[:999], mask[:999]).cpu().numpy(), atol_scale=1e-5)
+        finally:
+            net.base_fc[0].weight.copy_(saved)   # the fixture is shared: restore the golden weights bit for bit
+    assert net.blend_nograd(rgb_feat[:0], ray_diff[:0], mask[:0]).shape == (0, 3)
+    with pytest.raises(RuntimeError):
+        net.blend_nograd(rgb_feat.cpu(), ray_diff.cpu(), mask.cpu())
