@@ -61,6 +61,9 @@ constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
 // the reverse kernel keeps no encodings in shared memory: the ring starts at 0
 constexpr int kRevOffW = 0;
+// ... and stages the next layer's s1 / t2 there instead: 16 float4 per epilogue thread
+constexpr int kRevOffStage = kWStages * kWSlotBytes;
+static_assert(kRevOffStage + 16 * kEpiThreads * 16 <= kOffBias, "reverse-kernel staging overlaps the bias block");
 
 constexpr uint32_t kColAhi = 0, kColAlo = 128, kColAcc0 = 256, kColAcc1 = 384;
 
@@ -101,6 +104,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -221,6 +234,22 @@ __device__ __forceinline__ void softplus100_d12(float a, float& d1, float& d2) {
     d1 = t > 0.0f ? r : er;
     d2 = 100.0f * er * r;
     if (t > 20.0f) {
+        d1 = 1.0f;
+        d2 = 0.0f;
+    }
+}
+
+// softplus and both derivatives from one exponential: exactly softplus100() and softplus100_d12()
+__device__ __forceinline__ void softplus100_all(float a, float& sp, float& d1, float& d2) {
+    const float t = a * 100.0f;
+    const float e = exp_neg_abs(t);
+    const float r = __frcp_rn(1.0f + e);
+    const float er = e * r;
+    sp = (fmaxf(t, 0.0f) + log1p_unit(e)) * 0.01f;
+    d1 = t > 0.0f ? r : er;
+    d2 = 100.0f * er * r;
+    if (t > 20.0f) {
+        sp = a;
         d1 = 1.0f;
         d2 = 0.0f;
     }
@@ -461,29 +490,45 @@ sdf_mlp_fwd_kernel(const float* __restrict__ pos, const float* __restrict__ fe, 
                             for (int j = 0; j < 16; ++j)
                                 split_tf32(softplus100(__uint_as_float(v[j]) + b[col0 + j]), hi[j], lo[j]);
                         } else {
-                            float d1[16], d2[16];
+                            // Lanes (2i, 2i+1) hold the primal / tangent row of one point.  Instead of every lane
+                            // walking all 16 channels down its own branch (softplus on the primal lane, the two
+                            // derivatives on the tangent lane: both branches serialised in every warp), the pair
+                            // SPLITS the channels: the primal lane takes channels [0,8), the tangent lane [8,16),
+                            // each evaluates softplus, sp' and sp'' (one shared exponential) for its eight
+                            // (point, channel) entries, and one shuffle per entry hands the results back.
+                            const int cb = col0 + (tangent ? 8 : 0);
+                            float a8[8], da8[8];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const float mine = __uint_as_float(v[j]);
-                                const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
-                                const float a = (tangent ? other : mine) + b[col0 + j];  // pre-activation of the point
-                                float out;
-                                if (tangent) {
-                                    softplus100_d12(a, d1[j], d2[j]);
-                                    out = d1[j] * mine;   // dh = sp'(a) da
-                                    d2[j] *= mine;        // sp''(a) da
-                                } else {
-                                    out = softplus100(a);
-                                }
-                                split_tf32(out, hi[j], lo[j]);
+                            for (int k = 0; k < 8; ++k) {
+                                const float v_lo = __uint_as_float(v[k]), v_hi = __uint_as_float(v[8 + k]);
+                                // primal lane sends a[8+k] and receives da[k]; tangent lane sends da[k], receives a[8+k]
+                                const float got = __shfl_xor_sync(0xffffffffu, tangent ? v_lo : v_hi, 1);
+                                a8[k] = (tangent ? got : v_lo) + b[cb + k];
+                                da8[k] = tangent ? v_hi : got;
                             }
-                            if (tangent && live) {
-                                float4* o1 = reinterpret_cast<float4*>(s1_out + ((long long)layer * n + p) * 128 + col0);
-                                float4* o2 = reinterpret_cast<float4*>(t2_out + ((long long)layer * n + p) * 128 + col0);
+                            float o_p[8], o_t[8], s1v[8], t2v[8];
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    __stcs(o1 + q, make_float4(d1[4 * q], d1[4 * q + 1], d1[4 * q + 2], d1[4 * q + 3]));
-                                    __stcs(o2 + q, make_float4(d2[4 * q], d2[4 * q + 1], d2[4 * q + 2], d2[4 * q + 3]));
+                            for (int k = 0; k < 8; ++k) {
+                                float d2;
+                                softplus100_all(a8[k], o_p[k], s1v[k], d2);
+                                o_t[k] = s1v[k] * da8[k];   // dh = sp'(a) da
+                                t2v[k] = d2 * da8[k];       // sp''(a) da
+                            }
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                // primal lane needs h of channels [8,16) (computed by the tangent lane), the tangent
+                                // lane needs dh of channels [0,8) (computed by the primal lane)
+                                const float got = __shfl_xor_sync(0xffffffffu, tangent ? o_p[k] : o_t[k], 1);
+                                split_tf32(tangent ? got : o_p[k], hi[k], lo[k]);
+                                split_tf32(tangent ? o_t[k] : got, hi[8 + k], lo[8 + k]);
+                            }
+                            if (live) {
+                                float4* o1 = reinterpret_cast<float4*>(s1_out + ((long long)layer * n + p) * 128 + cb);
+                                float4* o2 = reinterpret_cast<float4*>(t2_out + ((long long)layer * n + p) * 128 + cb);
+#pragma unroll
+                                for (int q = 0; q < 2; ++q) {
+                                    __stcs(o1 + q, make_float4(s1v[4 * q], s1v[4 * q + 1], s1v[4 * q + 2], s1v[4 * q + 3]));
+                                    __stcs(o2 + q, make_float4(t2v[4 * q], t2v[4 * q + 1], t2v[4 * q + 2], t2v[4 * q + 3]));
                                 }
                             }
                         }
@@ -536,6 +581,26 @@ sdf_mlp_rev_kernel(const float* __restrict__ s1, const float* __restrict__ t2, l
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const bool tangent = row & 1;
         uint32_t acc_phase = 0;
+        // s1 / t2 of the NEXT layer are fetched with cp.async into a thread-private shared-memory column while
+        // the tensor core works on the current one (their DRAM latency used to sit on the layer-to-layer critical
+        // path): slot q = blk * 8 + {0..3: s1 chunks, 4..7: t2 chunks}, [q][thread] float4 -> conflict-free.
+        const uint32_t stage = c.s_base + kRevOffStage + threadIdx.x * 16u;
+        auto prefetch = [&](long long pp, int layer) {
+            if (pp < n) {
+#pragma unroll
+                for (int blk = 0; blk < 2; ++blk) {
+                    const float* g1 = s1 + ((long long)layer * n + pp) * 128 + cq * 32 + blk * 16;
+                    const float* g2 = t2 + ((long long)layer * n + pp) * 128 + cq * 32 + blk * 16;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        cp_async16(stage + (uint32_t)(blk * 8 + q) * (kEpiThreads * 16u), g1 + 4 * q);
+                        if (tangent) cp_async16(stage + (uint32_t)(blk * 8 + 4 + q) * (kEpiThreads * 16u), g2 + 4 * q);
+                    }
+                }
+            }
+            cp_async_commit();
+        };
+        if ((long long)blockIdx.x < n_tiles) prefetch((long long)blockIdx.x * kPts + (row >> 1), n_hidden - 1);
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const long long p = tile * kPts + (row >> 1);
             const bool live = p < n;
@@ -562,14 +627,14 @@ sdf_mlp_rev_kernel(const float* __restrict__ s1, const float* __restrict__ t2, l
                     }
                     float d1[16], d2[16];
                     {
-                        const float4* i1 = reinterpret_cast<const float4*>(s1 + ((long long)layer * n + p) * 128 + col0);
-                        const float4* i2 = reinterpret_cast<const float4*>(t2 + ((long long)layer * n + p) * 128 + col0);
+                        if (blk == 0) cp_async_wait_all();  // this layer's s1 / t2 (issued one layer ago)
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float4 a = live ? __ldcs(i1 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float4 a = live ? lds128(stage + (uint32_t)(blk * 8 + q) * (kEpiThreads * 16u))
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
                             d1[4 * q] = a.x; d1[4 * q + 1] = a.y; d1[4 * q + 2] = a.z; d1[4 * q + 3] = a.w;
                             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (live && tangent) b = __ldcs(i2 + q);
+                            if (live && tangent) b = lds128(stage + (uint32_t)(blk * 8 + 4 + q) * (kEpiThreads * 16u));
                             d2[4 * q] = b.x; d2[4 * q + 1] = b.y; d2[4 * q + 2] = b.z; d2[4 * q + 3] = b.w;
                         }
                     }
@@ -596,6 +661,9 @@ sdf_mlp_rev_kernel(const float* __restrict__ s1, const float* __restrict__ t2, l
                 tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(c.bar_a());
+                // the staged values are in registers / consumed: fetch the next layer's (or the next tile's top layer)
+                if (layer > 0) prefetch(p, layer - 1);
+                else if (tile + gridDim.x < n_tiles) prefetch((tile + gridDim.x) * kPts + (row >> 1), n_hidden - 1);
             }
             // -- results: accumulator 0 = layer 0's position cotangents, accumulator 1 = feature cotangents
             mbar_wait(c.bar_acc(0), acc_phase);
