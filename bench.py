@@ -137,7 +137,8 @@ def algorithmic_bytes_scale(d, nv, h, w):
 
 
 
-RENDER_CHUNK = 16384         # rays per ImplicitSurface.render call (the reference's validate uses 256)
+RENDER_CHUNK = 65536         # rays per ImplicitSurface.render call (the reference's validate uses 256);
+                             # 16384 -> 803 ms, 32768 -> 723 ms, 65536 -> 693 ms per 480x640 image on one B200
 
 
 def smooth_volumes(dims, device, seed=1):
@@ -265,23 +266,27 @@ def bench_render(args, rank, world, dev, sc, host, vol_mod, timed):
            "sharding": "none" if world == 1 else f"contiguous ray ranges over {world} ranks + final gather",
            "gpu_launches_per_step": launches}
 
-    # e2e: rays from pinned host memory per chunk, image outputs back to pinned host memory per chunk
-    if world == 1:
-        pin_o, pin_d = ro_all.cpu().pin_memory(), rd_all.cpu().pin_memory()
-        pin_out = torch.empty((n_total, 8), dtype=torch.float32).pin_memory()
+    # e2e: this rank's rays from pinned host memory per chunk; image outputs gathered, then rank 0 copies them to
+    # pinned host memory
+    pin_o, pin_d = ro.cpu().pin_memory(), rd.cpu().pin_memory()
+    pin_out = torch.empty((n_total, 8), dtype=torch.float32).pin_memory() if rank == 0 else None
 
-        def step_e2e():
-            with torch.no_grad():
-                for a in range(0, n_total, chunk):
-                    o = pin_o[a:a + chunk].to(dev, non_blocking=True)
-                    d = pin_d[a:a + chunk].to(dev, non_blocking=True)
-                    r = surf.render(o, d, sc.near, sc.far, vols, masks, sc.imgs, sc.features, sc.features, sc.intrs,
-                                    sc.c2ws, 1.0, None)
-                    out = torch.cat([r["color_fine"], r["render_depth"][:, None], r["normal"], r["sdf_depth"]], 1)
-                    pin_out[a:a + chunk].copy_(out, non_blocking=True)
-        e_ms, _ = timed(step_e2e, max(1, args.render_steps // 2), 0)
-        res["e2e"] = {"value": samples / (e_ms * 1e-3), "unit": "ray-samples/s", "ms_per_step": e_ms,
-                      "h2d_bytes_per_step": n_total * 6 * 4, "d2h_bytes_per_step": n_total * 8 * 4}
+    def step_e2e():
+        outs = []
+        with torch.no_grad():
+            for a in range(0, hi - lo, chunk):
+                o = pin_o[a:a + chunk].to(dev, non_blocking=True)
+                d = pin_d[a:a + chunk].to(dev, non_blocking=True)
+                r = surf.render(o, d, sc.near, sc.far, vols, masks, sc.imgs, sc.features, sc.features, sc.intrs,
+                                sc.c2ws, 1.0, None)
+                outs.append(torch.cat([r["color_fine"], r["render_depth"][:, None], r["normal"], r["sdf_depth"]], 1))
+        full = parallel.gather_rays(torch.cat(outs), n_total, rank, world)
+        if rank == 0:
+            pin_out.copy_(full, non_blocking=True)
+    e_ms, _ = timed(step_e2e, max(1, args.render_steps // 2), 0)
+    res["e2e"] = {"value": samples / (e_ms * 1e-3), "unit": "ray-samples/s", "ms_per_step": e_ms,
+                  "h2d_bytes_per_step": n_total * 6 * 4, "d2h_bytes_per_step": n_total * 8 * 4}
+    if world == 1:
 
         # roofline view of the gather kernel (K3): logical bytes = 5 scales x 8 corners x 16 B per point
         n_pts = 1 << 22
@@ -317,12 +322,16 @@ def run_ours(args, rank, world, local):
     vol_mod = Volume(volume_dims=DIMS)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
-    # slab sharding across ranks (planes of tensor dim 2); world == 1 -> full build
+    # slab sharding across ranks (planes of tensor dim 2); world == 1 -> full build.  N > 1: K1 stores every result
+    # into all ranks' final tensors over NVLink peer mappings (gens_b200.parallel.fused_sharded_agg_mean_var);
+    # --exchange nccl selects the all-gather + scatter path instead.
+    from gens_b200 import parallel as _par
+    sharded_build = _par.fused_sharded_agg_mean_var if args.exchange == "fused" else _par.sharded_agg_mean_var
+
     def step_device():
         if world == 1:
             return vol_mod.agg_mean_var(sc.features, sc.intrs, sc.c2ws)
-        from gens_b200.parallel import sharded_agg_mean_var
-        return sharded_agg_mean_var(vol_mod, sc.features, sc.intrs, sc.c2ws, rank, world)
+        return sharded_build(vol_mod, sc.features, sc.intrs, sc.c2ws, rank, world)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -367,20 +376,23 @@ def run_ours(args, rank, world, local):
         # ---- e2e: pinned host buffers -> public API -> pinned host result ------------------
         pin_feats = [f.pin_memory() for f in host.features]
         pin_intrs, pin_c2ws = host.intrs.pin_memory(), host.c2ws.pin_memory()
-        pin_out = [torch.empty((1, 9, d, d, d), dtype=torch.float32).pin_memory() for d in DIMS]
+        pin_out = [torch.empty((1, 9, d, d, d), dtype=torch.float32).pin_memory() for d in DIMS] if rank == 0 else []
         h2d = sum(f.numel() for f in pin_feats) * 4 + (pin_intrs.numel() + pin_c2ws.numel()) * 4
-        d2h = sum(o.numel() for o in pin_out) * 4
+        d2h = sum(9 * d ** 3 for d in DIMS) * 4
 
         def step_e2e():
             feats = [f.to(dev, non_blocking=True) for f in pin_feats]
-            vols, masks = vol_mod.agg_mean_var(feats, pin_intrs.to(dev, non_blocking=True),
-                                               pin_c2ws.to(dev, non_blocking=True))
+            intrs_d, c2ws_d = pin_intrs.to(dev, non_blocking=True), pin_c2ws.to(dev, non_blocking=True)
+            if world == 1:
+                vols, masks = vol_mod.agg_mean_var(feats, intrs_d, c2ws_d)
+            else:  # every rank uploads the inputs and builds its slabs; rank 0 reads the assembled volumes back
+                vols, masks = sharded_build(vol_mod, feats, intrs_d, c2ws_d, rank, world)
+                if rank != 0:
+                    return
             for o, v, m in zip(pin_out, vols, masks):
                 o[:, :8].copy_(v, non_blocking=True)
                 o[:, 8:].copy_(m, non_blocking=True)
-        e2e_ms = None
-        if world == 1:
-            e2e_ms, _ = timed(step_e2e, max(3, args.steps // 4), 2)
+        e2e_ms, _ = timed(step_e2e, max(3, args.steps // 4), 2)
         render = None
         if not args.no_render:
             render = bench_render(args, rank, world, dev, sc, host, vol_mod, timed)
@@ -419,7 +431,9 @@ def run_ours(args, rank, world, local):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"config2: {HW[0]}x{HW[1]}, {nv} views, volume dims {DIMS}, full 5-scale build",
-                   "sharding": "none" if world == 1 else f"x-slabs over {world} ranks + all-gather",
+                   "sharding": "none" if world == 1 else (
+                       f"x-slabs over {world} ranks; K1 stores into every rank's tensors over NVLink peer mappings + "
+                       "device barrier" if args.exchange == "fused" else f"x-slabs over {world} ranks + all-gather"),
                    "l2": "256 MiB memset between steps, outside the per-step event pairs",
                    "mask_fill": fill, "wall_s_timed_loop": round(wall, 4)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -451,6 +465,8 @@ def main():
     ap.add_argument("--no-render", action="store_true", help="volume-build metric only")
     ap.add_argument("--render-steps", type=int, default=2, help="full-image renders timed for the render metric")
     ap.add_argument("--render-chunk", type=int, default=RENDER_CHUNK)
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: slab exchange fused into K1's stores (NVLink peer memory) or NCCL all-gather + scatter")
     args = ap.parse_args()
     rank, world, local = dist_setup(args.gpus)
     if args.impl == "reference":

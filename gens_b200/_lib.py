@@ -19,11 +19,15 @@ _lib = None
 
 _vp, _i, _ll, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
 
+MAX_PEERS = 8
+
+
 class VolumeScale(ctypes.Structure):
     """Mirror of gens_volume_scale_t (include/gens_b200.h)."""
     _fields_ = [
         ("feat_padded", _vp), ("H", _i), ("W", _i), ("D", _i), ("a0", _i), ("a1", _i), ("a_base", _i),
         ("channel_stride", _ll), ("k_row_scale", _f), ("grid", _vp), ("volume", _vp), ("mask_volume", _vp),
+        ("n_peers", _i), ("peer_volume", _vp * MAX_PEERS), ("peer_mask", _vp * MAX_PEERS),
     ]
 
 

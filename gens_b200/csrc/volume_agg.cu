@@ -42,6 +42,15 @@ struct Extent {
     float hx, hy, inv_hx, inv_hy;
 };
 
+// Multi-GPU builds: every result is stored into the FINAL tensors of all ranks of the node (own memory and
+// NVLink peer mappings of the same symmetric allocation), so the slab exchange rides on the kernel's own
+// stores instead of an all-gather + scatter afterwards.  n == 0: single destination (volume / mask_volume).
+struct PeerOut {
+    float* vol[GENS_MAX_PEERS];
+    float* msk[GENS_MAX_PEERS];
+    int n;
+};
+
 // Stage the per-view matrices in shared memory.  `k_row_scale` = 0.5^scale multiplies rows 0-1 of
 // the intrinsics exactly as the reference's `intrs_stage[:, :2] *= 0.5**i` (volume.py:25); a
 // power-of-two factor, so the product is exact and bit-identical to the torch op.
@@ -145,7 +154,7 @@ __global__ void __launch_bounds__(256)
 volume_agg_scalar_kernel(const Pair* __restrict__ feat, int nv, int H, int W, const float* __restrict__ w2c,
                          const float* __restrict__ k_stage, float k_row_scale, const float* __restrict__ grid, int D, int a0,
                          long long out_off, long long channel_stride, int min_vis_view, Extent e,
-                         float* __restrict__ volume, float* __restrict__ mask_volume) {
+                         float* __restrict__ volume, float* __restrict__ mask_volume, const __grid_constant__ PeerOut peers) {
     __shared__ Cam s_cam[GENS_MAX_VIEWS];
     load_cams(s_cam, w2c, k_stage, k_row_scale, nv);
     const int c = blockIdx.x * 32 + threadIdx.x, b = blockIdx.y * 8 + threadIdx.y, a = a0 + blockIdx.z;
@@ -170,13 +179,21 @@ volume_agg_scalar_kernel(const Pair* __restrict__ feat, int nv, int H, int W, co
     const float den = cnt <= 0 ? 1e-8f : (float)cnt;
     const float sv[4] = {s.x, s.y, s.z, s.w}, qv[4] = {q.x, q.y, q.z, q.w};
     const long long o = out_off + ((long long)blockIdx.z * D + b) * D + c;
+    float res[9];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const float mean = __fdiv_rn(sv[k], den);
-        __stcs(volume + k * channel_stride + o, mean);
-        __stcs(volume + (4 + k) * channel_stride + o, __fsub_rn(__fdiv_rn(qv[k], den), __fmul_rn(mean, mean)));
+        res[k] = __fdiv_rn(sv[k], den);
+        res[4 + k] = __fsub_rn(__fdiv_rn(qv[k], den), __fmul_rn(res[k], res[k]));
     }
-    __stcs(mask_volume + o, cnt > min_vis_view ? 1.0f : 0.0f);
+    res[8] = cnt > min_vis_view ? 1.0f : 0.0f;
+    const int n_dst = peers.n > 0 ? peers.n : 1;
+    for (int d = 0; d < n_dst; ++d) {
+        float* vol = peers.n > 0 ? peers.vol[d] : volume;
+        float* msk = peers.n > 0 ? peers.msk[d] : mask_volume;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) __stcs(vol + k * channel_stride + o, res[k]);
+        __stcs(msk + o, res[8]);
+    }
 }
 
 template <bool RECIP>
@@ -338,12 +355,12 @@ __device__ __forceinline__ void accumulate_view(const Cam& cam, const Pair* __re
 }
 
 // ROWS: row-groups of 8 rows a block walks through, amortising the camera staging and its barriers.
-template <int PAIRS, bool RECIP, int MIN_BLOCKS, int GATHER, int ROWS>
+template <int PAIRS, bool RECIP, int MIN_BLOCKS, int GATHER, int ROWS, bool PEERS = false>
 __global__ void __launch_bounds__(256, MIN_BLOCKS)
 volume_agg_packed_kernel(const Pair* __restrict__ feat, int nv, int H, int W, const float* __restrict__ w2c,
                          const float* __restrict__ k_stage, float k_row_scale, const float* __restrict__ grid, int D, int a0,
                          long long out_off, long long channel_stride, int min_vis_view, Extent e,
-                         float* __restrict__ volume, float* __restrict__ mask_volume) {
+                         float* __restrict__ volume, float* __restrict__ mask_volume, const __grid_constant__ PeerOut peers) {
     __shared__ Cam s_cam[GENS_MAX_VIEWS];
     __shared__ float s_inv_count[GENS_MAX_VIEWS + 1];  // RN(1/n) for the exact count division
     if (threadIdx.y == 0 && threadIdx.x <= GENS_MAX_VIEWS)
@@ -385,6 +402,23 @@ volume_agg_packed_kernel(const Pair* __restrict__ feat, int nv, int H, int W, co
             const f32x2 m_xy = div_count2(acc[j].s_xy, n, r), m_zw = div_count2(acc[j].s_zw, n, r);
             const f32x2 v_xy = sub2(div_count2(acc[j].q_xy, n, r), mul2_rounded(m_xy, m_xy));
             const f32x2 v_zw = sub2(div_count2(acc[j].q_zw, n, r), mul2_rounded(m_zw, m_zw));
+            if (PEERS) {
+                // one store per channel and destination: the own tensor and every NVLink peer's
+                const float mk = cnt > min_vis_view ? 1.0f : 0.0f;
+                for (int d = 0; d < peers.n; ++d) {
+                    float* o = peers.vol[d] + row + 32 * j;
+                    __stcs(o, lo(m_xy));
+                    __stcs(o + channel_stride, hi(m_xy));
+                    __stcs(o + 2 * channel_stride, lo(m_zw));
+                    __stcs(o + 3 * channel_stride, hi(m_zw));
+                    __stcs(o + 4 * channel_stride, lo(v_xy));
+                    __stcs(o + 5 * channel_stride, hi(v_xy));
+                    __stcs(o + 6 * channel_stride, lo(v_zw));
+                    __stcs(o + 7 * channel_stride, hi(v_zw));
+                    __stcs(peers.msk[d] + row + 32 * j, mk);
+                }
+                continue;
+            }
             float* o = volume + row + 32 * j;
             __stcs(o, lo(m_xy));
             __stcs(o + channel_stride, hi(m_xy));
@@ -655,7 +689,10 @@ namespace {
 
 int launch_agg_fwd(const gens_volume_scale_t& sc, int nv, const float* w2c, const float* intrs, int min_vis_view,
                    int div_mode, cudaStream_t st) {
-    if (!(sc.feat_padded && sc.grid && sc.volume && sc.mask_volume)) return GENS_E_BADARG;
+    if (sc.n_peers < 0 || sc.n_peers > GENS_MAX_PEERS) return GENS_E_BADARG;
+    for (int i = 0; i < sc.n_peers; ++i)
+        if (!(sc.peer_volume[i] && sc.peer_mask[i])) return GENS_E_BADARG;
+    if (!(sc.feat_padded && sc.grid && (sc.n_peers > 0 || (sc.volume && sc.mask_volume)))) return GENS_E_BADARG;
     if (!(sc.H > 0 && sc.W > 0 && sc.D > 0) || bad_slab(sc.D, sc.a0, sc.a1, sc.a_base)) return GENS_E_BADARG;
     if ((long long)(sc.H + 1) * (sc.W + 1) * nv >= (1LL << 28)) return GENS_E_UNSUPPORTED;
     if (sc.a1 <= sc.a0) return 0;
@@ -665,14 +702,27 @@ int launch_agg_fwd(const gens_volume_scale_t& sc, int nv, const float* w2c, cons
     const Pair* feat = reinterpret_cast<const Pair*>(sc.feat_padded);
     const bool recip = div_mode == GENS_DIV_RECIP;
     const dim3 block(32, 8);
+    PeerOut peers;
+    peers.n = sc.n_peers;
+    for (int i = 0; i < GENS_MAX_PEERS; ++i) {
+        peers.vol[i] = i < sc.n_peers ? sc.peer_volume[i] : nullptr;
+        peers.msk[i] = i < sc.n_peers ? sc.peer_mask[i] : nullptr;
+    }
+    const bool to_peers = sc.n_peers > 0;
 #define GENS_AGG_ARGS \
     feat, nv, sc.H, sc.W, w2c, intrs, sc.k_row_scale, sc.grid, D, sc.a0, out_off, sc.channel_stride, min_vis_view, e, \
-        sc.volume, sc.mask_volume
+        sc.volume, sc.mask_volume, peers
 #define GENS_LAUNCH_PACKED(PAIRS, MINB, GATHER, ROWS)                                                              \
     do {                                                                                                         \
         const dim3 g(D / (64 * PAIRS), ceil_div_i(D, 8 * ROWS), planes);                                         \
-        if (recip) volume_agg_packed_kernel<PAIRS, true, MINB, GATHER, ROWS><<<g, block, 0, st>>>(GENS_AGG_ARGS); \
-        else volume_agg_packed_kernel<PAIRS, false, MINB, GATHER, ROWS><<<g, block, 0, st>>>(GENS_AGG_ARGS);     \
+        if (to_peers && recip)                                                                                   \
+            volume_agg_packed_kernel<PAIRS, true, MINB, GATHER, ROWS, true><<<g, block, 0, st>>>(GENS_AGG_ARGS);  \
+        else if (to_peers)                                                                                       \
+            volume_agg_packed_kernel<PAIRS, false, MINB, GATHER, ROWS, true><<<g, block, 0, st>>>(GENS_AGG_ARGS); \
+        else if (recip)                                                                                          \
+            volume_agg_packed_kernel<PAIRS, true, MINB, GATHER, ROWS><<<g, block, 0, st>>>(GENS_AGG_ARGS);        \
+        else                                                                                                     \
+            volume_agg_packed_kernel<PAIRS, false, MINB, GATHER, ROWS><<<g, block, 0, st>>>(GENS_AGG_ARGS);       \
     } while (0)
     const int variant = g_k1_variant;
     // rows per block: enough to amortise the camera staging, few enough to keep >= ~4 waves of blocks
@@ -777,6 +827,7 @@ extern "C" int gens_volume_agg_fwd(const float* feat_padded, int nv, int H, int 
     sc.feat_padded = feat_padded; sc.H = H; sc.W = W; sc.D = D; sc.a0 = a0; sc.a1 = a1; sc.a_base = a_base;
     sc.channel_stride = channel_stride; sc.k_row_scale = k_row_scale; sc.grid = grid; sc.volume = volume;
     sc.mask_volume = mask_volume;
+    sc.n_peers = 0;
     return gens_volume_agg_fwd_multi(&sc, 1, nv, w2c, intrs, min_vis_view, div_mode, stream);
 }
 

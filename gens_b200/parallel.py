@@ -64,6 +64,70 @@ def gather_slabs_inplace(full: torch.Tensor, d: int, rank: int, world: int, grou
     return full
 
 
+class SlabExchange:
+    """Peer-mapped output buffers for the fused build + exchange (one per process and pyramid shape).
+
+    Two symmetric allocations (torch.distributed._symmetric_memory: every rank's buffer is mapped into every
+    other rank's address space over NVLink) hold the final (1,9,D,D,D) tensors of all scales; builds alternate
+    between them.  K1 stores each result into the same offset of ALL ranks' buffers, a device-side barrier on
+    the stream closes the build.  OWNERSHIP: the tensors returned by build k are views of buffer k % 2 and are
+    overwritten by build k + 2 (the reference consumes a scene's volumes before it builds the next one); a rank
+    may not run more than one build ahead of its consumers, which stream order gives for free."""
+
+    _cache = {}
+
+    def __init__(self, dims, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.dims = list(dims)
+        self.offs = [0]
+        for d in self.dims:
+            self.offs.append(self.offs[-1] + 9 * d ** 3)
+        self.bufs, self.handles = [], []
+        for _ in range(2):
+            t = symm_mem.empty(self.offs[-1], dtype=torch.float32, device=device)
+            self.handles.append(symm_mem.rendezvous(t, group if group is not None else dist.group.WORLD))
+            self.bufs.append(t)
+        self.turn = 0
+
+    @classmethod
+    def get(cls, dims, device, group):
+        key = (tuple(dims), str(device), id(group))
+        if key not in cls._cache:
+            cls._cache[key] = cls(dims, device, group)
+        return cls._cache[key]
+
+    def next(self):
+        """(local buffer, its handle) of this build; alternates between the two allocations."""
+        i = self.turn
+        self.turn ^= 1
+        return self.bufs[i], self.handles[i]
+
+
+def fused_sharded_agg_mean_var(volume_module, features, intrs, c2ws, rank: int, world: int, min_vis_view: int = 1,
+                               group=None):
+    """Slab-sharded build whose stores ARE the exchange: every rank computes its planes of every scale and K1
+    writes them into the final tensors of all ranks over NVLink peer mappings (no all-gather, no scatter
+    pass); one device-side barrier makes the assembled volumes visible.  Bit-identical to the 1-GPU build.
+    See SlabExchange for the ownership of the returned tensors."""
+    from .volume import agg_mean_var
+    dims = volume_module.volume_dims
+    if world > 8:
+        raise RuntimeError("fused slab exchange supports up to 8 ranks of one node")
+    ex = SlabExchange.get(dims, features[0].device, group)
+    buf, hdl = ex.next()
+    ptrs = [int(p) for p in hdl.buffer_ptrs]
+    slabs = [slab_bounds(d, rank, world) for d in dims]
+    peer_outs = []
+    for d, off in zip(dims, ex.offs):
+        vol = buf[off: off + 8 * d ** 3].view(1, 8, d, d, d)
+        msk = buf[off + 8 * d ** 3: off + 9 * d ** 3].view(1, 1, d, d, d)
+        peer_outs.append((vol, msk, [p + 4 * off for p in ptrs], [p + 4 * (off + 8 * d ** 3) for p in ptrs]))
+    vols, masks = agg_mean_var(features, intrs, c2ws, dims, min_vis_view, slabs, volume_module.div_mode,
+                               peer_outs=peer_outs)
+    hdl.barrier(channel=0)  # every rank's stores into this buffer have landed (stream-ordered on all ranks)
+    return vols, masks
+
+
 def sharded_agg_mean_var(volume_module, features, intrs, c2ws, rank: int, world: int, min_vis_view: int = 1,
                          group=None):
     """Slab-sharded Volume.agg_mean_var + all-gather; same return value as the single-GPU call.

@@ -91,7 +91,7 @@ def _check_maps(features) -> List[torch.Tensor]:
     return feats
 
 
-def _build(c2ws, intrs, dims, slabs, min_vis_view, div_mode, outs, features):
+def _build(c2ws, intrs, dims, slabs, min_vis_view, div_mode, outs, features, peer_outs=None):
     """Every allocation first, then ONE C call (gens_volume_build): pack + pose inverse launch, then the
     aggregation launches, with no interpreter time between them.  Returns (vols, masks, packed, w2c)."""
     feats = _check_maps(features)
@@ -113,18 +113,28 @@ def _build(c2ws, intrs, dims, slabs, min_vis_view, div_mode, outs, features):
     for i, d in enumerate(dims):
         a0, a1 = slabs[i]
         planes = a1 - a0
-        if outs is None:
+        sc = scales[i]
+        if peer_outs is not None:
+            # multi-GPU: the slab is stored straight into the FULL (1,8,D,D,D) / (1,1,D,D,D) tensors of every
+            # rank (own + NVLink peer mappings); peer_outs[i] = (vol, mask, [vol pointers], [mask pointers])
+            vol, msk, vol_ptrs, msk_ptrs = peer_outs[i]
+            sc.n_peers = len(vol_ptrs)
+            for r, (pv, pm) in enumerate(zip(vol_ptrs, msk_ptrs)):
+                sc.peer_volume[r], sc.peer_mask[r] = pv, pm
+            base, stride = 0, d * d * d
+        elif outs is None:
             # the 8 feature channels and the mask of a scale share one allocation (both views are contiguous)
             both = torch.empty((1, 9, planes, d, d), device=dev, dtype=torch.float32)
             vol, msk = both[:, :8], both[:, 8:]
+            base, stride = a0, planes * d * d
         else:  # caller-provided slab buffers (views into the all-gather send buffer)
             vol, msk = outs[i]
+            base, stride = a0, planes * d * d
         grid = voxel_axis(d, dev)
-        sc = scales[i]
         sc.feat_padded = packed[i].data_ptr()
         sc.H, sc.W, sc.D = feats[i].shape[2], feats[i].shape[3], d
-        sc.a0, sc.a1, sc.a_base = a0, a1, a0
-        sc.channel_stride = planes * d * d
+        sc.a0, sc.a1, sc.a_base = a0, a1, base
+        sc.channel_stride = stride
         sc.k_row_scale = 0.5 ** i
         sc.grid, sc.volume, sc.mask_volume = grid.data_ptr(), vol.data_ptr(), msk.data_ptr()
         vols.append(vol)
@@ -181,7 +191,7 @@ class _AggMeanVar(torch.autograd.Function):
 
 def agg_mean_var(features, intrs, c2ws, dims, min_vis_view: int = 1,
                  slabs: Optional[Sequence[Tuple[int, int]]] = None, div_mode: int = DEFAULT_DIV_MODE,
-                 outs=None):
+                 outs=None, peer_outs=None):
     """The 5-scale build.  `slabs[i] = (a0, a1)` restricts scale i to planes of tensor dim 2 (the
     multi-GPU sharding); default = full volumes.  `outs[i] = (vol, mask)` lets the caller provide the
     (contiguous, fp32) output buffers, e.g. views into an all-gather send buffer.
@@ -190,8 +200,9 @@ def agg_mean_var(features, intrs, c2ws, dims, min_vis_view: int = 1,
     k = _lib.f32c(intrs)
     slabs = [(0, d) for d in dims] if slabs is None else list(slabs)
     feats = features[:len(dims)]
-    if not (torch.is_grad_enabled() and any(f.requires_grad for f in feats)):
-        vols, masks, _, _ = _build(_lib.f32c(c2ws), k, tuple(dims), tuple(slabs), min_vis_view, div_mode, outs, feats)
+    if peer_outs is not None or not (torch.is_grad_enabled() and any(f.requires_grad for f in feats)):
+        vols, masks, _, _ = _build(_lib.f32c(c2ws), k, tuple(dims), tuple(slabs), min_vis_view, div_mode, outs, feats,
+                                   peer_outs)
         return vols, masks
     out = _AggMeanVar.apply(_lib.f32c(c2ws), k, tuple(dims), tuple(slabs), min_vis_view, div_mode, outs,
                             *features[:len(dims)])

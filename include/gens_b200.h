@@ -58,6 +58,7 @@ int gens_unpack_feature_grads(const float *src_padded_nhwc, float *dst_nchw, int
  *   intrs (nv,4,4) unscaled intrinsics; rows 0-1 are multiplied by k_row_scale = 0.5^scale in
  *                  the kernel, exactly like `intrs_stage[:, :2] *= 0.5**i` (volume.py:24-25)
  * One scale: */
+#define GENS_MAX_PEERS 8
 typedef struct gens_volume_scale {
     const float *feat_padded; /* (nv,H+1,W,8) pixel pairs from gens_pack_feature_maps          */
     int H, W;                 /* feature-map size of this scale                              */
@@ -69,6 +70,12 @@ typedef struct gens_volume_scale {
     const float *grid;        /* (D) = linspace(-1,1,D)                       (volume.py:28) */
     float *volume;            /* channel c, voxel (a,b,c') at                                */
     float *mask_volume;       /*   [c*channel_stride + ((a-a_base)*D + b)*D + c']            */
+    /* multi-GPU: n_peers > 0 -> every result is stored to peer_volume[i] / peer_mask[i], i < n_peers (this
+     * rank's own buffer and the NVLink peer mappings of the other ranks' buffers, addressed like volume /
+     * mask_volume), and volume / mask_volume are ignored: the slab exchange rides on the kernel's stores.  */
+    int n_peers;
+    float *peer_volume[GENS_MAX_PEERS];
+    float *peer_mask[GENS_MAX_PEERS];
 } gens_volume_scale_t;
 /* (a_base = a0, channel_stride = (a1-a0)*D*D for a slab buffer;
  *  a_base = 0,  channel_stride = D*D*D       for the full (1,8,D,D,D) tensor). */

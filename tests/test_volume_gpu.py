@@ -216,3 +216,16 @@ def test_pose_inverse_is_bit_identical_to_torch(cuda_lib):
     rnd = torch.randn(20000, 4, 4, generator=g).to(DEV)
     share = float((_lib.invert_poses(rnd) == torch.inverse(rnd)).all(-1).all(-1).float().mean())
     print(f"general 4x4 matrices reproduced bit for bit: {share:.4f}")
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs of one node (NVLink peer mappings)")
+def test_fused_slab_exchange_two_gpus():
+    """K1 storing its slab into both ranks' final tensors over peer mappings: bit-identical to the 1-GPU build
+    (tools/check_fused_slabs.py under torchrun, world size 2)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", "tools/check_fused_slabs.py"],
+                       cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("bit-identical to the 1-GPU build: True") == 2, r.stdout[-2000:]
