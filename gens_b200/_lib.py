@@ -116,6 +116,7 @@ _SIGNATURES = {
     "gens_composite_rays": ([ctypes.POINTER(CompositeArgs), _vp], _i),
     "gens_blend_weight_floats": ([], _i),
     "gens_blend_colour": ([_vp, _vp, _vp, _ll, _i, _vp, _vp, _vp], _i),
+    "gens_patch_warp": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp], _i),
     "gens_tv_reduce": ([_PP, _PP, _i, _i, _vp, _vp], _i),
     "gens_debug_set_variant": ([_i], _i),
     "gens_selftest_division": ([_i, ctypes.c_ulonglong, _vp, _vp], _i),

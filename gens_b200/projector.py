@@ -262,6 +262,20 @@ def surface_patch_warp(pts_sdf0, gradients_sdf0, images, intrinsics, poses, patc
     reference view into the sources.  Returns ((1,B,p*p,c), (ns,B,p*p,c)); differentiable w.r.t. pts."""
     import torch.nn.functional as F
     b = pts_sdf0.shape[0]
+    if pts_sdf0.is_cuda and not (torch.is_grad_enabled() and (pts_sdf0.requires_grad or images.requires_grad)):
+        # K8 (csrc/patch_warp.cu): one launch for the homographies and every sample of every view
+        _lib.require_cuda(gradients_sdf0, images, intrinsics, poses)
+        nv, c, h, w = images.shape
+        pp = patch_size * patch_size
+        imgs, k, p = _lib.f32c(images.detach()), _lib.f32c(intrinsics), _lib.f32c(poses)
+        k_inv = _lib.invert_poses(k[:1])
+        ref = torch.empty((1, b, pp, c), device=images.device, dtype=torch.float32)
+        src = torch.empty((nv - 1, b, pp, c), device=images.device, dtype=torch.float32)
+        _lib.check(_lib.lib().gens_patch_warp(
+            _lib.ptr(_lib.f32c(pts_sdf0.detach().reshape(-1, 3))), _lib.ptr(_lib.f32c(gradients_sdf0.detach().reshape(-1, 3))),
+            _lib.ptr(imgs), _lib.ptr(k), _lib.ptr(p), _lib.ptr(k_inv), b, nv, c, h, w, int(patch_size), _lib.ptr(ref),
+            _lib.ptr(src) if nv > 1 else None, _lib.stream_ptr(images.device)), "gens_patch_warp")
+        return ref, src
     r0, c0 = poses[0, :3, :3], poses[0, :3, 3]
     k0 = intrinsics[0, :3, :3]
     k0_inv = _lib.inverse(intrinsics)[0, :3, :3]

@@ -317,6 +317,16 @@ int gens_blend_weight_floats(void);
 int gens_blend_colour(const float *rgb_feat, const float *ray_diff, const uint8_t *mask, long long n,
                       int n_src, const float *weights, float *rgb_out, void *stream);
 
+/* ---- K8: feature-metric consistency patches ------------------------------------------------
+ * surface_patch_warp + patch_homography (reference models/modules/projector.py:353-437) for inference: pts
+ * (n_rays,3) surface points, nrm (n_rays,3) unit normals in the reference camera frame, images (nv,C,H,W) NCHW,
+ * intrinsics / poses (nv,4,4), k0_inv4 (4,4) = inverse(intrinsics[0]); patch odd.  Writes the patch sampled in the
+ * reference view, ref_out (n_rays,patch^2,C), and warped into every source view, src_out (nv-1,n_rays,patch^2,C)
+ * (bilinear, zeros padding, align_corners = True). */
+int gens_patch_warp(const float *pts, const float *nrm, const float *images, const float *intrinsics,
+                    const float *poses, const float *k0_inv4, int n_rays, int nv, int channels, int H, int W,
+                    int patch, float *ref_out, float *src_out, void *stream);
+
 /* K9: masked total variation of the volume pyramid in one pass -- the reduction behind
  * ImplicitSurface.tv_regularization (reference models/modules/implicit_surface.py:135-150, called from
  * render_core :260).  vols->vol[s] = (channels,D,D,D) NCDHW, masks->vol[s] = (D,D,D) (masks or an entry NULL =

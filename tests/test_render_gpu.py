@@ -293,3 +293,26 @@ def test_k10_blend_kernel_matches_module(setup, ns):
     assert net.blend_nograd(rgb_feat[:0], ray_diff[:0], mask[:0]).shape == (0, 3)
     with pytest.raises(RuntimeError):
         net.blend_nograd(rgb_feat.cpu(), ray_diff.cpu(), mask.cpu())
+
+
+def test_k8_patch_warp_kernel_matches_aten_path(setup):
+    """K8 (csrc/patch_warp.cu) against the ATen formulation of surface_patch_warp (the one the golden render pins):
+    random surface points in front of the reference camera, incl. points whose patch leaves the images."""
+    g, surf, scene, volumes, masks = setup
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    b = 3000
+    ro, rd = scene.rays(step=1)
+    sel = torch.randint(0, ro.shape[0], (b,), device=DEV, generator=gen)
+    z = scene.near + (scene.far - scene.near) * torch.rand(b, 1, device=DEV, generator=gen)
+    pts = (ro[sel] + rd[sel] * z).reshape(b, 1, 3)
+    nrm = torch.nn.functional.normalize(torch.randn(b, 1, 3, device=DEV, generator=gen), dim=-1)
+    feats = torch.randn(scene.imgs.shape[0], 12, 96, 128, device=DEV, generator=gen)
+    with torch.no_grad():
+        ref_k, src_k = projector.surface_patch_warp(pts, nrm, feats, scene.intrs, scene.c2ws)
+    with torch.enable_grad():   # a point that needs a gradient keeps the differentiable ATen path
+        ref_t, src_t = projector.surface_patch_warp(pts.clone().requires_grad_(True), nrm, feats, scene.intrs, scene.c2ws)
+    assert src_t.requires_grad and not src_k.requires_grad
+    assert ref_k.shape == ref_t.shape == (1, b, 121, 12) and src_k.shape == src_t.shape == (scene.imgs.shape[0] - 1, b, 121, 12)
+    _check("K8 reference patch", ref_k, ref_t.detach().cpu().numpy(), **GRAY)
+    _check("K8 warped patches", src_k, src_t.detach().cpu().numpy(), **GRAY)
+    assert float((src_k != 0).float().mean()) > 0.3     # not vacuous: most warped samples land inside the images
