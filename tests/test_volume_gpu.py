@@ -229,3 +229,76 @@ def test_fused_slab_exchange_two_gpus():
                        cwd=root, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("bit-identical to the 1-GPU build: True") == 2, r.stdout[-2000:]
+
+
+def _k1_variant(variant, feat_d, nv, h, w, w2c_d, k_d, grid_d, d, a0=0, a1=None, min_vis_view=1):
+    a1 = d if a1 is None else a1
+    planes = a1 - a0
+    vol = torch.full((8, planes, d, d), float("nan"), device=DEV)
+    msk = torch.full((planes, d, d), float("nan"), device=DEV)
+    L = _lib.lib()
+    L.gens_debug_set_variant(variant)
+    try:
+        _lib.check(L.gens_volume_agg_fwd(_lib.ptr(feat_d), nv, h, w, _lib.ptr(w2c_d), _lib.ptr(k_d), 1.0,
+                                         _lib.ptr(grid_d), d, a0, a1, a0, planes * d * d, min_vis_view,
+                                         _lib.DIV_RECIP, _lib.ptr(vol), _lib.ptr(msk), _lib.stream_ptr()), "k1")
+        torch.cuda.synchronize()
+    finally:
+        L.gens_debug_set_variant(0)
+    return vol, msk
+
+
+def _camera_cases():
+    """The bench scene plus cameras that stress the frustum culling: inside the volume, looking away,
+    rolled by 90 degrees, nearly tangent to the volume faces."""
+    def scaled(f):
+        def mod(c):
+            c = c.clone(); c[:, :3, 3] *= f; return c
+        return mod
+
+    def turned(c):
+        c = c.clone()
+        c[1, :3, :3] = c[1, :3, :3] @ torch.tensor([[-1.0, 0, 0], [0, 1, 0], [0, 0, -1.0]])  # view 1 looks away
+        r = torch.tensor([[0.0, -1, 0], [1, 0, 0], [0, 0, 1]])
+        c[2, :3, :3] = c[2, :3, :3] @ r  # view 2 rolled
+        return c
+
+    def tangent(c):
+        c = c.clone(); c[:, 0, 3] += 1.7; return c
+    return [("bench", None), ("inside", scaled(0.3)), ("centre", scaled(0.0)), ("turned", turned), ("tangent", tangent)]
+
+
+@pytest.mark.parametrize("d,hw,nv", [(64, (96, 128), 3), (128, (240, 320), 3), (256, (480, 640), 5)])
+def test_rowgroup_kernel_variants_bit_identical(cuda_lib, d, hw, nv):
+    """The row-group kernel (conservative frustum culling + TMA box stores, variants 20-27 of the tuning knob)
+    writes exactly what the packed kernel (variant 10) writes, for every camera arrangement, slab builds and
+    mask thresholds included; at D = 64 both are also bit-identical to the C oracle."""
+    for name, mod in _camera_cases():
+        sc = make_scene(hw[0], hw[1], nv, seed=11, with_images=False)
+        c2ws = sc.c2ws if mod is None else mod(sc.c2ws)
+        w2c, k = stage_cameras(sc.intrs, c2ws, 0)
+        feat_d = pack_feature_maps(sc.features[0].to(DEV))
+        w2c_d, k_d, grid_d = w2c.to(DEV).contiguous(), k.to(DEV).contiguous(), torch.linspace(-1, 1, d).to(DEV)
+        args = (feat_d, nv, hw[0], hw[1], w2c_d, k_d, grid_d, d)
+        ref_vol, ref_msk = _k1_variant(10, *args)
+        assert not torch.isnan(ref_vol).any() and not torch.isnan(ref_msk).any()
+        if d == 64:
+            ovol, omsk = c_oracle.volume_agg(sc.features[0].numpy(), w2c.numpy(), k.numpy(),
+                                             torch.linspace(-1, 1, d).numpy(), div_mode=c_oracle.DIV_RECIP)
+            assert np.array_equal(ref_vol.cpu().numpy(), ovol) and np.array_equal(ref_msk.cpu().numpy(), omsk), name
+        for variant in (0, 20, 21, 22, 23, 24, 25, 26, 27, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 63, 64, 65):  # 73 (constant-bank cameras) needs gens_debug_set_const_cams: sweep only
+            vol, msk = _k1_variant(variant, *args)
+            assert torch.equal(vol, ref_vol), f"{name}: variant {variant} volumes differ"
+            assert torch.equal(msk, ref_msk), f"{name}: variant {variant} masks differ"
+        plain_d = torch.nn.functional.pad(sc.features[0].to(DEV).permute(0, 2, 3, 1), (0, 0, 0, 1, 0, 1)).contiguous()
+        for variant in ():  # (70, 71: padded channels-last maps -- tuning variants, see tools/sweep_k1.py)
+            vol, msk = _k1_variant(variant, plain_d, *args[1:])
+            assert torch.equal(vol, ref_vol) and torch.equal(msk, ref_msk), f"{name}: variant {variant} differs"
+        # a slab in the middle of the volume, into a slab-sized buffer, and min_vis_view = 0
+        a0, a1 = d // 4, d // 4 + d // 8
+        for variant in (20, 21, 30, 33, 36):
+            vol, msk = _k1_variant(variant, *args, a0=a0, a1=a1)
+            assert torch.equal(vol, ref_vol[:, a0:a1]) and torch.equal(msk, ref_msk[a0:a1]), (name, variant, "slab")
+            vol0, msk0 = _k1_variant(variant, *args, min_vis_view=0)
+            rvol0, rmsk0 = _k1_variant(10, *args, min_vis_view=0)
+            assert torch.equal(vol0, rvol0) and torch.equal(msk0, rmsk0), (name, variant, "min_vis_view=0")
