@@ -24,9 +24,6 @@
 // restatement it is tested against bit-for-bit): two-stage projection as k-ascending fma
 // chains, IEEE division, two-moment variance E[x^2]-E[x]^2 (NOT Welford -- parity with the
 // reference's cancellation behaviour is the contract).
-#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched from the driver at run time)
-
-#include <cstring>
 #include <mutex>
 
 #include "common.cuh"
@@ -292,38 +289,14 @@ struct Corner4 {
     float4 nw, ne, sw, se;
 };
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
-template <bool WIDE = true, bool FAKE = false, bool PLAIN = false>
 __device__ __forceinline__ Corner4 gather4(const Pair* __restrict__ map, int pitch, int x0, int y0) {
     const Pair* p = map + (y0 * pitch + x0);
+    const Pair top = ldg256(p), bot = ldg256(p + pitch);
     Corner4 c;
-    if (PLAIN) {  // `map` is a padded channels-last (H+1, W+1, 4) map, `pitch` = W + 1 texels of 16 bytes
-        const float4* q = reinterpret_cast<const float4*>(map) + (y0 * pitch + x0);
-        c.nw = __ldg(q);
-        c.ne = __ldg(q + 1);
-        c.sw = __ldg(q + pitch);
-        c.se = __ldg(q + pitch + 1);
-        return c;
-    }
-    if (FAKE) {  // tuning only: no memory traffic, values made up from the indices
-        const float t = __int2float_rn(x0), u = __int2float_rn(y0);
-        c.nw = make_float4(t, u, t, u); c.ne = make_float4(u, t, u, t); c.sw = c.nw; c.se = c.ne;
-        return c;
-    }
-    if (WIDE) {
-        const Pair top = ldg256(p), bot = ldg256(p + pitch);
-        c.nw = top.a;
-        c.ne = top.b;
-        c.sw = bot.a;
-        c.se = bot.b;
-    } else {  // four 128-bit read-only loads over the same texels
-        const float4* q = reinterpret_cast<const float4*>(p);
-        c.nw = __ldg(q);
-        c.ne = __ldg(q + 1);
-        c.sw = __ldg(q + 2 * pitch);
-        c.se = __ldg(q + 2 * pitch + 1);
-    }
+    c.nw = top.a;
+    c.ne = top.b;
+    c.sw = bot.a;
+    c.se = bot.b;
     return c;
 }
 
@@ -364,38 +337,18 @@ __device__ __forceinline__ void accumulate_view(const Cam& cam, const Pair* __re
         const f32x2 bx = sub2(p.ix, pk(fx_lo, fx_hi)), by = sub2(p.iy, pk(fy_lo, fy_hi));
         const f32x2 ax = sub2(bc(1.0f), bx), ay = sub2(bc(1.0f), by);
         const f32x2 w_nw = mul2(ax, ay), w_ne = mul2(bx, ay), w_sw = mul2(ax, by), w_se = mul2(bx, by);
-        if (GATHER == 5) {
-            // both footprints in flight before the first blend, without divergent loads: an invalid voxel reads
-            // texel 0 of the view (always mapped, L1-resident) and its blend is skipped
-            const int i_lo = p.valid_lo ? (int)fy_lo * pitch + (int)fx_lo : 0;
-            const int i_hi = p.valid_hi ? (int)fy_hi * pitch + (int)fx_hi : 0;
-            const Pair t_lo = ldg256(map + i_lo), b_lo = ldg256(map + i_lo + pitch);
-            const Pair t_hi = ldg256(map + i_hi), b_hi = ldg256(map + i_hi + pitch);
-            if (p.valid_lo) {
-                Corner4 c; c.nw = t_lo.a; c.ne = t_lo.b; c.sw = b_lo.a; c.se = b_lo.b;
-                blend_accumulate(c, lo(w_nw), lo(w_ne), lo(w_sw), lo(w_se), acc[2 * h]);
-            }
-            if (p.valid_hi) {
-                Corner4 c; c.nw = t_hi.a; c.ne = t_hi.b; c.sw = b_hi.a; c.se = b_hi.b;
-                blend_accumulate(c, hi(w_nw), hi(w_ne), hi(w_sw), hi(w_se), acc[2 * h + 1]);
-            }
-        } else if (GATHER == 0) {
+        if (GATHER == 0) {
             Corner4 v_lo, v_hi;
             if (p.valid_lo) v_lo = gather4(map, pitch, (int)fx_lo, (int)fy_lo);
             if (p.valid_hi) v_hi = gather4(map, pitch, (int)fx_hi, (int)fy_hi);
             if (p.valid_lo) blend_accumulate(v_lo, lo(w_nw), lo(w_ne), lo(w_sw), lo(w_se), acc[2 * h]);
             if (p.valid_hi) blend_accumulate(v_hi, hi(w_nw), hi(w_ne), hi(w_sw), hi(w_se), acc[2 * h + 1]);
         } else {
-            if (GATHER == 3 && p.valid_hi) {  // the second voxel's footprint travels to L1 while the first is blended
-                const Pair* q = map + ((int)fy_hi * pitch + (int)fx_hi);
-                prefetch_l1(q);
-                prefetch_l1(q + pitch);
-            }
             if (p.valid_lo)
-                blend_accumulate(gather4<GATHER != 2, GATHER == 4, GATHER == 6>(map, pitch, (int)fx_lo, (int)fy_lo), lo(w_nw), lo(w_ne), lo(w_sw),
+                blend_accumulate(gather4(map, pitch, (int)fx_lo, (int)fy_lo), lo(w_nw), lo(w_ne), lo(w_sw),
                                  lo(w_se), acc[2 * h]);
             if (p.valid_hi)
-                blend_accumulate(gather4<GATHER != 2, GATHER == 4, GATHER == 6>(map, pitch, (int)fx_hi, (int)fy_hi), hi(w_nw), hi(w_ne), hi(w_sw),
+                blend_accumulate(gather4(map, pitch, (int)fx_hi, (int)fy_hi), hi(w_nw), hi(w_ne), hi(w_sw),
                                  hi(w_se), acc[2 * h + 1]);
         }
     }
@@ -480,23 +433,18 @@ volume_agg_packed_kernel(const Pair* __restrict__ feat, int nv, int H, int W, co
     }
 }
 
-// Camera block in the constant bank (tuning experiment: the per-view coefficients then reach the FFMA2s as
-// uniform-register operands instead of shared-memory loads through the L1 data pipe).
-__constant__ Cam c_cams[GENS_MAX_VIEWS];
-
 // ------------------------------------------------------------------------------------------
-// row-group path (D % 64 == 0, single destination): the packed arithmetic above plus
-//   (1) conservative frustum culling per (row-group of 8 rows x 64 voxels, view), decided once per block
-//       from the four corners of the row-group, and
-//   (2) results staged in shared memory and written by the TMA (cp.async.bulk.tensor stores of 64x8 boxes),
-//       so that a warp's 18 result rows cost 18 shared-memory wavefronts instead of 72 global-store ones.
-// On the 480x640 / 3-view scene 47 % of the voxels are seen by no view at all and 38 % of the row-groups are
-// entirely dead: those cost one zero-box store per plane and no arithmetic.
+// row-group path (D % 64 == 0, single destination): the packed arithmetic above plus conservative frustum
+// culling per (tile of 8 rows x 64 voxels, view), decided once per block from the four corners of the tile.
+// On the 480x640 / 3-view scene 47 % of the voxels are seen by no view at all and 38 % of the tiles are
+// entirely dead: those cost their zero stores and no arithmetic; in the others 10 % of the tile-views are
+// skipped.  Measured alternatives (TMA box stores, walking x instead of y, other gather layouts, cameras in
+// the constant bank) are listed with their times in profiles/r01_k1_variant_sweep.txt.
 // ------------------------------------------------------------------------------------------
 
 // Frustum planes a point lies outside of WITH MARGIN (bit 0: behind the camera, 1: left, 2: right, 3: top,
 // 4: bottom).  Every test is a linear function L of the world point with a tolerance tau * (sum of the
-// magnitudes of its terms): if L > tol at the four corners of a row-group (fixed X, Y and Z ranges), L > 0
+// magnitudes of its terms): if L > tol at the four corners of a tile (fixed X, Y and Z ranges), L > 0
 // at every voxel inside, and then the voxel is invalid in the reference's arithmetic:
 //   behind:  depth < 0                                     -> `img2 > 0` fails (volume.py:43)
 //   left:    -img0 - m hx depth > 0  => x / hx < -m        -> |nx| = |x/hx - 1| > 1 (or depth <= 0)
@@ -527,57 +475,35 @@ __device__ __forceinline__ unsigned cull_planes(const Cam& cam, float X, float Y
     return bits;
 }
 
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-// One 64 x 8 box (z, y) of plane (x, ch) from dense shared memory [8][64] to the tensor behind `map`.
-__device__ __forceinline__ void tma_store_box(const CUtensorMap* map, uint32_t src, int z, int y, int x, int ch) {
-    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
-                 :: "l"(map), "r"(z), "r"(y), "r"(x), "r"(ch), "r"(src) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_smem_to_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// STORE = 0: streaming global stores; STORE = 1: shared-memory staging + TMA box stores.
-// A block owns one tile of 8 rows (y) x 64 voxels (z) and walks ROWS of them: WALKX = false along y
-// (blockIdx.y covers ROWS row-groups of one x plane), WALKX = true along x (the same (y,z) tile of ROWS
-// consecutive planes).  Consecutive planes project one or two pixels apart, so walking x keeps a tile's
-// footprints in L1 from one iteration to the next.
-template <bool RECIP, int ROWS, int STORE, bool CULL, bool WALKX, int GATHER = 1, int MINB = 4, bool CONSTCAM = false>
-__global__ void __launch_bounds__(256, MINB)
+// A block owns ROWS tiles of 8 rows (y) x 64 voxels (z) of one x plane.  CULL = false keeps every tile-view
+// (A/B reference for the culling, variant 25 of the tuning knob).
+template <bool RECIP, int ROWS, bool CULL>
+__global__ void __launch_bounds__(256, 4)
 volume_agg_rowgroup_kernel(const Pair* __restrict__ feat, int nv, int H, int W, const float* __restrict__ w2c,
                            const float* __restrict__ k_stage, float k_row_scale, const float* __restrict__ grid, int D,
-                           int a0, int planes, long long out_off, long long channel_stride, int min_vis_view, Extent e,
-                           float* __restrict__ volume, float* __restrict__ mask_volume, int plane0,
-                           const __grid_constant__ CUtensorMap map_vol, const __grid_constant__ CUtensorMap map_msk) {
+                           int a0, long long out_off, long long channel_stride, int min_vis_view, Extent e,
+                           float* __restrict__ volume, float* __restrict__ mask_volume) {
     __shared__ Cam s_cam[GENS_MAX_VIEWS];
     __shared__ float s_inv_count[GENS_MAX_VIEWS + 1];
     __shared__ unsigned s_live[ROWS];  // per tile: bit v set = view v may see a voxel of it
-    __shared__ __align__(128) float s_stage[STORE == 1 ? 9 : 1][8][64];
-    __shared__ __align__(128) float s_zero[STORE == 1 ? 8 : 1][64];
     const int tid = threadIdx.y * 32 + threadIdx.x;
     if (threadIdx.y == 0 && threadIdx.x <= GENS_MAX_VIEWS)
         s_inv_count[threadIdx.x] = threadIdx.x == 0 ? 1e8f : __fdiv_rn(1.0f, (float)threadIdx.x);
     if (tid < ROWS) s_live[tid] = CULL ? 0u : 0xffffffffu;
-    if (STORE == 1) {
-        for (int i = tid; i < 8 * 64; i += 256) (&s_zero[0][0])[i] = 0.0f;
-        fence_smem_to_async_proxy();
-    }
     load_cams(s_cam, w2c, k_stage, k_row_scale, nv);  // two barriers inside
 
-    // tile rr of this block: plane index p(rr) (relative to a0) and first row b0(rr)
-    const int cz0 = blockIdx.x * 64, c0 = cz0 + threadIdx.x;
-    const int p_first = WALKX ? blockIdx.z * ROWS : blockIdx.z, b_first = WALKX ? blockIdx.y * 8 : blockIdx.y * ROWS * 8;
+    const int cz0 = blockIdx.x * 64, c0 = cz0 + threadIdx.x, a = a0 + blockIdx.z;
+    const float X = __ldg(grid + a);
     if (CULL) {
-        const int total = ROWS * nv * 4;  // one item = one corner of one (tile, view)
+        const int total = ROWS * nv * 4;  // one item = one corner of one (tile, view); 4 consecutive lanes = one pair
         for (int base = 0; base < total; base += 256) {
             const int i = base + tid;
             const bool active = i < total;
             const int corner = i & 3, v = active ? (i >> 2) % nv : 0, rg = active ? (i >> 2) / nv : 0;
-            const int p = WALKX ? p_first + rg : p_first, b0 = WALKX ? b_first : b_first + 8 * rg;
+            const int b0 = (blockIdx.y * ROWS + rg) * 8;
             unsigned bits = 0;
-            if (active && b0 < D && p < planes && s_cam[v].affine)
-                bits = cull_planes(s_cam[v], __ldg(grid + a0 + p), __ldg(grid + b0 + (corner & 1) * 7),
-                                   __ldg(grid + cz0 + (corner >> 1) * 63), e);
+            if (active && b0 < D && s_cam[v].affine)
+                bits = cull_planes(s_cam[v], X, __ldg(grid + b0 + (corner & 1) * 7), __ldg(grid + cz0 + (corner >> 1) * 63), e);
             bits &= __shfl_xor_sync(0xffffffffu, bits, 1);
             bits &= __shfl_xor_sync(0xffffffffu, bits, 2);
             if (active && corner == 0 && bits == 0) atomicOr(&s_live[rg], 1u << v);
@@ -585,41 +511,26 @@ volume_agg_rowgroup_kernel(const Pair* __restrict__ feat, int nv, int H, int W, 
         __syncthreads();
     }
     const f32x2 Z[1] = {pk(__ldg(grid + c0), __ldg(grid + c0 + 32))};
-    // GATHER == 6: `feat` holds padded channels-last maps (nv, H+1, W+1, 4) instead of pixel pairs
-    const int pitch = GATHER == 6 ? W + 1 : W;
+    const int pitch = W;
     const long long map_stride = (long long)(H + 1) * pitch;
-    const bool issuer = STORE == 1 && threadIdx.y == 0 && threadIdx.x < 9;  // one plane each: 8 channels + mask
-    const CUtensorMap* my_map = threadIdx.x < 8 ? &map_vol : &map_msk;
-    const int my_ch = threadIdx.x < 8 ? threadIdx.x : 0;
 
 #pragma unroll 1
     for (int rr = 0; rr < ROWS; ++rr) {
-        const int p = WALKX ? p_first + rr : p_first, b0 = WALKX ? b_first : b_first + 8 * rr;
-        if (b0 >= D || p >= planes) break;
-        const int b = b0 + threadIdx.y;
+        const int b0 = (blockIdx.y * ROWS + rr) * 8, b = b0 + threadIdx.y;
+        if (b0 >= D) break;
         const unsigned live = s_live[rr];
-        const long long row = out_off + ((long long)p * D + b) * D + c0;
-        if (live == 0) {  // block-uniform: nothing of this tile is visible anywhere -> zeros
-            if (STORE == 1) {
-                if (issuer) {
-                    tma_store_box(my_map, smem_addr(&s_zero[0][0]), cz0, b0, plane0 + p, my_ch);
-                    bulk_commit();
-                }
-            } else if (STORE == 2) {
-                __stcs(mask_volume + row, 0.0f);
-                __stcs(mask_volume + row + 32, 0.0f);
-            } else {
+        const long long row = out_off + ((long long)blockIdx.z * D + b) * D + c0;
+        if (live == 0) {  // block-uniform: nothing of this tile is visible anywhere -> zeros (min_vis_view >= 0)
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    float* o = volume + row + 32 * j;
+            for (int j = 0; j < 2; ++j) {
+                float* o = volume + row + 32 * j;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) __stcs(o + k * channel_stride, 0.0f);
-                    __stcs(mask_volume + row + 32 * j, 0.0f);
-                }
+                for (int k = 0; k < 8; ++k) __stcs(o + k * channel_stride, 0.0f);
+                __stcs(mask_volume + row + 32 * j, 0.0f);
             }
             continue;
         }
-        const float X = __ldg(grid + a0 + p), Y = __ldg(grid + b);
+        const float Y = __ldg(grid + b);
         Acc acc[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -629,20 +540,9 @@ volume_agg_rowgroup_kernel(const Pair* __restrict__ feat, int nv, int H, int W, 
 #pragma unroll 1
         for (int v = 0; v < nv; ++v) {
             if (!((live >> v) & 1u)) continue;
-            const Pair* map = GATHER == 6 ? reinterpret_cast<const Pair*>(reinterpret_cast<const float4*>(feat) + v * map_stride)
-                                          : feat + v * map_stride;
-            if (CONSTCAM) {
-                if (c_cams[v].affine) accumulate_view<1, RECIP, true, GATHER>(c_cams[v], map, pitch, X, Y, Z, e, acc);
-                else accumulate_view<1, RECIP, false, GATHER>(c_cams[v], map, pitch, X, Y, Z, e, acc);
-                continue;
-            }
-            if (s_cam[v].affine) accumulate_view<1, RECIP, true, GATHER>(s_cam[v], map, pitch, X, Y, Z, e, acc);
-            else accumulate_view<1, RECIP, false, GATHER>(s_cam[v], map, pitch, X, Y, Z, e, acc);
-        }
-        if (STORE == 1) {
-            // the previous boxes must have left the staging buffer (they had a whole tile's arithmetic to)
-            if (issuer) bulk_wait_read_all();
-            __syncthreads();
+            const Pair* map = feat + v * map_stride;
+            if (s_cam[v].affine) accumulate_view<1, RECIP, true, 1>(s_cam[v], map, pitch, X, Y, Z, e, acc);
+            else accumulate_view<1, RECIP, false, 1>(s_cam[v], map, pitch, X, Y, Z, e, acc);
         }
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -652,41 +552,18 @@ volume_agg_rowgroup_kernel(const Pair* __restrict__ feat, int nv, int H, int W, 
             const f32x2 m_xy = div_count2(acc[j].s_xy, n, r), m_zw = div_count2(acc[j].s_zw, n, r);
             const f32x2 v_xy = sub2(div_count2(acc[j].q_xy, n, r), mul2_rounded(m_xy, m_xy));
             const f32x2 v_zw = sub2(div_count2(acc[j].q_zw, n, r), mul2_rounded(m_zw, m_zw));
-            const float mk = cnt > min_vis_view ? 1.0f : 0.0f;
-            if (STORE == 1) {
-                float* o = &s_stage[0][threadIdx.y][threadIdx.x + 32 * j];
-                o[0 * 512] = lo(m_xy); o[1 * 512] = hi(m_xy); o[2 * 512] = lo(m_zw); o[3 * 512] = hi(m_zw);
-                o[4 * 512] = lo(v_xy); o[5 * 512] = hi(v_xy); o[6 * 512] = lo(v_zw); o[7 * 512] = hi(v_zw);
-                o[8 * 512] = mk;
-            } else if (STORE == 2) {  // tuning only: results kept alive, (almost) nothing written
-                float* o = volume + row + 32 * j;
-                if (lo(m_xy) == 123.456f || hi(m_xy) == 123.456f || lo(m_zw) == 123.456f || hi(m_zw) == 123.456f ||
-                    lo(v_xy) == 123.456f || hi(v_xy) == 123.456f || lo(v_zw) == 123.456f || hi(v_zw) == 123.456f)
-                    __stcs(o, mk);
-                __stcs(mask_volume + row + 32 * j, mk);
-            } else {
-                float* o = volume + row + 32 * j;
-                __stcs(o, lo(m_xy));
-                __stcs(o + channel_stride, hi(m_xy));
-                __stcs(o + 2 * channel_stride, lo(m_zw));
-                __stcs(o + 3 * channel_stride, hi(m_zw));
-                __stcs(o + 4 * channel_stride, lo(v_xy));
-                __stcs(o + 5 * channel_stride, hi(v_xy));
-                __stcs(o + 6 * channel_stride, lo(v_zw));
-                __stcs(o + 7 * channel_stride, hi(v_zw));
-                __stcs(mask_volume + row + 32 * j, mk);
-            }
-        }
-        if (STORE == 1) {
-            fence_smem_to_async_proxy();
-            __syncthreads();
-            if (issuer) {
-                tma_store_box(my_map, smem_addr(&s_stage[threadIdx.x][0][0]), cz0, b0, plane0 + p, my_ch);
-                bulk_commit();
-            }
+            float* o = volume + row + 32 * j;
+            __stcs(o, lo(m_xy));
+            __stcs(o + channel_stride, hi(m_xy));
+            __stcs(o + 2 * channel_stride, lo(m_zw));
+            __stcs(o + 3 * channel_stride, hi(m_zw));
+            __stcs(o + 4 * channel_stride, lo(v_xy));
+            __stcs(o + 5 * channel_stride, hi(v_xy));
+            __stcs(o + 6 * channel_stride, lo(v_zw));
+            __stcs(o + 7 * channel_stride, hi(v_zw));
+            __stcs(mask_volume + row + 32 * j, cnt > min_vis_view ? 1.0f : 0.0f);
         }
     }
-    if (issuer) bulk_wait_read_all();  // shared memory must outlive the TMA's reads of it
 }
 
 // Backward w.r.t. the feature maps.  With m_v the view validity, n' the clamped count,
@@ -883,40 +760,7 @@ inline Extent extent(int W, int H) {
     return e;
 }
 
-// ---- tensor maps for the TMA store path ---------------------------------------------------------------
-// cuTensorMapEncodeTiled is a host-side encoder in libcuda; it is looked up through the runtime so that the
-// library links against cudart only (and loads on a machine without a driver, e.g. for the ABI tests).
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn tensor_map_encoder() {
-    static EncodeTiledFn fn = [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess) {
-            cudaGetLastError();
-            p = nullptr;
-        }
-        return (EncodeTiledFn)p;
-    }();
-    return fn;
-}
-
-// fp32 tensor (C, X, D, D) with `channel_stride` elements between channels, boxes of 64 (z) x 8 (y).
-bool make_plane_map(CUtensorMap* m, float* base, int D, int X, int C, long long channel_stride) {
-    EncodeTiledFn enc = tensor_map_encoder();
-    if (!enc || ((uintptr_t)base & 15) != 0) return false;
-    const cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)D, (cuuint64_t)X, (cuuint64_t)C};
-    const cuuint64_t strides[3] = {(cuuint64_t)D * 4, (cuuint64_t)D * D * 4, (cuuint64_t)channel_stride * 4};
-    const cuuint32_t box[4] = {64, 8, 1, 1}, elem[4] = {1, 1, 1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 int g_k1_variant = 0;  // tuning knob (gens_debug_set_variant); 0 = shipped configuration
-// Shipped row-group mode for D >= 128 (see launch_agg_fwd): 1 = culling + TMA box stores, 8 row-groups per block.
-#define GENS_K1_DEFAULT_RG 1
 
 inline bool bad_slab(int D, int a0, int a1, int a_base) { return a0 < 0 || a1 > D || a_base < 0 || a_base > a0; }
 
@@ -925,25 +769,6 @@ inline bool bad_slab(int D, int a0, int a1, int a_base) { return a0 < 0 || a1 > 
 extern "C" int gens_debug_set_variant(int variant) {
     g_k1_variant = variant;
     return 0;
-}
-
-// Tuning only: fills c_cams from device matrices with a synchronous round trip through the host.
-extern "C" int gens_debug_set_const_cams(const float* w2c, const float* intrs, float k_row_scale, int nv) {
-    if (nv <= 0 || nv > GENS_MAX_VIEWS) return GENS_E_BADARG;
-    float hw[GENS_MAX_VIEWS * 16], hk[GENS_MAX_VIEWS * 16];
-    if (cudaMemcpy(hw, w2c, sizeof(float) * 16 * nv, cudaMemcpyDeviceToHost) != cudaSuccess) return gens_launch_status();
-    if (cudaMemcpy(hk, intrs, sizeof(float) * 16 * nv, cudaMemcpyDeviceToHost) != cudaSuccess) return gens_launch_status();
-    Cam cams[GENS_MAX_VIEWS];
-    memset(cams, 0, sizeof(cams));
-    for (int v = 0; v < nv; ++v) {
-        for (int j = 0; j < 16; ++j) cams[v].w2c[j] = hw[16 * v + j];
-        for (int j = 0; j < 12; ++j) cams[v].k[j] = hk[16 * v + j] * (j < 8 ? k_row_scale : 1.0f);
-        const float* w = cams[v].w2c;
-        const float* k = cams[v].k;
-        cams[v].affine = w[12] == 0.f && w[13] == 0.f && w[14] == 0.f && w[15] == 1.f && k[1] == 0.f && k[3] == 0.f &&
-                         k[4] == 0.f && k[7] == 0.f && k[8] == 0.f && k[9] == 0.f && k[10] == 1.f && k[11] == 0.f;
-    }
-    return (int)cudaMemcpyToSymbol(c_cams, cams, sizeof(Cam) * nv);
 }
 
 extern "C" int gens_invert_poses(const float* poses, int n, float* poses_inv, void* stream) {
@@ -1017,9 +842,10 @@ int launch_agg_fwd(const gens_volume_scale_t& sc, int nv, const float* w2c, cons
         peers.msk[i] = i < sc.n_peers ? sc.peer_mask[i] : nullptr;
     }
     const bool to_peers = sc.n_peers > 0;
-#define GENS_AGG_ARGS \
+#define GENS_AGG_ARGS_RG \
     feat, nv, sc.H, sc.W, w2c, intrs, sc.k_row_scale, sc.grid, D, sc.a0, out_off, sc.channel_stride, min_vis_view, e, \
-        sc.volume, sc.mask_volume, peers
+        sc.volume, sc.mask_volume
+#define GENS_AGG_ARGS GENS_AGG_ARGS_RG, peers
 #define GENS_LAUNCH_PACKED(PAIRS, MINB, GATHER, ROWS)                                                              \
     do {                                                                                                         \
         const dim3 g(D / (64 * PAIRS), ceil_div_i(D, 8 * ROWS), planes);                                         \
@@ -1033,65 +859,20 @@ int launch_agg_fwd(const gens_volume_scale_t& sc, int nv, const float* w2c, cons
             volume_agg_packed_kernel<PAIRS, false, MINB, GATHER, ROWS><<<g, block, 0, st>>>(GENS_AGG_ARGS);       \
     } while (0)
     const int variant = g_k1_variant;
-    // Row-group kernel (culling + TMA box stores): one destination, D a multiple of 64, a mask threshold that
-    // leaves unseen voxels at 0, and an output the tensor-map encoder accepts.  Variants 20-29 select its
-    // store path / rows per block for tuning; 10 forces the packed kernel below.
-    const int rg_mode = variant >= 20 && variant < 100 ? variant - 20 : (variant == 0 && D >= 128 ? GENS_K1_DEFAULT_RG : -1);
-    if (rg_mode >= 0 && !to_peers && D % 64 == 0 && min_vis_view >= 0 && sc.channel_stride % ((long long)D * D) == 0) {
-        const int X = sc.a1 - sc.a_base, plane0 = sc.a0 - sc.a_base;
-        CUtensorMap map_vol, map_msk;
-        const bool tma = rg_mode != 0 && rg_mode != 5 && (rg_mode < 10 || rg_mode == 16) && make_plane_map(&map_vol, sc.volume, D, X, 8, sc.channel_stride) &&
-                         make_plane_map(&map_msk, sc.mask_volume, D, X, 1, (long long)X * D * D);
-        if (!tma) {
-            memset(&map_vol, 0, sizeof(map_vol));
-            memset(&map_msk, 0, sizeof(map_msk));
+    // Row-group kernel (frustum culling): one destination, D >= 256 and a multiple of 64 (smaller volumes are
+    // a single wave of blocks, where the per-block culling prologue costs more than it saves: 128^3 35.6 us
+    // packed vs 37.8 us culled), and a mask threshold that leaves unseen voxels at 0.  Tuning knob: 10 forces
+    // the packed kernel, 20 / 25 the row-group kernel with / without culling at any D % 64 == 0.
+    const bool rg = variant == 20 || variant == 25 || (variant == 0 && D >= 256);
+    if (rg && !to_peers && D % 64 == 0 && min_vis_view >= 0) {
+        const dim3 g(D / 64, ceil_div_i(D, 64), planes);
+        if (variant == 25) {
+            if (recip) volume_agg_rowgroup_kernel<true, 8, false><<<g, block, 0, st>>>(GENS_AGG_ARGS_RG);
+            else volume_agg_rowgroup_kernel<false, 8, false><<<g, block, 0, st>>>(GENS_AGG_ARGS_RG);
+        } else {
+            if (recip) volume_agg_rowgroup_kernel<true, 8, true><<<g, block, 0, st>>>(GENS_AGG_ARGS_RG);
+            else volume_agg_rowgroup_kernel<false, 8, true><<<g, block, 0, st>>>(GENS_AGG_ARGS_RG);
         }
-#define GENS_LAUNCH_RG(ROWS, STORE, CULL, WALKX, ...)                                                                 \
-    do {                                                                                                          \
-        const dim3 g(D / 64, WALKX ? D / 8 : ceil_div_i(D, 8 * ROWS), WALKX ? ceil_div_i(planes, ROWS) : planes); \
-        if (recip)                                                                                                \
-            volume_agg_rowgroup_kernel<true, ROWS, STORE, CULL, WALKX, ##__VA_ARGS__><<<g, block, 0, st>>>(GENS_AGG_ARGS_RG);     \
-        else                                                                                                      \
-            volume_agg_rowgroup_kernel<false, ROWS, STORE, CULL, WALKX, ##__VA_ARGS__><<<g, block, 0, st>>>(GENS_AGG_ARGS_RG);    \
-    } while (0)
-#define GENS_AGG_ARGS_RG \
-    feat, nv, sc.H, sc.W, w2c, intrs, sc.k_row_scale, sc.grid, D, sc.a0, planes, out_off, sc.channel_stride, min_vis_view, e, \
-        sc.volume, sc.mask_volume, plane0, map_vol, map_msk
-        switch (tma ? rg_mode : (rg_mode == 5 || (rg_mode >= 10 && rg_mode != 16) ? rg_mode : rg_mode == 16 ? 10 : 0)) {
-            case 5: GENS_LAUNCH_RG(8, 0, false, false); break;  // packed arithmetic, no culling (A/B reference)
-            case 0: GENS_LAUNCH_RG(8, 0, true, false); break;
-            case 2: GENS_LAUNCH_RG(4, 1, true, false); break;
-            case 3: GENS_LAUNCH_RG(2, 1, true, false); break;
-            case 4: GENS_LAUNCH_RG(16, 1, true, false); break;
-            case 6: GENS_LAUNCH_RG(8, 1, false, false); break;  // TMA stores without culling
-            case 7: GENS_LAUNCH_RG(1, 1, true, false); break;
-            case 10: GENS_LAUNCH_RG(8, 0, true, true); break;   // walk x, streaming stores
-            case 11: GENS_LAUNCH_RG(4, 0, true, true); break;
-            case 12: GENS_LAUNCH_RG(16, 0, true, true); break;
-            case 13: GENS_LAUNCH_RG(32, 0, true, true); break;
-            case 14: GENS_LAUNCH_RG(8, 0, false, true); break;  // walk x without culling
-            case 15: GENS_LAUNCH_RG(8, 0, true, true, 0); break;  // walk x, both voxels' gathers in flight
-            case 16: GENS_LAUNCH_RG(8, 1, true, true); break;     // walk x, TMA stores
-            case 43: GENS_LAUNCH_RG(8, 0, true, false, 5, 3); break;  // both voxels' gathers in flight, 3 blocks / SM
-            case 44: GENS_LAUNCH_RG(8, 0, true, false, 1, 3); break;
-            case 45: GENS_LAUNCH_RG(8, 0, true, false, 5, 4); break;
-            case 54: GENS_LAUNCH_RG(2, 0, true, false); break;
-            case 55: GENS_LAUNCH_RG(4, 0, true, false); break;
-            case 56: GENS_LAUNCH_RG(1, 0, true, false); break;
-            case 53: GENS_LAUNCH_RG(8, 0, true, false, 1, 4, true); break;  // tuning: cameras from the constant bank
-            case 50: GENS_LAUNCH_RG(8, 0, true, false, 6); break;  // padded channels-last maps (nv,H+1,W+1,4), walk y
-            case 51: GENS_LAUNCH_RG(8, 0, true, true, 6); break;   // same, walk x
-            case 52: GENS_LAUNCH_RG(8, 2, true, false, 6); break;  // tuning: same without result stores
-            case 40: GENS_LAUNCH_RG(8, 2, true, false); break;     // tuning: no result stores
-            case 41: GENS_LAUNCH_RG(8, 0, true, false, 4); break;  // tuning: no gathers
-            case 42: GENS_LAUNCH_RG(8, 2, true, false, 4); break;  // tuning: arithmetic only
-            case 19: GENS_LAUNCH_RG(8, 0, true, false, 3); break;  // walk y, L1 prefetch of the second voxel
-            case 17: GENS_LAUNCH_RG(8, 0, true, false, 2); break;  // walk y, 128-bit gathers
-            case 18: GENS_LAUNCH_RG(8, 0, true, true, 2); break;   // walk x, 128-bit gathers
-            default: GENS_LAUNCH_RG(8, 1, true, false); break;
-        }
-#undef GENS_LAUNCH_RG
-#undef GENS_AGG_ARGS_RG
         return gens_launch_status();
     }
     // rows per block: enough to amortise the camera staging, few enough to keep >= ~4 waves of blocks
@@ -1112,6 +893,7 @@ int launch_agg_fwd(const gens_volume_scale_t& sc, int nv, const float* w2c, cons
     }
 #undef GENS_LAUNCH_PACKED
 #undef GENS_AGG_ARGS
+#undef GENS_AGG_ARGS_RG
     return gens_launch_status();
 }
 

@@ -363,20 +363,28 @@ class ImplicitSurface(nn.Module):
 
     # ---------------------------------------------------------------------- geometry / driver
     @torch.no_grad()
-    def sdf_grid(self, volumes, bound_min, bound_max, resolution, block: int = 128, out=None):
+    def sdf_grid(self, volumes, bound_min, bound_max, resolution, block: int = 128, out=None, x_range=None):
         """u[x,y,z] = -sdf on a resolution^3 lattice (the loop of reference :407-421), evaluated in
-        `block`^3 chunks that stay on the device; returns a float32 CUDA tensor."""
+        `block`^3 chunks that stay on the device; returns a float32 CUDA tensor.  `x_range` = (x0, x1)
+        evaluates only that slab of lattice planes (multi-GPU sharding, parallel.sharded_sdf_grid) and
+        returns (x1 - x0, resolution, resolution); the lattice coordinates are those of the full grid."""
         dev = bound_min.device
         axes = [torch.linspace(float(bound_min[k]), float(bound_max[k]), resolution, device=dev) for k in range(3)]
-        u = torch.empty((resolution,) * 3, device=dev, dtype=torch.float32) if out is None else out
+        xa, xb = (0, resolution) if x_range is None else (int(x_range[0]), int(x_range[1]))
+        if not 0 <= xa <= xb <= resolution:
+            raise RuntimeError(f"x_range {x_range} outside the lattice [0, {resolution}]")
+        shape = (xb - xa, resolution, resolution)
+        u = torch.empty(shape, device=dev, dtype=torch.float32) if out is None else out
+        if tuple(u.shape) != shape:
+            raise RuntimeError(f"sdf_grid output must be {shape}, got {tuple(u.shape)}")
         folded = self._fold_sdf()
-        for x0 in range(0, resolution, block):
+        for x0 in range(xa, xb, block):
             for y0 in range(0, resolution, block):
                 for z0 in range(0, resolution, block):
-                    xs, ys, zs = axes[0][x0:x0 + block], axes[1][y0:y0 + block], axes[2][z0:z0 + block]
+                    xs, ys, zs = axes[0][x0:min(x0 + block, xb)], axes[1][y0:y0 + block], axes[2][z0:z0 + block]
                     pts = torch.stack(torch.meshgrid(xs, ys, zs, indexing="ij"), -1).reshape(-1, 3)
                     val = self.sdf_network.sdf_nograd(pts, volumes, folded).reshape(len(xs), len(ys), len(zs))
-                    u[x0:x0 + len(xs), y0:y0 + len(ys), z0:z0 + len(zs)] = -val
+                    u[x0 - xa:x0 - xa + len(xs), y0:y0 + len(ys), z0:z0 + len(zs)] = -val
         return u
 
     def extract_geometry(self, volumes, bound_min, bound_max, resolution, threshold):

@@ -10,7 +10,7 @@ The reference has neither (it is data-parallel over scenes only, runner.py:104).
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -173,3 +173,29 @@ def gather_rays(local: torch.Tensor, n_total: int, rank: int, world: int, group=
         return local
     sizes = [shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world)]
     return torch.cat(_all_gather_rows(local, sizes, group), dim=0)
+
+
+def sharded_sdf_grid(sdf_grid_fn, resolution: int, rank: int, world: int, group=None, dst: Optional[int] = 0):
+    """The mesh-extraction lattice (reference implicit_surface.py:407-421) sharded by
+    x-slabs: rank r evaluates planes shard_range(resolution, r, world) with
+    `sdf_grid_fn(x_range) -> (x1 - x0, resolution, resolution)` (ImplicitSurface.sdf_grid bound to its
+    volumes) -- points are independent, so there is no collective during compute -- and the slabs are then
+    gathered: on rank `dst` only (the rank that runs marching cubes; the others get None) or, with
+    dst=None, on every rank.  Bit-identical to the single-GPU lattice: a point's value does not depend on
+    which rank evaluates it."""
+    x0, x1 = shard_range(resolution, rank, world)
+    local = sdf_grid_fn((x0, x1))
+    if tuple(local.shape) != (x1 - x0, resolution, resolution):
+        raise RuntimeError(f"sdf_grid_fn returned {tuple(local.shape)} for x_range {(x0, x1)}")
+    if world == 1:
+        return local
+    sizes = [shard_range(resolution, r, world)[1] - shard_range(resolution, r, world)[0] for r in range(world)]
+    if dst is None:
+        return torch.cat(_all_gather_rows(local.contiguous(), sizes, group), dim=0)
+    top = max(sizes)  # equal-sized messages for every backend: pad the short shards, trim after the gather
+    send = local.contiguous()
+    if send.shape[0] < top:
+        send = torch.cat([send, send.new_zeros((top - send.shape[0], resolution, resolution))], dim=0)
+    outs = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+    dist.gather(send, outs, dst=dst, group=group)
+    return torch.cat([o[:n] for o, n in zip(outs, sizes)], dim=0) if rank == dst else None

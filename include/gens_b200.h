@@ -339,8 +339,6 @@ int gens_tv_reduce(const gens_pyramid_t *vols, const gens_pyramid_t *masks, int 
 /* Tuning knob for profiling sessions: selects among compiled-in launch configurations of K1
  * (0 = the shipped one).  Results are identical for every variant. */
 int gens_debug_set_variant(int variant);
-/* tuning only: camera block of K1's constant-bank variant (synchronous) */
-int gens_debug_set_const_cams(const float *w2c, const float *intrs, float k_row_scale, int nv);
 
 /* Device self-test of the exact-division shortcuts K1 uses (tests only): [0] = mismatches of
  * the count division s/n (every fp32 s, n = 1..max_n) and [1] = mismatches of the shared-

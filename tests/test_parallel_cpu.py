@@ -53,6 +53,19 @@ def _worker(rank, world, port, golden_dir, out_q):
         rays = torch.arange(n, dtype=torch.float32)[:, None].repeat(1, 3)
         got = parallel.gather_rays(rays[lo:hi] * 2, n, rank, world)
         ok &= torch.equal(got, rays * 2)
+        # mesh-extraction lattice sharded by x-slabs (config 5): a stub evaluator stands in for the CUDA MLP
+        res = 21  # not divisible by the world size: shards differ by one plane
+        lattice = torch.arange(res ** 3, dtype=torch.float32).reshape(res, res, res).sin()
+        calls = []
+
+        def sdf_grid_fn(x_range):
+            calls.append(tuple(x_range))
+            return lattice[x_range[0]:x_range[1]].clone()
+        on_dst = parallel.sharded_sdf_grid(sdf_grid_fn, res, rank, world, dst=0)
+        ok &= calls == [parallel.shard_range(res, rank, world)]
+        ok &= (on_dst is None) if rank != 0 else torch.equal(on_dst, lattice)
+        everywhere = parallel.sharded_sdf_grid(sdf_grid_fn, res, rank, world, dst=None)
+        ok &= torch.equal(everywhere, lattice)
         out_q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

@@ -114,3 +114,9 @@ def test_validate_forward_and_sdf_grid_drivers(cuda_lib):
         pts = torch.stack(torch.meshgrid(axes, axes, axes, indexing="ij"), -1).reshape(-1, 3)
         direct = -surf.sdf_network.sdf_nograd(pts, vols).reshape(40, 40, 40)
         assert torch.allclose(u, direct, rtol=1e-4, atol=1e-5)
+        # x-slabs of the lattice (the multi-GPU sharding of config 5) re-assemble the full lattice bit for bit
+        from gens_b200 import parallel
+        slabs = [surf.sdf_grid(vols, ipts["bound_min"], ipts["bound_max"], 40, block=16,
+                               x_range=parallel.shard_range(40, r, 3)) for r in range(3)]
+        assert [s.shape[0] for s in slabs] == [13, 13, 14]
+        assert torch.equal(torch.cat(slabs, 0), u)
