@@ -100,6 +100,26 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+    fd 1 when the box sets NCCL_DEBUG=VERSION), so fd 1 is pointed at stderr for the whole run and the JSON line
+    goes to a private duplicate of the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def dist_setup(n_gpus: int):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -235,7 +255,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": render, "e2e": {"value": render["value"], "unit": "ray-samples/s",
                                             "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------- our arm
@@ -441,7 +461,7 @@ def run_ours(args, rank, world, local):
                      "traffic_source": "profiles/r01_k1_256_kernel.txt (ncu --set full: dram__bytes_read.sum + "
                                        "dram__bytes_write.sum of one launch; the tail of the writes is still in L2 "
                                        "when the kernel ends, hence below the algorithmic bytes)",
-                     "kernel": "volume_agg_packed_kernel @ 256^3", "ms": k1_ms,
+                     "kernel": "volume_agg_rowgroup_kernel @ 256^3", "ms": k1_ms,
                      "algorithmic_bytes": abytes, "peak_source": f"MEASURED_PEAKS.json ({peak_kind}, burst copy)"},
         "cpu_baseline": cpu,
         "e2e": None if e2e_ms is None else {"value": vv / (e2e_ms * 1e-3), "unit": "voxel*views/s",
@@ -451,7 +471,7 @@ def run_ours(args, rank, world, local):
         "clocks": clk,
         "render": render,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -468,6 +488,7 @@ def main():
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N > 1: slab exchange fused into K1's stores (NVLink peer memory) or NCCL all-gather + scatter")
     args = ap.parse_args()
+    claim_stdout()
     rank, world, local = dist_setup(args.gpus)
     if args.impl == "reference":
         args.warmup = min(args.warmup, 2)  # each step is a full 3-5 s CPU build

@@ -761,13 +761,15 @@ inline Extent extent(int W, int H) {
 }
 
 int g_k1_variant = 0;  // tuning knob (gens_debug_set_variant); 0 = shipped configuration
+int g_k1_sched = 3;    // build-level scheduling knob (gens_debug_set_variant(100 + s)), see gens_volume_agg_fwd_multi
 
 inline bool bad_slab(int D, int a0, int a1, int a_base) { return a0 < 0 || a1 > D || a_base < 0 || a_base > a0; }
 
 }  // namespace
 
 extern "C" int gens_debug_set_variant(int variant) {
-    g_k1_variant = variant;
+    if (variant >= 100) g_k1_sched = variant - 100;
+    else g_k1_variant = variant;
     return 0;
 }
 
@@ -900,12 +902,17 @@ int launch_agg_fwd(const gens_volume_scale_t& sc, int nv, const float* w2c, cons
 }  // namespace
 
 namespace {
-// One auxiliary stream per device: the small scales of a build run beside the largest one instead of
-// behind it (their launch latencies and tails disappear into the big kernel).  Fork/join with events, so
-// the work is still ordered entirely by the caller's stream (and capturable in a CUDA graph).
+// Auxiliary streams per device: the small scales of a build run beside the largest one instead of behind it
+// (their launch latencies and tails disappear into the big kernel).  Fork/join with events, so the work is
+// still ordered entirely by the caller's stream (and capturable in a CUDA graph).  Measured through bench.py
+// (5-scale build, 480x640, 3 views): no fork 259-289 us; big kernel first + one auxiliary stream 248 us; big
+// first + one stream per small scale 234 us; small scales first, one stream each, big kernel last 227 us
+// (shipped: the block scheduler drains the kernels in launch order, so the short ones must be ahead of the
+// 4096-block launch to run inside it rather than in its tail).
+constexpr int kAuxStreams = 4;
 struct Fork {
-    cudaStream_t aux = nullptr;
-    cudaEvent_t forked = nullptr, joined = nullptr;
+    cudaStream_t aux[kAuxStreams] = {};
+    cudaEvent_t forked = nullptr, joined[kAuxStreams] = {};
     bool ok = false, tried = false;
 };
 std::mutex g_fork_mutex;
@@ -917,13 +924,15 @@ Fork* fork_for_current_device() {
     Fork& f = g_forks[dev];
     if (!f.tried) {
         f.tried = true;
-        f.ok = cudaStreamCreateWithFlags(&f.aux, cudaStreamNonBlocking) == cudaSuccess &&
-               cudaEventCreateWithFlags(&f.forked, cudaEventDisableTiming) == cudaSuccess &&
-               cudaEventCreateWithFlags(&f.joined, cudaEventDisableTiming) == cudaSuccess;
+        f.ok = cudaEventCreateWithFlags(&f.forked, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < kAuxStreams && f.ok; ++i)
+            f.ok = cudaStreamCreateWithFlags(&f.aux[i], cudaStreamNonBlocking) == cudaSuccess &&
+                   cudaEventCreateWithFlags(&f.joined[i], cudaEventDisableTiming) == cudaSuccess;
         if (!f.ok) cudaGetLastError();
     }
     return f.ok ? &f : nullptr;
 }
+
 }  // namespace
 
 extern "C" int gens_volume_agg_fwd_multi(const gens_volume_scale_t* scales, int n_scales, int nv, const float* w2c,
@@ -935,20 +944,32 @@ extern "C" int gens_volume_agg_fwd_multi(const gens_volume_scale_t* scales, int 
     for (int i = 1; i < n_scales; ++i)
         if (scales[i].D > scales[big].D) big = i;
     std::lock_guard<std::mutex> lock(g_fork_mutex);
-    Fork* f = n_scales > 1 && g_k1_variant != 7 ? fork_for_current_device() : nullptr;
-    if (f && (cudaEventRecord(f->forked, st) != cudaSuccess || cudaStreamWaitEvent(f->aux, f->forked, 0) != cudaSuccess)) {
-        cudaGetLastError();
-        f = nullptr;
+    const int sched = g_k1_sched;
+    // sched 3 (shipped): the small scales first, round-robin over the auxiliary streams, the big one last on `st`;
+    // 0: big first, the rest in order on one auxiliary stream; 1: the rest first on one stream; 2: like 3 but big
+    // first; 7: no fork
+    Fork* f = n_scales > 1 && g_k1_variant != 7 && sched != 7 ? fork_for_current_device() : nullptr;
+    const int n_aux = sched >= 2 ? kAuxStreams : 1;
+    if (f) {
+        bool ok = cudaEventRecord(f->forked, st) == cudaSuccess;
+        for (int i = 0; i < n_aux && ok; ++i) ok = cudaStreamWaitEvent(f->aux[i], f->forked, 0) == cudaSuccess;
+        if (!ok) {
+            cudaGetLastError();
+            f = nullptr;
+        }
     }
     int rc = 0;
     if (f) {
-        // largest scale on the caller's stream, the rest beside it
-        rc = launch_agg_fwd(scales[big], nv, w2c, intrs, min_vis_view, div_mode, st);
+        const bool big_first = sched == 0 || sched == 2;
+        if (big_first) rc = launch_agg_fwd(scales[big], nv, w2c, intrs, min_vis_view, div_mode, st);
+        int k = 0;
         for (int i = 0; i < n_scales && rc == 0; ++i)
-            if (i != big) rc = launch_agg_fwd(scales[i], nv, w2c, intrs, min_vis_view, div_mode, f->aux);
-        // always join, even after an error, so the auxiliary stream never outlives the call's ordering
-        if (cudaEventRecord(f->joined, f->aux) != cudaSuccess || cudaStreamWaitEvent(st, f->joined, 0) != cudaSuccess)
-            return rc != 0 ? rc : gens_launch_status();
+            if (i != big) rc = launch_agg_fwd(scales[i], nv, w2c, intrs, min_vis_view, div_mode, f->aux[k++ % n_aux]);
+        if (!big_first && rc == 0) rc = launch_agg_fwd(scales[big], nv, w2c, intrs, min_vis_view, div_mode, st);
+        // always join, even after an error, so the auxiliary streams never outlive the call's ordering
+        for (int i = 0; i < n_aux; ++i)
+            if (cudaEventRecord(f->joined[i], f->aux[i]) != cudaSuccess || cudaStreamWaitEvent(st, f->joined[i], 0) != cudaSuccess)
+                return rc != 0 ? rc : gens_launch_status();
         return rc;
     }
     for (int i = 0; i < n_scales; ++i) {
