@@ -337,7 +337,10 @@ int gens_tv_reduce(const gens_pyramid_t *vols, const gens_pyramid_t *masks, int 
                    double *out, void *stream);
 
 /* Tuning knob for profiling sessions: selects among compiled-in launch configurations of K1
- * (0 = the shipped one).  Results are identical for every variant. */
+ * (0 = the shipped one; 10 = packed kernel at every D % 64 == 0, 20 / 25 = row-group kernel with / without
+ * frustum culling, 1/2/4/8/16 = rows per block of the packed kernel, 9 = scalar kernel, 7 = no stream fork)
+ * and, with 100 + s, the build-level launch order (s = 3 shipped: small scales first on their own streams;
+ * 0 = largest first + one auxiliary stream, 7 = no fork).  Results are identical for every variant. */
 int gens_debug_set_variant(int variant);
 
 /* Device self-test of the exact-division shortcuts K1 uses (tests only): [0] = mismatches of
