@@ -462,7 +462,10 @@ def run_ours(args, rank, world, local):
                                        "dram__bytes_write.sum of one launch; the tail of the writes is still in L2 "
                                        "when the kernel ends, hence below the algorithmic bytes)",
                      "kernel": "volume_agg_rowgroup_kernel @ 256^3", "ms": k1_ms,
-                     "algorithmic_bytes": abytes, "peak_source": f"MEASURED_PEAKS.json ({peak_kind}, burst copy)"},
+                     "algorithmic_bytes": abytes, "peak_source": f"MEASURED_PEAKS.json ({peak_kind}, burst copy)",
+                     "limiter": "SM L1 data pipe (72 % busy avg / 79 % max under ncu: STG at 32 B/clk/SM + LDG.256 "
+                                "returns + camera LDS) on top of 108 us of arithmetic; the same store pattern alone "
+                                "runs at 6.5 TB/s (profiles/r01_k1_variant_sweep.txt, r01_ubench_planes.txt)"},
         "cpu_baseline": cpu,
         "e2e": None if e2e_ms is None else {"value": vv / (e2e_ms * 1e-3), "unit": "voxel*views/s",
                                             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
