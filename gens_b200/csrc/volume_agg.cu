@@ -290,8 +290,11 @@ struct Corner4 {
 };
 
 __device__ __forceinline__ Corner4 gather4(const Pair* __restrict__ map, int pitch, int x0, int y0) {
-    const Pair* p = map + (y0 * pitch + x0);
-    const Pair top = ldg256(p), bot = ldg256(p + pitch);
+    // 32-bit texel indices scaled onto a per-view base held in a register pair: one IMAD.WIDE per address
+    // instead of a sign extension, a 64-bit add of the view offset and a 64-bit shift-add (launch_agg_fwd
+    // bounds the map size so that the index fits).
+    const unsigned i = (unsigned)(y0 * pitch + x0);
+    const Pair top = ldg256(map + i), bot = ldg256(map + (i + (unsigned)pitch));
     Corner4 c;
     c.nw = top.a;
     c.ne = top.b;
@@ -324,6 +327,9 @@ template <int PAIRS, bool RECIP, bool AFFINE, int GATHER>
 __device__ __forceinline__ void accumulate_view(const Cam& cam, const Pair* __restrict__ map, int pitch,
                                                 float X, float Y, const f32x2 (&Z)[PAIRS], const Extent& e,
                                                 Acc (&acc)[2 * PAIRS]) {
+    // keep the view's base pointer in a register pair: otherwise ptxas folds the (uniform) view offset into every
+    // address as a 64-bit add + shift-add, six integer instructions per gather instead of two
+    asm("" : "+l"(map));
     float pre[4];
 #pragma unroll
     for (int r = 0; r < (AFFINE ? 3 : 4); ++r)
@@ -477,6 +483,13 @@ __device__ __forceinline__ unsigned cull_planes(const Cam& cam, float X, float Y
 
 // A block owns ROWS tiles of 8 rows (y) x 64 voxels (z) of one x plane.  CULL = false keeps every tile-view
 // (A/B reference for the culling, variant 25 of the tuning knob).
+// o + stride as ONE 64-bit add the compiler cannot turn back into (base + k * stride) multiplies
+__device__ __forceinline__ float* next_plane(float* o, long long stride_elems) {
+    float* n = o + stride_elems;
+    asm("" : "+l"(n));
+    return n;
+}
+
 template <bool RECIP, int ROWS, bool CULL>
 __global__ void __launch_bounds__(256, 4)
 volume_agg_rowgroup_kernel(const Pair* __restrict__ feat, int nv, int H, int W, const float* __restrict__ w2c,
@@ -514,20 +527,27 @@ volume_agg_rowgroup_kernel(const Pair* __restrict__ feat, int nv, int H, int W, 
     const int pitch = W;
     const long long map_stride = (long long)(H + 1) * pitch;
 
+    // running output pointers of this thread's voxel pair (plane 0 of the volume, and the mask): one 64-bit add per
+    // tile instead of rebuilding ((x * D + y) * D + z) and nine channel offsets from scratch
+    const long long first = out_off + ((long long)blockIdx.z * D + (blockIdx.y * ROWS * 8 + threadIdx.y)) * D + c0;
+    float* vol_row = volume + first;
+    float* msk_row = mask_volume + first;
+    const long long tile_step = 8LL * D;
 #pragma unroll 1
-    for (int rr = 0; rr < ROWS; ++rr) {
+    for (int rr = 0; rr < ROWS; ++rr, vol_row += tile_step, msk_row += tile_step) {
         const int b0 = (blockIdx.y * ROWS + rr) * 8, b = b0 + threadIdx.y;
         if (b0 >= D) break;
         const unsigned live = s_live[rr];
-        const long long row = out_off + ((long long)blockIdx.z * D + b) * D + c0;
         if (live == 0) {  // block-uniform: nothing of this tile is visible anywhere -> zeros (min_vis_view >= 0)
+            float* o = vol_row;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                float* o = volume + row + 32 * j;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) __stcs(o + k * channel_stride, 0.0f);
-                __stcs(mask_volume + row + 32 * j, 0.0f);
+            for (int k = 0; k < 8; ++k) {
+                __stcs(o, 0.0f);
+                __stcs(o + 32, 0.0f);
+                o = next_plane(o, channel_stride);
             }
+            __stcs(msk_row, 0.0f);
+            __stcs(msk_row + 32, 0.0f);
             continue;
         }
         const float Y = __ldg(grid + b);
@@ -544,6 +564,7 @@ volume_agg_rowgroup_kernel(const Pair* __restrict__ feat, int nv, int H, int W, 
             if (s_cam[v].affine) accumulate_view<1, RECIP, true, 1>(s_cam[v], map, pitch, X, Y, Z, e, acc);
             else accumulate_view<1, RECIP, false, 1>(s_cam[v], map, pitch, X, Y, Z, e, acc);
         }
+        float res[2][9];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int cnt = acc[j].cnt;
@@ -552,17 +573,20 @@ volume_agg_rowgroup_kernel(const Pair* __restrict__ feat, int nv, int H, int W, 
             const f32x2 m_xy = div_count2(acc[j].s_xy, n, r), m_zw = div_count2(acc[j].s_zw, n, r);
             const f32x2 v_xy = sub2(div_count2(acc[j].q_xy, n, r), mul2_rounded(m_xy, m_xy));
             const f32x2 v_zw = sub2(div_count2(acc[j].q_zw, n, r), mul2_rounded(m_zw, m_zw));
-            float* o = volume + row + 32 * j;
-            __stcs(o, lo(m_xy));
-            __stcs(o + channel_stride, hi(m_xy));
-            __stcs(o + 2 * channel_stride, lo(m_zw));
-            __stcs(o + 3 * channel_stride, hi(m_zw));
-            __stcs(o + 4 * channel_stride, lo(v_xy));
-            __stcs(o + 5 * channel_stride, hi(v_xy));
-            __stcs(o + 6 * channel_stride, lo(v_zw));
-            __stcs(o + 7 * channel_stride, hi(v_zw));
-            __stcs(mask_volume + row + 32 * j, cnt > min_vis_view ? 1.0f : 0.0f);
+            res[j][0] = lo(m_xy); res[j][1] = hi(m_xy); res[j][2] = lo(m_zw); res[j][3] = hi(m_zw);
+            res[j][4] = lo(v_xy); res[j][5] = hi(v_xy); res[j][6] = lo(v_zw); res[j][7] = hi(v_zw);
+            res[j][8] = cnt > min_vis_view ? 1.0f : 0.0f;
         }
+        // plane after plane: one 64-bit pointer bump per channel, both voxels of the pair off the same register
+        float* o = vol_row;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            __stcs(o, res[0][k]);
+            __stcs(o + 32, res[1][k]);
+            o = next_plane(o, channel_stride);
+        }
+        __stcs(msk_row, res[0][8]);
+        __stcs(msk_row + 32, res[1][8]);
     }
 }
 
