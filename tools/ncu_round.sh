@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -25 gpurun_out/pytest_gpu.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:volume_agg_packed -s 3 -c 1 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'volume_agg_(rowgroup|packed)' -s 3 -c 1 \
   -f -o gpurun_out/r01_k1_256 python tools/sweep_k1.py 3 0 > gpurun_out/ncu_k1.log 2>&1
 echo "ncu k1 exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on \
