@@ -316,3 +316,17 @@ def test_k8_patch_warp_kernel_matches_aten_path(setup):
     _check("K8 reference patch", ref_k, ref_t.detach().cpu().numpy(), **GRAY)
     _check("K8 warped patches", src_k, src_t.detach().cpu().numpy(), **GRAY)
     assert float((src_k != 0).float().mean()) > 0.3     # not vacuous: most warped samples land inside the images
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs of one node")
+def test_sharded_lattice_and_ray_sharding_two_gpus():
+    """SURVEY 8e rows 2-3 over NCCL: x-slabs of the SDF lattice and contiguous ray shards re-assemble to what one
+    GPU computes (tools/check_sharded_render.py under torchrun, world size 2)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29537", "tools/check_sharded_render.py"],
+                       cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("sharded lattice bit-identical to the 1-GPU lattice: True") == 2, r.stdout[-2000:]
+    assert r.stdout.count("ray-sharded render matches the 1-GPU render: True") == 2, r.stdout[-2000:]
