@@ -218,6 +218,34 @@ def cpu_render_baseline(nv, n_rays=2048, dims=(64, 32, 16, 8, 4)):
                       f"of ImplicitSurface.render on host tensors, all host threads)", "ms": dt * 1e3}
 
 
+def gpu_render_baseline(dev, sc, vols, masks, n_rays=2048):
+    """SURVEY 8d "GPU reference baseline": the reference's op sequence (ATen ops, autograd second-order term, 256-ray
+    chunks as its validate()) on THIS GPU -- the product's host logic with the oracle's ATen look-ups plugged in
+    (oracle/torch_oracle.CpuOps is device-agnostic), on the bench's own volumes and a bounded sample of its rays."""
+    from oracle import torch_oracle
+    surf = build_surface(dev, ops=torch_oracle.CpuOps)
+    ro, rd = sc.rays(step=1)
+    sel = torch.arange(0, ro.shape[0], ro.shape[0] // n_rays, device=ro.device)[:n_rays]
+    ro, rd = ro[sel].to(dev).contiguous(), rd[sel].to(dev).contiguous()
+
+    def run(o, d):
+        # as the reference's validate(): under no_grad, the SDF gradient re-enables autograd (sdf_network.py:131)
+        with torch.no_grad():
+            for a in range(0, o.shape[0], 256):
+                r = surf.render(o[a:a + 256], d[a:a + 256], sc.near, sc.far, vols, masks, sc.imgs, sc.features,
+                                sc.features, sc.intrs, sc.c2ws, 1.0, None)
+                del r
+    run(ro[:256], rd[:256])
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); run(ro, rd); b.record()
+    torch.cuda.synchronize(dev)
+    ms = a.elapsed_time(b)
+    return {"value": n_rays * 128 / (ms * 1e-3), "unit": "ray-samples/s", "ms": ms,
+            "sample": f"{n_rays} rays x 128 samples in 256-ray chunks through the bench's volumes {DIMS}: the reference's "
+                      "ATen op sequence + autograd gradients on this GPU (oracle/torch_oracle ops; host-launch bound)"}
+
+
 # --------------------------------------------------------------------------- reference arm
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path: the same ATen op sequence as
@@ -321,6 +349,7 @@ def bench_render(args, rank, world, dev, sc, host, vol_mod, timed):
                                                 "(307 MB) are read through L2, compulsory HBM bytes are far fewer"}
         if rank == 0 and not args.no_cpu:
             res["cpu_baseline"] = cpu_render_baseline(args.nv)
+            res["reference_ops_on_gpu"] = gpu_render_baseline(dev, sc, vols, masks)
     return res
 
 
@@ -440,6 +469,18 @@ def run_ours(args, rank, world, local):
                "sample": "full 5-scale build, best of 2 after 1 warm-up (ATen-op restatement of volume.py, "
                          "all host threads)", "ms": best * 1e3}
 
+    ref_gpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        # SURVEY 8d "GPU reference baseline": the reference's op sequence (volume.py as ~320 ATen ops per scale) on
+        # THIS GPU, same inputs, L2 flushed, CUDA events
+        from oracle import torch_oracle
+        with torch.no_grad():
+            r_ms, _ = timed(lambda: torch_oracle.agg_mean_var(sc.features, sc.intrs, sc.c2ws, DIMS), 3, 2)
+        ref_gpu = {"value": voxel_views(nv) / (r_ms * 1e-3), "unit": "voxel*views/s", "ms": r_ms,
+                   "sample": "full 5-scale build, 3 steps after 2 warm-ups: the reference's ATen op sequence on this GPU "
+                             "(oracle/torch_oracle.agg_mean_var)"}
+        torch.cuda.empty_cache()
+
     if rank != 0:
         return
     peak, peak_kind = measured_peak_gbs()
@@ -467,6 +508,7 @@ def run_ours(args, rank, world, local):
                                 "returns + camera LDS) on top of 108 us of arithmetic; the same store pattern alone "
                                 "runs at 6.5 TB/s (profiles/r01_k1_variant_sweep.txt, r01_ubench_planes.txt)"},
         "cpu_baseline": cpu,
+        "reference_ops_on_gpu": ref_gpu,
         "e2e": None if e2e_ms is None else {"value": vv / (e2e_ms * 1e-3), "unit": "voxel*views/s",
                                             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                             "ms_per_step": e2e_ms},
