@@ -314,6 +314,18 @@ def bench_render(args, rank, world, dev, sc, host, vol_mod, timed):
            "sharding": "none" if world == 1 else f"contiguous ray ranges over {world} ranks + final gather",
            "gpu_launches_per_step": launches}
 
+    # SURVEY 8d figures for the whole ray march (inference): logical gather bytes and MLP flops per final ray-sample
+    ns = args.nv - 1
+    gather_b = 5 * 8 * 16 * 240 / 128 + 592 * 5 * 4 / 128 + ns * (5 * 4 * 16 + 4 * 12)
+    mlp_flop = 345e3 * (240 + 2 * 128) / 128
+    peak_gbs, _ = measured_peak_gbs()
+    res["algorithmic"] = {
+        "gather_bytes_per_ray_sample": round(gather_b, 1), "gather_gbs": samples * gather_b / (ms * 1e-3) / 1e9,
+        "gather_frac_of_hbm_peak": samples * gather_b / (ms * 1e-3) / 1e9 / peak_gbs,
+        "mlp_flop_per_ray_sample": mlp_flop, "mlp_tflops_fp32_equivalent": samples * mlp_flop / (ms * 1e-3) / 1e12,
+        "note": "the march is bound by the SDF MLP on the tensor cores (3xTF32: three tcgen05 MMAs per fp32-equivalent "
+                "product), not by its gathers: 75 % of a chunk is K4, see profiles/README.md"}
+
     # e2e: this rank's rays from pinned host memory per chunk; image outputs gathered, then rank 0 copies them to
     # pinned host memory
     pin_o, pin_d = ro.cpu().pin_memory(), rd.cpu().pin_memory()
