@@ -508,7 +508,7 @@ volume_agg_rowgroup_kernel(const Pair* __restrict__ feat, int nv, int H, int W, 
     const int cz0 = blockIdx.x * 64, c0 = cz0 + threadIdx.x, a = a0 + blockIdx.z;
     const float X = __ldg(grid + a);
     if (CULL) {
-        const int total = ROWS * nv * 4;  // one item = one corner of one (tile, view); 4 consecutive lanes = one pair
+        const int total = ROWS * nv * 4;  // one item = one corner of one (tile, view); 4 consecutive lanes = one (tile, view)
         for (int base = 0; base < total; base += 256) {
             const int i = base + tid;
             const bool active = i < total;
