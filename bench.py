@@ -46,6 +46,16 @@ def measured_peak_gbs():
     return 6650.0, "fallback"
 
 
+def measured_bf16_tflops():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["bf16_tflops_sustained"]), "measured, sustained"
+        except Exception:
+            pass
+    return 1500.0, "fallback"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -323,6 +333,10 @@ def bench_render(args, rank, world, dev, sc, host, vol_mod, timed):
         "gather_bytes_per_ray_sample": round(gather_b, 1), "gather_gbs": samples * gather_b / (ms * 1e-3) / 1e9,
         "gather_frac_of_hbm_peak": samples * gather_b / (ms * 1e-3) / 1e9 / peak_gbs,
         "mlp_flop_per_ray_sample": mlp_flop, "mlp_tflops_fp32_equivalent": samples * mlp_flop / (ms * 1e-3) / 1e12,
+        # tensor-core view: three TF32 MMAs per fp32-equivalent product; TF32 peak taken as half the measured bf16 one
+        "mlp_tensor_tflops_tf32": 3 * samples * mlp_flop / (ms * 1e-3) / 1e12,
+        "tf32_peak_tflops_estimate": measured_bf16_tflops()[0] / 2,
+        "mlp_tensor_frac_of_tf32_peak": 3 * samples * mlp_flop / (ms * 1e-3) / 1e12 / (measured_bf16_tflops()[0] / 2),
         "note": "the march is bound by the SDF MLP on the tensor cores (3xTF32: three tcgen05 MMAs per fp32-equivalent "
                 "product), not by its gathers: 75 % of a chunk is K4, see profiles/README.md"}
 
