@@ -126,6 +126,12 @@ def test_full_size_properties(cuda_lib):
         assert vols[i][0][:, dead].abs().max().item() == 0.0
         fill = masks[i].mean().item()
         assert 0.15 < fill < 0.6, fill
+    # exact homogeneity at full size: features x 4 -> means x 4, variances x 16, masks unchanged, bit for bit
+    vols4, masks4 = Volume(volume_dims=dims).agg_mean_var([f * 4 for f in sc.features], sc.intrs, sc.c2ws)
+    for i in range(len(dims)):
+        assert torch.equal(masks4[i], masks[i])
+        assert torch.equal(vols4[i][:, :4], vols[i][:, :4] * 4) and torch.equal(vols4[i][:, 4:], vols[i][:, 4:] * 16)
+    del vols4, masks4
     # largest scale against the ATen op sequence on the same device (64^3 sub-sample to bound memory)
     rvol, rmask = torch_oracle.agg_mean_var_scale(sc.features[2], sc.intrs, sc.c2ws, 2, 64)
     assert torch.equal(rmask, masks[2])
