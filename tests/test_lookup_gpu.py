@@ -162,3 +162,28 @@ def test_lookup_feature_k6(cuda_lib, golden_dir):
     gb = torch.autograd.grad(fr, feats_r, w)
     for a, b in zip(ga, gb):
         assert _close(a, b, scale=b.abs().max().item() * 10)
+
+
+def test_full_size_voxel_centre_properties(cuda_lib):
+    """BASELINE config 2 pyramid (256..16): a trilinear look-up at a voxel centre (align_corners=True lattice)
+    returns that voxel of every scale's volume, and a nearest look-up at a cell centre (align_corners=False lattice)
+    returns that cell of the mask exactly -- the size-independent statement of projector.py:217-245's conventions
+    (points are (x, y, z), tensor dims 2/3/4 are x/y/z)."""
+    dims = [256, 128, 64, 32, 16]
+    gen = torch.Generator(device=DEV).manual_seed(7)
+    vols = [torch.randn(1, 4, d, d, d, device=DEV, generator=gen) for d in dims]
+    masks = [(torch.rand(1, 1, d, d, d, device=DEV, generator=gen) > 0.5).float() for d in dims]
+    n = 200_000
+    for s, d in enumerate(dims):
+        idx = torch.randint(0, d, (n, 3), device=DEV, generator=gen)
+        # trilinear: lattice of align_corners=True
+        pts = torch.linspace(-1, 1, d, device=DEV)[idx]
+        got = projector.lookup_volume(pts, vols)[:, 4 * s:4 * s + 4]
+        want = vols[s][0, :, idx[:, 0], idx[:, 1], idx[:, 2]].t()
+        # the un-normalised coordinate misses the integer by up to D * 2^-23, times the jump to the next voxel of a
+        # white-noise volume (a few units): a few 1e-4 at D = 256
+        assert (got - want).abs().max().item() <= 1e-3, f"scale {s}: {(got - want).abs().max().item()}"
+        # nearest: cell centres of align_corners=False
+        ctr = (idx.float() + 0.5) / d * 2 - 1
+        each = projector.lookup_volume(ctr, masks, "nearest")[:, s]
+        assert torch.equal(each, masks[s][0, 0, idx[:, 0], idx[:, 1], idx[:, 2]]), f"scale {s}"
