@@ -161,6 +161,9 @@ def sharded_agg_mean_var(volume_module, features, intrs, c2ws, rank: int, world:
             _lib.check(_lib.lib().gens_unpack_slabs(_lib.ptr(recv), world, stride, off, d, _lib.ptr(v), _lib.ptr(m),
                                                     _lib.stream_ptr(dev)), "gens_unpack_slabs")
         return vols, masks
+    if torch.is_grad_enabled() and any(f.requires_grad for f in features[:len(dims)]):
+        raise RuntimeError("gens_b200: sharded_agg_mean_var is inference-only (the gathered volumes carry no grad_fn); "
+                           "run it under torch.no_grad()")
     vols, masks = agg_mean_var(features, intrs, c2ws, dims, min_vis_view, slabs, volume_module.div_mode)
     full_v = [gather_slabs(v, d, world, group) for v, d in zip(vols, dims)]
     full_m = [gather_slabs(m, d, world, group) for m, d in zip(masks, dims)]

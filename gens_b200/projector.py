@@ -271,10 +271,14 @@ def surface_patch_warp(pts_sdf0, gradients_sdf0, images, intrinsics, poses, patc
         k_inv = _lib.invert_poses(k[:1])
         ref = torch.empty((1, b, pp, c), device=images.device, dtype=torch.float32)
         src = torch.empty((nv - 1, b, pp, c), device=images.device, dtype=torch.float32)
+        # converted inputs stay referenced until the launch is enqueued (f32c may return a temporary)
+        pts_c = _lib.f32c(pts_sdf0.detach().reshape(-1, 3))
+        nrm_c = _lib.f32c(gradients_sdf0.detach().reshape(-1, 3))
         _lib.check(_lib.lib().gens_patch_warp(
-            _lib.ptr(_lib.f32c(pts_sdf0.detach().reshape(-1, 3))), _lib.ptr(_lib.f32c(gradients_sdf0.detach().reshape(-1, 3))),
+            _lib.ptr(pts_c), _lib.ptr(nrm_c),
             _lib.ptr(imgs), _lib.ptr(k), _lib.ptr(p), _lib.ptr(k_inv), b, nv, c, h, w, int(patch_size), _lib.ptr(ref),
             _lib.ptr(src) if nv > 1 else None, _lib.stream_ptr(images.device)), "gens_patch_warp")
+        del pts_c, nrm_c
         return ref, src
     r0, c0 = poses[0, :3, :3], poses[0, :3, 3]
     k0 = intrinsics[0, :3, :3]
@@ -321,10 +325,13 @@ def upsample_rays(rays_o, rays_d, z_vals, sdf, mask_volumes, inv_s: float, n_new
     ms = [_lib.f32c(v) for v in _as_list(mask_volumes)]
     pyr = _lib.make_pyramid(ms, [v.shape[2] for v in ms])
     out = torch.empty((b, n_new), device=z_vals.device, dtype=torch.float32)
+    # every converted input is held in `keep` until the launch is enqueued: f32c returns a temporary for
+    # non-contiguous / non-fp32 callers (e.g. an expanded rays_o), which must not be freed and recycled before
+    keep = [_lib.f32c(rays_o), _lib.f32c(rays_d), _lib.f32c(z_vals), _lib.f32c(sdf.reshape(b, m))]
     _lib.check(_lib.lib().gens_upsample_rays(
-        _lib.ptr(_lib.f32c(rays_o)), _lib.ptr(_lib.f32c(rays_d)), _lib.ptr(_lib.f32c(z_vals)),
-        _lib.ptr(_lib.f32c(sdf.reshape(b, m))), b, m, pyr, ATEN_CUDA_FLAVOUR, float(inv_s), int(n_new), _lib.ptr(out),
-        _lib.stream_ptr(z_vals.device)), "gens_upsample_rays")
+        _lib.ptr(keep[0]), _lib.ptr(keep[1]), _lib.ptr(keep[2]), _lib.ptr(keep[3]), b, m, pyr, ATEN_CUDA_FLAVOUR,
+        float(inv_s), int(n_new), _lib.ptr(out), _lib.stream_ptr(z_vals.device)), "gens_upsample_rays")
+    del keep
     return out
 
 
@@ -339,10 +346,12 @@ def merge_samples(z_vals, sdf, new_z, new_sdf=None):
     sdf_out = torch.empty((b, m + k), device=dev, dtype=torch.float32) if with_sdf else None
     sdf_c = _lib.f32c(sdf.reshape(b, m)) if with_sdf else None
     nsdf_c = _lib.f32c(new_sdf.reshape(b, k)) if with_sdf else None
+    z_c, nz_c = _lib.f32c(z_vals), _lib.f32c(new_z)  # held until the launch is enqueued (see upsample_rays)
     _lib.check(_lib.lib().gens_merge_samples(
-        _lib.ptr(_lib.f32c(z_vals)), _lib.ptr(sdf_c) if with_sdf else None, _lib.ptr(_lib.f32c(new_z)),
+        _lib.ptr(z_c), _lib.ptr(sdf_c) if with_sdf else None, _lib.ptr(nz_c),
         _lib.ptr(nsdf_c) if with_sdf else None, b, m, k, _lib.ptr(z_out), _lib.ptr(sdf_out) if with_sdf else None,
         _lib.stream_ptr(dev)), "gens_merge_samples")
+    del z_c, nz_c, sdf_c, nsdf_c
     return z_out, sdf_out
 
 

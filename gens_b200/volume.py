@@ -200,7 +200,13 @@ def agg_mean_var(features, intrs, c2ws, dims, min_vis_view: int = 1,
     k = _lib.f32c(intrs)
     slabs = [(0, d) for d in dims] if slabs is None else list(slabs)
     feats = features[:len(dims)]
-    if peer_outs is not None or not (torch.is_grad_enabled() and any(f.requires_grad for f in feats)):
+    wants_grad = torch.is_grad_enabled() and any(f.requires_grad for f in feats)
+    if wants_grad and (peer_outs is not None or outs is not None):
+        # the multi-GPU builds write through raw pointers into exchange buffers: their results carry no grad_fn,
+        # so a training step would silently send zero gradient to the feature network
+        raise RuntimeError("gens_b200: slab-sharded / caller-buffer volume builds are inference-only (no backward to "
+                           "the feature maps); run them under torch.no_grad() or use Volume.agg_mean_var")
+    if peer_outs is not None or not wants_grad:
         vols, masks, _, _ = _build(_lib.f32c(c2ws), k, tuple(dims), tuple(slabs), min_vis_view, div_mode, outs, feats,
                                    peer_outs)
         return vols, masks
