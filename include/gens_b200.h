@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GENS_ABI_VERSION 1
+#define GENS_ABI_VERSION 2
 
 #define GENS_E_BADARG (-1)      /* null pointer / non-positive size            */
 #define GENS_E_UNSUPPORTED (-2) /* shape outside what the kernels are built for */
@@ -76,10 +76,26 @@ typedef struct gens_volume_scale {
     int n_peers;
     float *peer_volume[GENS_MAX_PEERS];
     float *peer_mask[GENS_MAX_PEERS];
+    int self_peer;            /* n_peers > 0: index of this rank's own buffer in peer_volume / peer_mask.  The culling
+                               * kernel then visits EVERY plane: tiles no view can see are zero-filled in the own
+                               * buffer by each rank for itself (they never cross NVLink), visible tiles of [a0,a1)
+                               * are stored to all peers, visible tiles of other slabs are left to their owner
+                               * (needs a_base = 0, i.e. full tensors)                                         */
+    int cam_slot;             /* 0: camera matrices staged in shared memory by every block; > 0: a slot returned by
+                               * gens_stage_cameras (cameras read from the constant bank)                       */
 } gens_volume_scale_t;
 /* (a_base = a0, channel_stride = (a1-a0)*D*D for a slab buffer;
  *  a_base = 0,  channel_stride = D*D*D       for the full (1,8,D,D,D) tensor). */
 
+/* Camera matrices of up to 8 scales into the constant bank: one tiny launch + one stream-ordered device-to-device
+ * copy.  cam_slots[i] receives the slot of scale i (K rows 0-1 times k_row_scales[i]) for gens_volume_scale_t.cam_slot,
+ * or 0 when the constant-bank path does not apply (nv > 8) and the kernels stage the cameras in shared memory.
+ * Slots live in a ring of 4 groups per device: a slot stays valid until 4 later gens_stage_cameras /
+ * gens_volume_build calls on the same device (stream order protects builds issued on one stream; more than 4
+ * builds in flight on DIFFERENT streams of one device are not supported).  gens_volume_build does this itself,
+ * inside its pack launch. */
+int gens_stage_cameras(const float *w2c, const float *intrs, int nv, const float *k_row_scales, int n_scales,
+                       int *cam_slots, void *stream);
 /* All scales of one build, launched back to back on `stream` (one host call per build). */
 int gens_volume_agg_fwd_multi(const gens_volume_scale_t *scales, int n_scales, int nv,
                               const float *w2c, const float *intrs, int min_vis_view,

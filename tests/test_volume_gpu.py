@@ -95,6 +95,31 @@ def test_matches_c_oracle(cuda_lib, nv, hw, dims):
             assert np.array_equal(vol, ovol), f"values not bit-identical to the oracle (div_mode {div_mode}, D {d})"
 
 
+@pytest.mark.parametrize("nv", [3, 5])
+def test_shipped_path_bit_identical_to_c_oracle_at_baseline_sizes(cuda_lib, nv):
+    """BASELINE config 2 (480x640, 3 views) and config 3/4 shape (5 views) at the FULL volume sizes, through the
+    public API (Volume.agg_mean_var -> gens_volume_build: pose inverse in the pack launch, the culling row-group
+    kernel at 256^3, the packed kernel below): visibility masks AND mean/variance volumes of every scale are
+    np.array_equal to the C oracle (oracle/gens_oracle.c, restating volume.py:21-58) fed with the same camera
+    matrices.  The 256^3 x nv oracle pass takes a few seconds of OpenMP C."""
+    host = make_scene(480, 640, nv, seed=0, with_images=False)
+    sc = host.to(DEV)
+    dims = [256, 128, 64, 32, 16]
+    vols, masks = Volume(volume_dims=dims).agg_mean_var(sc.features, sc.intrs, sc.c2ws)
+    torch.cuda.synchronize()
+    w2c = _lib.invert_poses(sc.c2ws).cpu().numpy()  # bit-identical to torch.inverse on this device (tested below)
+    for i, d in enumerate(dims):
+        k = host.intrs.clone()
+        k[:, :2] *= 0.5 ** i
+        ovol, omsk = c_oracle.volume_agg(host.features[i].numpy(), w2c, k.numpy(), torch.linspace(-1, 1, d).numpy(),
+                                         div_mode=c_oracle.DIV_RECIP)
+        got_m = masks[i][0, 0].cpu().numpy()
+        assert np.array_equal(got_m, omsk), f"nv={nv} D={d}: {(got_m != omsk).sum()} mask flips"
+        got_v = vols[i][0].cpu().numpy()
+        assert np.array_equal(got_v, ovol), f"nv={nv} D={d}: {(got_v != ovol).sum()} values differ from the oracle"
+        del got_v, ovol
+
+
 def test_public_api_matches_aten_ops_on_gpu(cuda_lib):
     """Volume.agg_mean_var (default DIV_RECIP) vs the same ATen op sequence the reference would run on
     this GPU: visibility masks bit-exact, volumes within tolerance."""
@@ -237,7 +262,9 @@ def test_fused_slab_exchange_two_gpus():
     assert r.stdout.count("bit-identical to the 1-GPU build: True") == 2, r.stdout[-2000:]
 
 
-def _k1_variant(variant, feat_d, nv, h, w, w2c_d, k_d, grid_d, d, a0=0, a1=None, min_vis_view=1):
+def _k1_variant(variant, feat_d, nv, h, w, w2c_d, k_d, grid_d, d, a0=0, a1=None, min_vis_view=1, const_cams=False):
+    """One K1 launch under a tuning variant; const_cams stages the cameras in the constant bank first."""
+    from gens_b200.volume import agg_scale_into, stage_camera_slots
     a1 = d if a1 is None else a1
     planes = a1 - a0
     vol = torch.full((8, planes, d, d), float("nan"), device=DEV)
@@ -245,9 +272,9 @@ def _k1_variant(variant, feat_d, nv, h, w, w2c_d, k_d, grid_d, d, a0=0, a1=None,
     L = _lib.lib()
     L.gens_debug_set_variant(variant)
     try:
-        _lib.check(L.gens_volume_agg_fwd(_lib.ptr(feat_d), nv, h, w, _lib.ptr(w2c_d), _lib.ptr(k_d), 1.0,
-                                         _lib.ptr(grid_d), d, a0, a1, a0, planes * d * d, min_vis_view,
-                                         _lib.DIV_RECIP, _lib.ptr(vol), _lib.ptr(msk), _lib.stream_ptr()), "k1")
+        slot = stage_camera_slots(w2c_d, k_d, [1.0])[0] if const_cams else 0
+        assert slot > 0 or not const_cams or nv > 8
+        agg_scale_into(feat_d, (h, w), w2c_d, k_d, 1.0, grid_d, d, vol, msk, (a0, a1), min_vis_view, _lib.DIV_RECIP, slot)
         torch.cuda.synchronize()
     finally:
         L.gens_debug_set_variant(0)
@@ -293,10 +320,13 @@ def test_rowgroup_kernel_culling_is_bit_identical(cuda_lib, d, hw, nv):
             ovol, omsk = c_oracle.volume_agg(sc.features[0].numpy(), w2c.numpy(), k.numpy(),
                                              torch.linspace(-1, 1, d).numpy(), div_mode=c_oracle.DIV_RECIP)
             assert np.array_equal(ref_vol.cpu().numpy(), ovol) and np.array_equal(ref_msk.cpu().numpy(), omsk), name
-        for variant in (0, 20, 25):
-            vol, msk = _k1_variant(variant, *args)
-            assert torch.equal(vol, ref_vol), f"{name}: variant {variant} volumes differ"
-            assert torch.equal(msk, ref_msk), f"{name}: variant {variant} masks differ"
+        # 0 = shipped (bulk zero fill of dead tiles), 11 = STG zero fill, 20 / 25 = with / without culling at any D;
+        # each also with the cameras read from the constant bank instead of shared memory
+        for variant in (0, 11, 20, 25):
+            for const_cams in (False, True):
+                vol, msk = _k1_variant(variant, *args, const_cams=const_cams)
+                assert torch.equal(vol, ref_vol), f"{name}: variant {variant} const_cams {const_cams} volumes differ"
+                assert torch.equal(msk, ref_msk), f"{name}: variant {variant} const_cams {const_cams} masks differ"
         # a slab in the middle of the volume, into a slab-sized buffer, and min_vis_view = 0 / -1 (no culling)
         a0, a1 = d // 4, d // 4 + d // 8
         vol, msk = _k1_variant(20, *args, a0=a0, a1=a1)

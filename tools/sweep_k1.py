@@ -4,18 +4,21 @@ sys.path.insert(0, '.')
 import torch
 from gens_b200 import _lib, build
 from gens_b200.synthetic import make_scene
-from gens_b200.volume import pack_feature_maps, stage_cameras
+from gens_b200.volume import agg_scale_into, pack_feature_maps, stage_camera_slots, stage_cameras
 
 build.build(); L = _lib.lib()
 dev = torch.device('cuda:0')
 nv = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-variants = [int(v) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else [10, 25, 20]
+# '0c' = variant 0 with the cameras staged in the constant bank (gens_stage_cameras), '0' = shared-memory cameras
+variants = sys.argv[2].split(',') if len(sys.argv) > 2 else ['10', '11', '12c', '13', '0', '0c']
 sc = make_scene(480, 640, nv, seed=0, with_images=False).to(dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 ref = {}
-for variant in variants:
+for vname in variants:
+    const_cams = vname.endswith('c')
+    variant = int(vname.rstrip('c'))
     L.gens_debug_set_variant(variant)
-    line = [f'variant {variant}:']
+    line = [f'variant {vname}:']
     tot = 0.0
     for i, d in enumerate([256, 128, 64]):
         feat = pack_feature_maps(sc.features[i])
@@ -23,9 +26,9 @@ for variant in variants:
         w2c, k = stage_cameras(sc.intrs, sc.c2ws, i)
         grid = torch.linspace(-1, 1, d, device=dev)
         vol = torch.empty((8, d, d, d), device=dev); msk = torch.empty((d, d, d), device=dev)
+        slot = stage_camera_slots(w2c, k, [1.0])[0] if const_cams else 0
         def run():
-            _lib.check(L.gens_volume_agg_fwd(_lib.ptr(feat), nv, h, w, _lib.ptr(w2c), _lib.ptr(k), 1.0, _lib.ptr(grid), d, 0, d, 0,
-                                             d ** 3, 1, 1, _lib.ptr(vol), _lib.ptr(msk), _lib.stream_ptr()), 'k1')
+            agg_scale_into(feat, (h, w), w2c, k, 1.0, grid, d, vol, msk, None, 1, 1, slot)
         for _ in range(3): run()
         ts = []
         for _ in range(10):
