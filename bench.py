@@ -31,9 +31,35 @@ sys.path.insert(0, ROOT)
 DIMS = [256, 128, 64, 32, 16]
 HW = (480, 640)
 L2_FLUSH_BYTES = 256 << 20
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE K1 launch at 256^3, nv=3, 480x640 (ncu --set full capture of
-# this round, profiles/r01_k1_256_kernel.txt): 29.5 MB + 545.8 MB
-K1_NCU_DRAM_BYTES = 29477632 + 545840640
+K1_TRAFFIC_PROFILE = os.path.join(ROOT, "profiles", "r02_k1_256_traffic.json")
+K1_SOURCES = ("gens_b200/csrc/volume_agg.cu", "gens_b200/csrc/f32x2.cuh", "gens_b200/csrc/common.cuh")
+
+
+def k1_source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    for rel in K1_SOURCES:
+        with open(os.path.join(ROOT, rel), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def k1_ncu_traffic(nv):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE K1 launch at 256^3 from the committed ncu capture
+    (profiles/r02_k1_256_traffic.json, written by tools/summarize_ncu.py from the .ncu-rep).  The capture is tied to
+    the kernel sources by their hash: a stale or missing capture gives traffic = null and says so loudly."""
+    try:
+        rec = json.load(open(K1_TRAFFIC_PROFILE))
+    except Exception as exc:  # noqa: BLE001
+        sys.stderr.write(f"bench.py: NO ncu traffic capture ({K1_TRAFFIC_PROFILE}: {exc}); roofline.traffic = null\n")
+        return None, "no committed ncu capture"
+    if rec.get("kernel_source_sha256_16") != k1_source_hash():
+        sys.stderr.write("bench.py: STALE ncu traffic capture (kernel sources changed since "
+                         f"{K1_TRAFFIC_PROFILE} was taken); roofline.traffic = null\n")
+        return None, "ncu capture is stale against the kernel sources"
+    if int(rec.get("nv", 3)) != nv:
+        return None, f"ncu capture is for nv={rec.get('nv')}"
+    return int(rec["dram_bytes_read"]) + int(rec["dram_bytes_write"]), rec.get("source", K1_TRAFFIC_PROFILE)
 
 
 def measured_peak_gbs():
@@ -54,6 +80,36 @@ def measured_bf16_tflops():
         except Exception:
             pass
     return 1500.0, "fallback"
+
+
+_TF32_PEAK = {}
+
+
+def measured_tf32_tflops(dev):
+    """Dense TF32 tensor-core peak of THIS GPU, measured live with a resident-operand tcgen05 MMA loop
+    (gens_tf32_mma_peak: one CTA per SM issues kind::tf32 128x256x8 MMAs from shared memory into TMEM accumulators
+    with nothing else in flight).  Falls back to half the measured bf16 figure if the probe is unavailable."""
+    key = str(dev)
+    if key not in _TF32_PEAK:
+        try:
+            from gens_b200 import _lib
+            out = torch.zeros(2, device=dev, dtype=torch.float64)
+            iters = 4096
+            lib = _lib.lib()
+            for _ in range(2):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                _lib.check(lib.gens_tf32_mma_peak(iters, _lib.ptr(out), _lib.stream_ptr(dev)), "gens_tf32_mma_peak")
+                b.record()
+                torch.cuda.synchronize(dev)
+                ms = a.elapsed_time(b)
+            n_cta = int(out[0].item())
+            flops = n_cta * iters * 2.0 * 128 * 256 * 8
+            _TF32_PEAK[key] = (flops / (ms * 1e-3) / 1e12,
+                               f"measured: {n_cta} CTAs x {iters} tcgen05.mma kind::tf32 128x256x8, {ms:.3f} ms")
+        except Exception as exc:  # noqa: BLE001
+            _TF32_PEAK[key] = (measured_bf16_tflops()[0] / 2, f"estimate = measured bf16 / 2 (probe failed: {exc})")
+    return _TF32_PEAK[key]
 
 
 class ClockSampler:
@@ -204,9 +260,10 @@ def render_rays(surf, sc, vols, masks, rays_o, rays_d, chunk):
     return torch.cat(cols), torch.cat(deps), torch.cat(nrms), torch.cat(sdeps)
 
 
-def cpu_render_baseline(nv, n_rays=2048, dims=(64, 32, 16, 8, 4)):
+def cpu_render_baseline(nv, n_rays=2048, dims=tuple(DIMS)):
     """Reference-path render on host cores: the same host logic with every look-up expressed in ATen ops
-    on CPU tensors (oracle/torch_oracle.CpuOps).  Bounded sample: `n_rays` rays through a 64^3 pyramid."""
+    on CPU tensors (oracle/torch_oracle.CpuOps).  Bounded sample: `n_rays` rays of the bench image through the
+    SAME volume pyramid the GPU arm marches (dims 256...16), in the reference's 256-ray chunks."""
     from gens_b200.synthetic import make_scene
     from oracle import torch_oracle
     cores = os.cpu_count() or 1
@@ -228,32 +285,104 @@ def cpu_render_baseline(nv, n_rays=2048, dims=(64, 32, 16, 8, 4)):
                       f"of ImplicitSurface.render on host tensors, all host threads)", "ms": dt * 1e3}
 
 
-def gpu_render_baseline(dev, sc, vols, masks, n_rays=2048):
-    """SURVEY 8d "GPU reference baseline": the reference's op sequence (ATen ops, autograd second-order term, 256-ray
-    chunks as its validate()) on THIS GPU -- the product's host logic with the oracle's ATen look-ups plugged in
-    (oracle/torch_oracle.CpuOps is device-agnostic), on the bench's own volumes and a bounded sample of its rays."""
+def load_reference():
+    """The UNMODIFIED reference staged under baseline/_ref (baseline/setup_ref.py), or None."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    try:
+        import ref_runtime
+        if not ref_runtime.available():
+            return None
+        return ref_runtime.load()
+    except Exception as exc:  # noqa: BLE001
+        sys.stderr.write(f"bench.py: staged reference unavailable ({exc})\n")
+        return None
+
+
+def gpu_render_baseline(dev, sc, vols, masks, surf, n_rays=2048):
+    """SURVEY 8d "GPU reference baseline" for the ray march, on the bench's own volumes and a bounded sample of its
+    rays, in 256-ray chunks as the reference's validate().  With baseline/_ref staged this is the UNMODIFIED reference
+    (models/modules/implicit_surface.py:351-405 with its own gridsample_grad2 extension, kind "reference") carrying
+    the product's weights, and the same rays are rendered by the product for a live parity figure; otherwise the
+    ATen-op restatement (oracle/torch_oracle ops plugged into the host logic, kind "port")."""
+    from gens_b200.config import gens_model_conf
     from oracle import torch_oracle
-    surf = build_surface(dev, ops=torch_oracle.CpuOps)
+    ns = load_reference()
+    kind = "reference" if ns is not None else "port"
+    if ns is not None:
+        ref_surf = ns.implicit_surface.ImplicitSurface(gens_model_conf(perturb=0.0)["implicit_surface"]).to(dev)
+        ref_surf.load_state_dict(surf.state_dict())
+    else:
+        ref_surf = build_surface(dev, ops=torch_oracle.CpuOps)
+        ref_surf.perturb = 0.0
+    ref_surf.eval()
     ro, rd = sc.rays(step=1)
     sel = torch.arange(0, ro.shape[0], ro.shape[0] // n_rays, device=ro.device)[:n_rays]
     ro, rd = ro[sel].to(dev).contiguous(), rd[sel].to(dev).contiguous()
+    keys = ("color_fine", "render_depth", "normal", "weight_sum")
 
-    def run(o, d):
+    def run(model, o, d):
         # as the reference's validate(): under no_grad, the SDF gradient re-enables autograd (sdf_network.py:131)
+        outs = []
         with torch.no_grad():
             for a in range(0, o.shape[0], 256):
-                r = surf.render(o[a:a + 256], d[a:a + 256], sc.near, sc.far, vols, masks, sc.imgs, sc.features,
-                                sc.features, sc.intrs, sc.c2ws, 1.0, None)
-                del r
-    run(ro[:256], rd[:256])
+                r = model.render(o[a:a + 256], d[a:a + 256], sc.near, sc.far, vols, masks, sc.imgs, sc.features,
+                                 sc.features, sc.intrs, sc.c2ws, 1.0, None)
+                outs.append({k: r[k].detach() for k in keys})
+        return {k: torch.cat([x[k] for x in outs]) for k in keys}
+    run(ref_surf, ro[:256], rd[:256])
     torch.cuda.synchronize(dev)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); run(ro, rd); b.record()
+    torch.manual_seed(5)
+    a.record(); ref_out = run(ref_surf, ro, rd); b.record()
     torch.cuda.synchronize(dev)
     ms = a.elapsed_time(b)
-    return {"value": n_rays * 128 / (ms * 1e-3), "unit": "ray-samples/s", "ms": ms,
-            "sample": f"{n_rays} rays x 128 samples in 256-ray chunks through the bench's volumes {DIMS}: the reference's "
-                      "ATen op sequence + autograd gradients on this GPU (oracle/torch_oracle ops; host-launch bound)"}
+    res = {"value": n_rays * 128 / (ms * 1e-3), "unit": "ray-samples/s", "ms": ms, "kind": kind,
+           "sample": f"{n_rays} rays x 128 samples in 256-ray chunks through the bench's volumes {DIMS} on this GPU: "
+                     + ("the unmodified reference (baseline/_ref, its own CUDA extension)" if ns is not None else
+                        "the reference's ATen op sequence (oracle/torch_oracle ops; baseline/_ref not staged)")}
+    if ns is not None:
+        old = surf.perturb
+        surf.perturb = 0.0
+        try:
+            torch.manual_seed(5)
+            our_out = run(surf, ro, rd)
+        finally:
+            surf.perturb = old
+        res["parity_vs_reference_max_rel"] = {
+            k: float((our_out[k] - ref_out[k]).abs().max() / ref_out[k].abs().max().clamp_min(1e-12)) for k in keys}
+        import ref_runtime
+        ref_runtime.purge()
+    return res
+
+
+def gpu_build_baseline(dev, sc, timed, vols_ours, masks_ours):
+    """SURVEY 8d "GPU reference baseline" for the build: the unmodified reference's Volume.agg_mean_var
+    (models/modules/volume.py:13-63) on this GPU when baseline/_ref is staged (kind "reference", outputs compared
+    with the product's), else the ATen-op restatement (kind "port")."""
+    from gens_b200.config import Conf
+    from oracle import torch_oracle
+    ns = load_reference()
+    if ns is not None:
+        ref_vol = ns.volume.Volume(Conf(volume_dims=DIMS))
+        fn = lambda: ref_vol.agg_mean_var(sc.features, sc.intrs, sc.c2ws)
+    else:
+        fn = lambda: torch_oracle.agg_mean_var(sc.features, sc.intrs, sc.c2ws, DIMS)
+    with torch.no_grad():
+        r_ms, _ = timed(fn, 3, 3)
+        res = {"value": voxel_views(sc.intrs.shape[0]) / (r_ms * 1e-3), "unit": "voxel*views/s", "ms": r_ms,
+               "kind": "reference" if ns is not None else "port",
+               "sample": "full 5-scale build, 3 steps after 3 warm-ups on this GPU: "
+                         + ("the unmodified reference's Volume.agg_mean_var (baseline/_ref)" if ns is not None else
+                            "the reference's ATen op sequence (oracle/torch_oracle.agg_mean_var)")}
+        if ns is not None:
+            rv, rm = fn()
+            res["masks_bit_identical_to_reference"] = all(torch.equal(a, b) for a, b in zip(masks_ours, rm))
+            res["volumes_max_abs_diff_vs_reference"] = max(float((a - b).abs().max()) for a, b in zip(vols_ours, rv))
+            del rv, rm
+            import ref_runtime
+            ref_runtime.purge()
+    torch.cuda.empty_cache()
+    return res
 
 
 # --------------------------------------------------------------------------- reference arm
@@ -296,6 +425,66 @@ def run_reference(args, rank, world):
     emit(line)
 
 
+def live_tile_map(w2c, k_scaled, d, hw, dev):
+    """K1's frustum-culling rule (csrc/volume_agg.cu: cull_planes) restated in fp32 torch ops: bool (D, D/8, D/64),
+    True = the tile of 8 rows x 64 voxels is computed and crosses NVLink in the fused exchange.  Used only to
+    ACCOUNT the bytes of the exchange (the kernel takes its own decision; borderline tiles may differ)."""
+    g = torch.linspace(-1, 1, d, device=dev)
+    hx, hy = torch.tensor((hw[1] - 1) / 2.0, device=dev), torch.tensor((hw[0] - 1) / 2.0, device=dev)
+    live = torch.zeros((d, d // 8, d // 64), dtype=torch.bool, device=dev)
+    tau, m = 1e-4, 1e-3
+    for v in range(w2c.shape[0]):
+        w, k = w2c[v], k_scaled[v]
+        dead = None
+        for yc in (g[0::8], g[7::8]):
+            for zc in (g[0::64], g[63::64]):
+                X, Y, Z = g[:, None, None], yc[None, :, None], zc[None, None, :]
+                c = [w[r, 0] * X + w[r, 1] * Y + w[r, 2] * Z + w[r, 3] for r in range(3)]
+                sm = [(w[r, 0] * X).abs() + (w[r, 1] * Y).abs() + (w[r, 2] * Z).abs() + w[r, 3].abs() for r in range(3)]
+                depth = c[2]
+                img0, s0 = k[0, 0] * c[0] + k[0, 2] * c[2], k[0, 0].abs() * sm[0] + k[0, 2].abs() * sm[2]
+                img1, s1 = k[1, 1] * c[1] + k[1, 2] * c[2], k[1, 1].abs() * sm[1] + k[1, 2].abs() * sm[2]
+                lx, rx, ly, ry = m * hx, (2 + m) * hx, m * hy, (2 + m) * hy
+                bits = (depth < -tau * sm[2]).int()
+                bits = bits | ((-img0 - lx * depth > tau * (s0 + lx * sm[2])).int() * 2)
+                bits = bits | ((img0 - rx * depth > tau * (s0 + rx * sm[2])).int() * 4)
+                bits = bits | ((-img1 - ly * depth > tau * (s1 + ly * sm[2])).int() * 8)
+                bits = bits | ((img1 - ry * depth > tau * (s1 + ry * sm[2])).int() * 16)
+                dead = bits if dead is None else dead & bits
+        live |= dead == 0
+    return live
+
+
+def exchange_ingest_bytes(sc, rank, world, dev):
+    """Bytes the other ranks store into THIS rank's tensors during one fused slab build: 36 B per voxel of every
+    live tile outside the own slab (scales with D % 64 == 0 run the culling kernel; smaller ones ship everything)."""
+    from gens_b200 import parallel
+    from gens_b200.volume import stage_cameras
+    total, live_frac = 0, []
+    for i, d in enumerate(DIMS):
+        a0, a1 = parallel.slab_bounds(d, rank, world)
+        if d % 64 == 0:
+            w2c, k = stage_cameras(sc.intrs, sc.c2ws, i)
+            live = live_tile_map(w2c, k, d, sc.features[i].shape[-2:], dev)
+            live_frac.append(round(float(live.float().mean()), 4))
+            foreign = live.clone()
+            foreign[a0:a1] = False
+            total += int(foreign.sum().item()) * 512 * 36
+        else:
+            live_frac.append(1.0)
+            total += (d - (a1 - a0)) * d * d * 36
+    return total, live_frac
+
+
+def all_ranks_true(flag: bool, world: int, dev) -> bool:
+    if world == 1:
+        return bool(flag)
+    import torch.distributed as dist
+    t = torch.tensor([1 if flag else 0], device=dev, dtype=torch.int32)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item())
+
+
 # --------------------------------------------------------------------------- our arm
 def bench_render(args, rank, world, dev, sc, host, vol_mod, timed):
     """ray-samples/s of the full-image render (all 18 outputs of render() computed, i.e. the parity path)."""
@@ -329,14 +518,15 @@ def bench_render(args, rank, world, dev, sc, host, vol_mod, timed):
     gather_b = 5 * 8 * 16 * 240 / 128 + 592 * 5 * 4 / 128 + ns * (5 * 4 * 16 + 4 * 12)
     mlp_flop = 345e3 * (240 + 2 * 128) / 128
     peak_gbs, _ = measured_peak_gbs()
+    tf32_peak, tf32_src = measured_tf32_tflops(dev)
     res["algorithmic"] = {
         "gather_bytes_per_ray_sample": round(gather_b, 1), "gather_gbs": samples * gather_b / (ms * 1e-3) / 1e9,
         "gather_frac_of_hbm_peak": samples * gather_b / (ms * 1e-3) / 1e9 / peak_gbs,
         "mlp_flop_per_ray_sample": mlp_flop, "mlp_tflops_fp32_equivalent": samples * mlp_flop / (ms * 1e-3) / 1e12,
         # tensor-core view: three TF32 MMAs per fp32-equivalent product; TF32 peak taken as half the measured bf16 one
         "mlp_tensor_tflops_tf32": 3 * samples * mlp_flop / (ms * 1e-3) / 1e12,
-        "tf32_peak_tflops_estimate": measured_bf16_tflops()[0] / 2,
-        "mlp_tensor_frac_of_tf32_peak": 3 * samples * mlp_flop / (ms * 1e-3) / 1e12 / (measured_bf16_tflops()[0] / 2),
+        "tf32_peak_tflops_per_gpu": tf32_peak, "tf32_peak_source": tf32_src, "n_gpus": world,
+        "mlp_tensor_frac_of_tf32_peak": 3 * samples * mlp_flop / (ms * 1e-3) / 1e12 / (tf32_peak * world),
         "note": "the march is bound by the SDF MLP on the tensor cores (3xTF32: three tcgen05 MMAs per fp32-equivalent "
                 "product), not by its gathers: 75 % of a chunk is K4, see profiles/README.md"}
 
@@ -360,6 +550,25 @@ def bench_render(args, rank, world, dev, sc, host, vol_mod, timed):
     e_ms, _ = timed(step_e2e, max(1, args.render_steps // 2), 0)
     res["e2e"] = {"value": samples / (e_ms * 1e-3), "unit": "ray-samples/s", "ms_per_step": e_ms,
                   "h2d_bytes_per_step": n_total * 6 * 4, "d2h_bytes_per_step": n_total * 8 * 4}
+    if world > 1:
+        # every rank renders its shard of a ray sample (jitter off); the gathered image must equal a local render
+        n_ver = 4096
+        idx = torch.linspace(0, n_total - 1, n_ver, device=ro_all.device).long()
+        ro_s, rd_s = ro_all[idx].contiguous(), rd_all[idx].contiguous()
+        a0, a1 = parallel.shard_range(n_ver, rank, world)
+        old_perturb, surf.perturb = surf.perturb, 0.0
+        try:
+            mine = torch.cat([x if x.dim() == 2 else x[:, None] for x in
+                              render_rays(surf, sc, vols, masks, ro_s[a0:a1], rd_s[a0:a1], chunk)], dim=1)
+            gathered = parallel.gather_rays(mine, n_ver, rank, world)
+            local = torch.cat([x if x.dim() == 2 else x[:, None] for x in
+                               render_rays(surf, sc, vols, masks, ro_s, rd_s, chunk)], dim=1)
+        finally:
+            surf.perturb = old_perturb
+        diff = float((gathered - local).abs().max())
+        res["verified"] = {"ray_shards_match_local_render": all_ranks_true(diff <= 1e-6, world, dev),
+                           "ray_shards_bit_identical": all_ranks_true(bool(torch.equal(gathered, local)), world, dev),
+                           "max_abs_diff": diff, "rays_checked": n_ver}
     if world == 1:
 
         # roofline view of the gather kernel (K3): logical bytes = 5 scales x 8 corners x 16 B per point
@@ -375,8 +584,44 @@ def bench_render(args, rank, world, dev, sc, host, vol_mod, timed):
                                                 "(307 MB) are read through L2, compulsory HBM bytes are far fewer"}
         if rank == 0 and not args.no_cpu:
             res["cpu_baseline"] = cpu_render_baseline(args.nv)
-            res["reference_ops_on_gpu"] = gpu_render_baseline(dev, sc, vols, masks)
+            res["reference_ops_on_gpu"] = gpu_render_baseline(dev, sc, vols, masks, surf)
     return res
+
+
+def bench_lattice(args, rank, world, dev, timed):
+    """BASELINE config 5: the mesh-extraction SDF lattice u = -sdf on 512^3 points (reference implicit_surface.py:
+    407-421: 512 sequential 64^3 blocks, each with a .cpu() sync) through ImplicitSurface.sdf_grid -- fused 5-scale
+    trilinear gather + tcgen05 SDF value kernel, 128^3 blocks resident on the device; N > 1: x-slabs per rank
+    (parallel.sharded_sdf_grid), one gather of the slabs to rank 0.  The lattice depends on the volumes only, so
+    the 576x768 image size of config 5 does not enter."""
+    from gens_b200 import parallel
+    res = args.lattice_res
+    surf = build_surface(dev)
+    vols = smooth_volumes(DIMS, dev)
+    bmin, bmax = torch.tensor([-1.0, -1.0, -1.0], device=dev), torch.tensor([1.0, 1.0, 1.0], device=dev)
+    grid_fn = lambda xr: surf.sdf_grid(vols, bmin, bmax, res, x_range=xr)
+
+    def step():
+        return parallel.sharded_sdf_grid(grid_fn, res, rank, world, dst=0)
+    ms, _ = timed(step, 2, 1)
+    pts = res ** 3
+    out = {"metric": "points/s (512^3 SDF lattice of extract_geometry)", "value": pts / (ms * 1e-3), "unit": "points/s",
+           "ms_per_step": ms, "resolution": res, "n_gpus": world, "steps": 2, "warmup": 1,
+           "mlp_tflops_fp32_equivalent": pts * 345e3 / (ms * 1e-3) / 1e12,
+           "logical_gather_gbs": pts * 640 / (ms * 1e-3) / 1e9,
+           "gathered_bytes_to_rank0": 0 if world == 1 else pts * 4 * (world - 1) // world,
+           "sharding": "none" if world == 1 else f"x-slabs over {world} ranks + gather to rank 0"}
+    if world > 1:
+        full = step()
+        ok = True
+        if rank == 0:  # a few planes of every other rank's slab, recomputed locally: bit-identical
+            for r in range(1, world):
+                x0, _ = parallel.shard_range(res, r, world)
+                ok = ok and bool(torch.equal(grid_fn((x0, x0 + 2)), full[x0:x0 + 2]))
+        out["verified"] = {"lattice_slabs_bit_identical": all_ranks_true(ok, world, dev),
+                           "checked": "2 planes of every other rank's slab recomputed on rank 0"}
+        del full
+    return out
 
 
 def run_ours(args, rank, world, local):
@@ -472,12 +717,38 @@ def run_ours(args, rank, world, local):
         render = None
         if not args.no_render:
             render = bench_render(args, rank, world, dev, sc, host, vol_mod, timed)
+        lattice = None if args.no_lattice else bench_lattice(args, rank, world, dev, timed)
     clk = clocks.summary()
 
     fill = None
     if rank == 0:
         _, masks = vol_mod.agg_mean_var(sc.features, sc.intrs, sc.c2ws)
         fill = [round(m.mean().item(), 4) for m in masks]
+
+    # ---- N > 1: the assembled volumes of EVERY rank must be bit-identical to a local 1-GPU build (outside the timed
+    # region), and the exchange gets its own roofline line: bytes the peers store into one GPU over NVLink
+    verified, nvlink = None, None
+    if world > 1:
+        with torch.no_grad():
+            sv, sm = sharded_build(vol_mod, sc.features, sc.intrs, sc.c2ws, rank, world)
+            sv, sm = [v.clone() for v in sv], [m.clone() for m in sm]
+            lv, lm = vol_mod.agg_mean_var(sc.features, sc.intrs, sc.c2ws)
+            torch.cuda.synchronize(dev)
+            same = all(torch.equal(a, b) for a, b in zip(sv, lv)) and all(torch.equal(a, b) for a, b in zip(sm, lm))
+            del sv, sm, lv, lm
+        verified = {"slabs_bit_identical": all_ranks_true(same, world, dev), "checked_on": f"all {world} ranks",
+                    "against": "local 1-GPU Volume.agg_mean_var on every rank (torch.equal on all volumes and masks)"}
+        ingest, live_frac = exchange_ingest_bytes(sc, rank, world, dev)
+        ingest = int(max_over_ranks(float(ingest), world, dev))
+        link_peak = 770.0  # GB/s per direction per GPU: peer-copy rate measured on this pool (B200_PROFILING.md)
+        nvlink = {"bound": "nvlink", "achieved": ingest / (ms_step * 1e-3) / 1e9, "peak": link_peak, "unit": "GB/s",
+                  "frac": ingest / (ms_step * 1e-3) / 1e9 / link_peak, "ingest_bytes_per_gpu": ingest,
+                  "ingest_bytes_without_culling": int(sum(9 * d ** 3 * 4 for d in DIMS) * (world - 1) / world),
+                  "live_tile_fraction": live_frac,
+                  "peak_source": "B200_PROFILING.md: measured peer copy 770 GB/s per direction (900 nominal)",
+                  "note": "every GPU must ingest the live tiles of the other ranks' slabs: (P-1)/P of the visible part "
+                          "of 690 MB; tiles no view can see are zero-filled locally and never cross NVLink; time = the "
+                          "whole 5-scale step (compute + exchange + device barrier)"}
 
     # ---- CPU baseline (rank 0, N=1): bounded sample of the same workload --------------------
     cpu = None
@@ -498,22 +769,24 @@ def run_ours(args, rank, world, local):
 
     ref_gpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        # SURVEY 8d "GPU reference baseline": the reference's op sequence (volume.py as ~320 ATen ops per scale) on
-        # THIS GPU, same inputs, L2 flushed, CUDA events
-        from oracle import torch_oracle
-        with torch.no_grad():
-            r_ms, _ = timed(lambda: torch_oracle.agg_mean_var(sc.features, sc.intrs, sc.c2ws, DIMS), 3, 2)
-        ref_gpu = {"value": voxel_views(nv) / (r_ms * 1e-3), "unit": "voxel*views/s", "ms": r_ms,
-                   "sample": "full 5-scale build, 3 steps after 2 warm-ups: the reference's ATen op sequence on this GPU "
-                             "(oracle/torch_oracle.agg_mean_var)"}
-        torch.cuda.empty_cache()
+        vols_o, masks_o = vol_mod.agg_mean_var(sc.features, sc.intrs, sc.c2ws)
+        ref_gpu = gpu_build_baseline(dev, sc, timed, vols_o, masks_o)
+        del vols_o, masks_o
 
     if rank != 0:
         return
     peak, peak_kind = measured_peak_gbs()
+    traffic, traffic_src = k1_ncu_traffic(nv)
     abytes = algorithmic_bytes_scale(d0, nv, HW[0], HW[1])
     achieved = abytes / (k1_ms * 1e-3) / 1e9
     vv = voxel_views(nv)
+    k1_roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                 "traffic": traffic, "traffic_source": traffic_src,
+                 "kernel": "volume_agg_rowgroup_kernel @ 256^3", "ms": k1_ms,
+                 "algorithmic_bytes": abytes, "peak_source": f"MEASURED_PEAKS.json ({peak_kind}, burst copy)",
+                 "limiter": "SM L1 data pipe (72 % busy avg / 79 % max under ncu: STG at 32 B/clk/SM + LDG.256 "
+                            "returns + camera LDS) on top of 108 us of arithmetic; the same store pattern alone "
+                            "runs at 6.5 TB/s (profiles/r01_k1_variant_sweep.txt, r01_ubench_planes.txt)"}
     line = {
         "metric": "voxel*views/s (volume build)", "value": vv / (ms_step * 1e-3), "unit": "voxel*views/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -524,16 +797,9 @@ def run_ours(args, rank, world, local):
                        "device barrier" if args.exchange == "fused" else f"x-slabs over {world} ranks + all-gather"),
                    "l2": "256 MiB memset between steps, outside the per-step event pairs",
                    "mask_fill": fill, "wall_s_timed_loop": round(wall, 4)},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": K1_NCU_DRAM_BYTES if (nv == 3 and world == 1) else None,
-                     "traffic_source": "profiles/r01_k1_256_kernel.txt (ncu --set full: dram__bytes_read.sum + "
-                                       "dram__bytes_write.sum of one launch; the tail of the writes is still in L2 "
-                                       "when the kernel ends, hence below the algorithmic bytes)",
-                     "kernel": "volume_agg_rowgroup_kernel @ 256^3", "ms": k1_ms,
-                     "algorithmic_bytes": abytes, "peak_source": f"MEASURED_PEAKS.json ({peak_kind}, burst copy)",
-                     "limiter": "SM L1 data pipe (72 % busy avg / 79 % max under ncu: STG at 32 B/clk/SM + LDG.256 "
-                                "returns + camera LDS) on top of 108 us of arithmetic; the same store pattern alone "
-                                "runs at 6.5 TB/s (profiles/r01_k1_variant_sweep.txt, r01_ubench_planes.txt)"},
+        "roofline": nvlink if world > 1 else k1_roof,
+        "roofline_k1": k1_roof,
+        "verified": verified,
         "cpu_baseline": cpu,
         "reference_ops_on_gpu": ref_gpu,
         "e2e": None if e2e_ms is None else {"value": vv / (e2e_ms * 1e-3), "unit": "voxel*views/s",
@@ -542,6 +808,7 @@ def run_ours(args, rank, world, local):
         "gpu_launches": (1 + len(DIMS)) * args.steps,  # per step: 1 pack+pose-inverse kernel + 5 aggregation kernels
         "clocks": clk,
         "render": render,
+        "lattice": lattice,
     }
     emit(line)
 
@@ -557,16 +824,17 @@ def main():
     ap.add_argument("--no-render", action="store_true", help="volume-build metric only")
     ap.add_argument("--render-steps", type=int, default=2, help="full-image renders timed for the render metric")
     ap.add_argument("--render-chunk", type=int, default=RENDER_CHUNK)
+    ap.add_argument("--no-lattice", action="store_true", help="skip the config-5 lattice leg")
+    ap.add_argument("--lattice-res", type=int, default=512)
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N > 1: slab exchange fused into K1's stores (NVLink peer memory) or NCCL all-gather + scatter")
     args = ap.parse_args()
     claim_stdout()
     rank, world, local = dist_setup(args.gpus)
+    args.warmup = max(args.warmup, 3)  # the same W on both arms
     if args.impl == "reference":
-        args.warmup = min(args.warmup, 2)  # each step is a full 3-5 s CPU build
         run_reference(args, rank, world)
     else:
-        args.warmup = max(args.warmup, 3)
         run_ours(args, rank, world, local)
     if world > 1:
         import torch.distributed as dist

@@ -352,6 +352,11 @@ int gens_patch_warp(const float *pts, const float *nrm, const float *images, con
 int gens_tv_reduce(const gens_pyramid_t *vols, const gens_pyramid_t *masks, int channels, int n_blocks,
                    double *out, void *stream);
 
+/* Measurement probe (bench.py): `iters` resident-operand tcgen05.mma.kind::tf32 128x256x8 instructions per CTA, one
+ * CTA per SM; out[0] = CTAs launched, out[1] = one accumulator element.  Dense TF32 peak = out[0] * iters *
+ * 2*128*256*8 flop / the CUDA-event time of the call (MEASURED_PEAKS.json has no TF32 figure). */
+int gens_tf32_mma_peak(int iters, double *out, void *stream);
+
 /* Tuning knob for profiling sessions: selects among compiled-in launch configurations of K1
  * (0 = the shipped one; 10 = packed kernel at every D % 64 == 0, 20 / 25 = row-group kernel with / without
  * frustum culling, 1/2/4/8/16 = rows per block of the packed kernel, 9 = scalar kernel, 7 = no stream fork)

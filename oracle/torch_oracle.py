@@ -241,3 +241,42 @@ class CpuOps:
         pgrid = torch.stack([2 * patch[..., 0] / (w - 1) - 1, 2 * patch[..., 1] / (h - 1) - 1], -1)
         ref = F.grid_sample(images[:1], pgrid.detach().view(1, -1, 1, 2), align_corners=True)
         return ref.view(1, -1, b, npx).permute(0, 2, 3, 1).contiguous(), src.contiguous()
+
+
+# ---- loss-side consumers of the hot path's outputs (reference models/losses/ncc.py:7-50, loss.py:23-84) ----------
+def compute_lncc(ref_gray, src_grays):
+    """Patch NCC score, restating compute_LNCC (ncc.py:7-50).  ref_gray (1,B,P,C), src_grays (S,B,P,C) with
+    P = patch^2 samples.  The reference runs five grouped patch x patch convolutions over zero-padded patches only to
+    read the centre pixel, i.e. plain sums over the P samples; the sums are taken directly here.  Returns (B,1)."""
+    ref = ref_gray.permute(1, 0, 3, 2)   # (B,1,C,P)
+    src = src_grays.permute(1, 0, 3, 2)  # (B,S,C,P)
+    npatch = src.shape[-1]
+    ref_sum, src_sum = ref.sum(-1), src.sum(-1)
+    ref_sq_sum, src_sq_sum = ref.pow(2).sum(-1), src.pow(2).sum(-1)
+    ref_src_sum = (ref * src).sum(-1)
+    u_ref, u_src = ref_sum / npatch, src_sum / npatch
+    cross = ref_src_sum - u_src * ref_sum - u_ref * src_sum + u_ref * u_src * npatch
+    ref_var = ref_sq_sum - 2 * u_ref * ref_sum + u_ref * u_ref * npatch
+    src_var = src_sq_sum - 2 * u_src * src_sum + u_src * u_src * npatch
+    cc = cross * cross / (ref_var * src_var + 1e-5)
+    ncc = torch.clamp(1 - cc, 0.0, 2.0).mean(dim=2)          # (B,S)
+    ncc, _ = torch.topk(ncc, 2, dim=1, largest=False)
+    return ncc.mean(dim=1, keepdim=True)
+
+
+def loss_forward(preds, targets, w):
+    """Loss.forward (loss.py:23-84) for the keys the synthetic fixtures provide; `w` = the train.loss conf block."""
+    valid = preds["valid_mask"].float()
+    color = (F.l1_loss(preds["color_fine"], targets["color"], reduction="none") * valid).sum() / (valid.sum() + 1e-5)
+    eikonal = preds["gradient_error"].mean()
+    sparse = torch.exp(-torch.abs(preds["sparse_sdf"]) * w["sparse_scale_factor"]).mean()
+    smooth = preds["smooth_error"].mean()
+    tv = preds["tv_reg"].mean()
+    ncc = compute_lncc(preds["ref_gray_val"], preds["sampled_gray_val"])
+    ncc_mask = valid * preds["mid_inside_sphere"]
+    mfc = 0.5 * ((ncc * ncc_mask).sum(dim=0) / (ncc_mask.sum(dim=0) + 1e-8)).squeeze(-1)
+    pseudo = torch.abs(preds["pseudo_sdf"]).mean() if "pseudo_sdf" in preds else torch.zeros((), device=mfc.device)
+    loss = (color * w["color_weight"] + eikonal * w["igr_weight"] + sparse * w["sparse_weight"] + mfc * w["mfc_weight"]
+            + smooth * w["smooth_weight"] + tv * w["tv_weight"] + pseudo * w["pseudo_sdf_weight"])
+    return {"loss": loss, "color_loss": color, "eikonal_loss": eikonal, "sparse_loss": sparse, "mfc_loss": mfc,
+            "smooth_loss": smooth, "tv_loss": tv, "pseudo_sdf_loss": pseudo}

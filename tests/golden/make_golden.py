@@ -196,8 +196,92 @@ def golden_render():
           "of", rays_o.shape[0], "weight_sum mean", float(res["weight_sum"].mean()))
 
 
+TRAIN_DIMS = [32, 16, 8, 8, 4]   # every scale keeps visible voxels (an all-masked scale gives the reference a NaN TV gradient)
+TRAIN_HW = (96, 128)
+TRAIN_NV = 5          # config 3: 4 source views (confs/gens.conf:9)
+TRAIN_RAYS = 32
+# train.loss block of confs/gens.conf:47-58
+LOSS_CONF = dict(color_weight=1.0, sparse_scale_factor=100.0, sparse_weight=0.02, igr_weight=0.1, mfc_weight=1.0,
+                 smooth_weight=0.0001, tv_weight=0.0001, depth_weight=0.0, pseudo_sdf_weight=1.0,
+                 pseudo_depth_weight=0.05)
+
+
+def train_inputs():
+    """Deterministic inputs of the training fixture (config-3 shape, mini scene); tests rebuild them from the seeds."""
+    from gens_b200.synthetic import make_reg_volumes
+    scene = make_scene(TRAIN_HW[0], TRAIN_HW[1], TRAIN_NV, seed=31)
+    volumes = make_reg_volumes(TRAIN_DIMS, seed=31)
+    g = torch.Generator().manual_seed(77)
+    ro, rd = scene.rays(step=1)
+    sel = torch.randperm(ro.shape[0], generator=g)[:TRAIN_RAYS]
+    rays_o, rays_d = ro[sel].contiguous(), rd[sel].contiguous()
+    pseudo = torch.rand(256, 3, generator=g) * 1.0 - 0.5
+    target = torch.rand(TRAIN_RAYS, 3, generator=g)
+    return scene, volumes, rays_o, rays_d, pseudo, target
+
+
+def golden_train():
+    """The reference's training step on the mini scene: ImplicitSurface.forward("train") (implicit_surface.py:472-499,
+    incl. pseudo_pts) -> Loss.forward (models/losses/loss.py:23-84, weights of confs/gens.conf) -> backward().
+    Records every output, the loss terms and the gradients w.r.t. the five feature maps, the five volumes and every
+    MLP parameter -- the second-order path of SDFNetwork.gradient (sdf_network.py:131-153) included."""
+    sys.path.insert(0, HERE)
+    import ref_shims
+    ref_shims.install()
+    import models.modules.implicit_surface as IS
+    import models.losses.loss as LS
+    volume_mod = load_ref_module("models/modules/volume.py", "ref_volume")
+
+    torch.manual_seed(0)
+    surf = IS.ImplicitSurface(Conf(ref_shims.REF_CONF))
+    from gens_b200.config import Conf as FullConf  # the ConfigTree look-alike with `default=` getters
+    loss_fn = LS.Loss(FullConf(LOSS_CONF))
+    # geometric initialisation zeroes the weights that read the volume features; a small perturbation makes the
+    # gradients w.r.t. the volumes a real signal instead of second-order crumbs (the state_dict is recorded)
+    gp = torch.Generator().manual_seed(9)
+    with torch.no_grad():
+        for n_, p_ in surf.sdf_network.named_parameters():
+            if n_.endswith("weight_v"):
+                p_.add_(0.004 * torch.randn(p_.shape, generator=gp))
+    scene, volumes, rays_o, rays_d, pseudo, target = train_inputs()
+    with torch.no_grad():
+        _, masks = volume_mod.Volume(Conf(volume_dims=TRAIN_DIMS)).agg_mean_var(scene.features, scene.intrs, scene.c2ws)
+    vols = [v.clone().requires_grad_(True) for v in volumes]
+    feats = [f.clone().requires_grad_(True) for f in scene.features]
+    ipts = {"imgs": scene.imgs, "intrs": scene.intrs, "c2ws": scene.c2ws, "rays_o": rays_o, "rays_d": rays_d,
+            "near": scene.near, "far": scene.far, "pseudo_pts": pseudo}
+    torch.manual_seed(123)
+    res = surf("train", ipts, vols, masks, feats, feats, cos_anneal_ratio=0.7, step=3)
+    losses = loss_fn(res, {"color": target}, step=3)
+    losses["loss"].backward()
+
+    out = {"mask_fill": np.array([float(m.mean()) for m in masks])}
+    for k, v in surf.state_dict().items():
+        out["sd/" + k] = v.numpy()
+    for i, m in enumerate(masks):
+        out[f"mask{i}"] = m[0, 0].numpy().astype(np.uint8)
+    for k, v in res.items():
+        out["out/" + k] = v.detach().numpy()
+    for k, v in losses.items():
+        out["loss/" + k] = np.asarray(v.detach().numpy())
+    for n, p_ in surf.named_parameters():
+        if p_.grad is not None:
+            out["grad/param/" + n] = p_.grad.numpy()
+    for i, v in enumerate(vols):
+        out[f"grad/volume{i}"] = v.grad.numpy()
+    for i, f in enumerate(feats):
+        out[f"grad/feature{i}"] = (f.grad if f.grad is not None else torch.zeros_like(f)).numpy()
+    np.savez_compressed(os.path.join(HERE, "train.npz"), **out)
+    print("train.npz written; loss terms", {k: float(v) for k, v in losses.items()}, "mask fill", out["mask_fill"],
+          "valid rays", int(res["valid_mask"].sum()), "of", TRAIN_RAYS,
+          "| grad norms: params", float(sum((p_.grad ** 2).sum() for p_ in surf.parameters() if p_.grad is not None)) ** 0.5,
+          "volumes", [float(v.grad.norm()) for v in vols], "features", [float(f.grad.norm()) for f in feats if f.grad is not None])
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["volume", "render"]
+    if "train" in which:
+        golden_train()
     if "volume" in which:
         golden_volume()
     if "render" in which:

@@ -97,3 +97,20 @@ def test_oracle_lookup_volume_matches_reference(golden_dir):
     assert np.array_equal(tn, g["lv_nearest"])
     dd = torch.cat([torch_oracle.trilinear_dd(v, torch.from_numpy(pts)) for v in vols], -1).numpy()
     assert np.all(np.abs(dd - g["lv_feat"]) <= 1e-6 + 1e-5 * np.abs(g["lv_feat"]))
+
+
+def test_loss_restatement_matches_reference_loss_terms(golden_dir):
+    """oracle/torch_oracle.loss_forward + compute_lncc (restating models/losses/loss.py:23-84, ncc.py:7-50) on the
+    outputs the reference recorded for the training fixture reproduce the loss terms the reference's own Loss
+    computed from them (tests/golden/train.npz, written by make_golden.py train)."""
+    import sys
+    sys.path.insert(0, golden_dir)
+    from make_golden import LOSS_CONF, train_inputs
+    from oracle import torch_oracle
+    g = np.load(f"{golden_dir}/train.npz")
+    preds = {k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("out/")}
+    target = train_inputs()[-1]
+    got = torch_oracle.loss_forward(preds, {"color": target}, LOSS_CONF)
+    for k, v in got.items():
+        ref = float(g["loss/" + k])
+        assert abs(float(v) - ref) <= 1e-6 * max(abs(ref), 1.0), (k, float(v), ref)

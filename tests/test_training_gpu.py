@@ -120,3 +120,74 @@ def test_validate_forward_and_sdf_grid_drivers(cuda_lib):
                                x_range=parallel.shard_range(40, r, 3)) for r in range(3)]
         assert [s.shape[0] for s in slabs] == [13, 13, 14]
         assert torch.equal(torch.cat(slabs, 0), u)
+
+
+def test_training_step_matches_reference_golden_gradients(cuda_lib, golden_dir):
+    """Config-3-shaped mini scene (5 views, 32 rays, pseudo points): forward("train") + the reference's loss +
+    backward() through the CUDA training path against what the UNMODIFIED reference recorded on CPU
+    (tests/golden/train.npz <- make_golden.py train: implicit_surface.py:472-499, loss.py:23-84, the second-order
+    graph of sdf_network.py:131-153): all 19 outputs, the loss terms, and the gradients w.r.t. the five feature
+    maps, the five volumes and every MLP parameter.
+    Tolerance: outputs at north_star's 1e-4 (stated exceptions in parity.JUMPY); gradients are sums over ~4k samples
+    of products through the second-order graph, compared at rtol 1e-3 with an absolute floor of 2e-4 x the tensor's
+    largest entry (fp32 accumulation order differs between the CPU reference and the atomics of the backward kernels)."""
+    import sys
+    sys.path.insert(0, golden_dir)
+    from make_golden import LOSS_CONF, TRAIN_DIMS, train_inputs
+    from oracle import torch_oracle
+    from parity import JUMPY, mismatch
+    g = np.load(f"{golden_dir}/train.npz")
+    conf = gens_model_conf(perturb=0.0)["implicit_surface"]
+    torch.manual_seed(0)
+    surf = ImplicitSurface(conf)
+    surf.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd/")}, strict=True)
+    surf = surf.to(DEV)
+    scene, volumes, rays_o, rays_d, pseudo, target = train_inputs()
+    sg = scene.to(DEV)
+    masks = [torch.from_numpy(g[f"mask{i}"].astype(np.float32))[None, None].to(DEV) for i in range(len(TRAIN_DIMS))]
+    vols = [v.clone().to(DEV).requires_grad_(True) for v in volumes]
+    feats = [f.clone().to(DEV).requires_grad_(True) for f in scene.features]
+    ipts = {"imgs": sg.imgs, "intrs": sg.intrs, "c2ws": sg.c2ws, "rays_o": rays_o.to(DEV), "rays_d": rays_d.to(DEV),
+            "near": sg.near, "far": sg.far, "pseudo_pts": pseudo.to(DEV)}
+    projector.ATEN_CUDA_FLAVOUR = 0  # the golden run is the reference on CPU
+    try:
+        torch.manual_seed(123)
+        res = surf("train", ipts, vols, masks, feats, feats, cos_anneal_ratio=0.7, step=3)
+        losses = torch_oracle.loss_forward(res, {"color": target.to(DEV)}, LOSS_CONF)
+        losses["loss"].backward()
+    finally:
+        projector.ATEN_CUDA_FLAVOUR = 1
+    problems = []
+    for k in sorted(res):
+        ref = g["out/" + k]
+        got = res[k]
+        if ref.dtype == np.bool_:
+            if not np.array_equal(got.cpu().numpy(), ref):
+                problems.append(f"{k}: bool mismatch")
+            continue
+        kw = {"outlier_frac": JUMPY[k]} if k in JUMPY else {}
+        msg = mismatch(k, got, ref, **kw)
+        if msg:
+            problems.append(msg)
+    for k, v in losses.items():
+        ref = float(g["loss/" + k])
+        if abs(float(v) - ref) > 1e-4 * max(abs(ref), 1e-3):
+            problems.append(f"loss term {k}: {float(v)} vs {ref}")
+    def grad_check(name, got, ref):
+        if got is None:
+            if float(np.abs(ref).max()) > 0:
+                problems.append(f"{name}: missing gradient")
+            return
+        msg = mismatch(name, got, ref, rtol=1e-3, atol_scale=0.0 if ref.size == 0 else
+                       2e-4 * float(np.abs(ref).max()) / max(float(np.abs(ref).max()), 1.0))
+        if msg:
+            problems.append(msg)
+    for n, p in surf.named_parameters():
+        key = "grad/param/" + n
+        if key in g.files:
+            grad_check(key, p.grad, g[key])
+    for i, v in enumerate(vols):
+        grad_check(f"grad/volume{i}", v.grad, g[f"grad/volume{i}"])
+    for i, f in enumerate(feats):
+        grad_check(f"grad/feature{i}", f.grad, g[f"grad/feature{i}"])
+    assert not problems, "\n".join(problems)

@@ -2,6 +2,9 @@
 
     python tools/summarize_ncu.py launches gpurun_out/launches_bench.csv profiles/r01_launches_bench.txt
     python tools/summarize_ncu.py kernels  gpurun_out/r01_render.ncu-rep   profiles/r01_render_kernels.txt
+    python tools/summarize_ncu.py traffic  gpurun_out/r02_k1_256.ncu-rep   profiles/r02_k1_256_traffic.json
+        (DRAM bytes of the captured K1 launch + the hash of the kernel sources the .so was built from -- run it
+         BEFORE touching the kernel sources again; bench.py refuses a capture whose hash is stale)
 """
 import collections
 import csv
@@ -53,5 +56,28 @@ def kernels(src, dst):
             f.write(r[ix["Kernel Name"]].split("(")[0][-40:].ljust(42) + " ".join(f"{r[ix[c]]:>12.12}" for c in cols) + "\n")
 
 
+def traffic(src, dst):
+    import json
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ix = {h: i for i, h in enumerate(hdr)}
+    r = rows[2]  # first captured launch
+
+    def nbytes(name):
+        v, u = float(r[ix[name]].replace(",", "")), units[ix[name]].lower()
+        return int(round(v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]))
+    rec = {"kernel": r[ix["Kernel Name"]][:160], "nv": 3, "D": 256,
+           "dram_bytes_read": nbytes("dram__bytes_read.sum"), "dram_bytes_write": nbytes("dram__bytes_write.sum"),
+           "gpu_time_us_under_ncu": float(r[ix["gpu__time_duration.sum"]].replace(",", "")),
+           "kernel_source_sha256_16": bench.k1_source_hash(), "kernel_sources": list(bench.K1_SOURCES),
+           "source": f"{src} (ncu --set full --clock-control none, one launch)"}
+    json.dump(rec, open(dst, "w"), indent=1)
+    print(rec)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernels": kernels}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "kernels": kernels, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
