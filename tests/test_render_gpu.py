@@ -330,3 +330,57 @@ def test_sharded_lattice_and_ray_sharding_two_gpus():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("sharded lattice bit-identical to the 1-GPU lattice: True") == 2, r.stdout[-2000:]
     assert r.stdout.count("ray-sharded render matches the 1-GPU render: True") == 2, r.stdout[-2000:]
+
+
+def test_full_render_big_pyramid_matches_reference(cuda_lib, golden_dir, use_tc):
+    """The same golden comparison through a pyramid whose finest scale is 128^3 built at 240x320 (tests/golden/
+    render_big.npz <- make_golden.py render_big): K1's masks at 128...8 in the CPU flavour must be the recorded ones
+    bit for bit, then both render paths (autograd and the no-grad kernels) against the reference's outputs."""
+    import sys
+    sys.path.insert(0, golden_dir)
+    from make_golden import BIG_DIMS, big_render_inputs
+    from gens_b200 import _lib
+    g = np.load(f"{golden_dir}/render_big.npz")
+    small = np.load(f"{golden_dir}/render.npz")
+    conf = gens_model_conf(perturb=0.0)["implicit_surface"]
+    torch.manual_seed(0)
+    surf = ImplicitSurface(conf)
+    surf.load_state_dict({k[3:]: torch.from_numpy(small[k]) for k in small.files if k.startswith("sd/")}, strict=True)
+    surf = surf.to(DEV)
+    host, volumes, ro, rd = big_render_inputs()
+    scene = host.to(DEV)
+    volumes = [v.to(DEV) for v in volumes]
+    # K1 in the reference's CPU flavour (true division by (W-1)/2) on the world-to-camera matrices the reference's
+    # own CPU torch.inverse produced when the fixture was recorded
+    from gens_b200.volume import agg_scale_into, pack_feature_maps
+    w2c = torch.from_numpy(g["w2c"]).to(DEV)
+    masks = []
+    for i, d in enumerate(BIG_DIMS):
+        k = host.intrs.clone()
+        k[:, :2] *= 0.5 ** i
+        vol = torch.empty((8, d, d, d), device=DEV)
+        msk = torch.empty((d, d, d), device=DEV)
+        agg_scale_into(pack_feature_maps(scene.features[i]), scene.features[i].shape[-2:], w2c, k.to(DEV), 1.0,
+                       torch.linspace(-1, 1, d).to(DEV), d, vol, msk, None, 1, _lib.DIV_TRUE)
+        ref_bits = np.unpackbits(g[f"maskbits{i}"])[: d ** 3].reshape(d, d, d)
+        assert np.array_equal(msk.cpu().numpy().astype(np.uint8), ref_bits), f"mask {d}^3 differs from the reference"
+        masks.append(msk[None, None])
+    ro, rd = ro.to(DEV), rd.to(DEV)
+    ref_keys = sorted(k[7:] for k in g.files if k.startswith("render/"))
+    skip = {"valid_mask", "inside_sphere", "mid_inside_sphere", "sparse_sdf"}
+    projector.ATEN_CUDA_FLAVOUR = 0
+    try:
+        for nograd in (False, True):
+            torch.manual_seed(123)
+            with torch.set_grad_enabled(not nograd):
+                res = surf.render(ro, rd, scene.near, scene.far, volumes, masks, scene.imgs, scene.features,
+                                  scene.features, scene.intrs, scene.c2ws, 1.0, None)
+            assert sorted(res.keys()) == ref_keys
+            assert np.array_equal(res["valid_mask"].cpu().numpy(), g["render/valid_mask"])
+            assert np.array_equal(res["mid_inside_sphere"].cpu().numpy(), g["render/mid_inside_sphere"])
+            problems = [_mismatch(k, res[k], g["render/" + k], **_render_tolerances(k, use_tc)) for k in ref_keys
+                        if k not in skip]
+            problems = [p for p in problems if p]
+            assert not problems, f"nograd={nograd}:\n" + "\n".join(problems)
+    finally:
+        projector.ATEN_CUDA_FLAVOUR = 1

