@@ -386,18 +386,34 @@ def gpu_build_baseline(dev, sc, timed, vols_ours, masks_ours):
 
 
 # --------------------------------------------------------------------------- reference arm
+def cpu_reference_build_fn(sc):
+    """(callable, kind): the reference's own Volume.agg_mean_var (models/modules/volume.py:13-63, loaded by path from the
+    staged copy baseline/_ref -- pure PyTorch, runs on host tensors unmodified) when it is staged, else the ATen-op
+    restatement oracle/torch_oracle.agg_mean_var."""
+    from gens_b200.config import Conf
+    path = os.path.join(ROOT, "baseline", "_ref", "GenS", "models", "modules", "volume.py")
+    if os.path.exists(path):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("gens_ref_volume_cpu", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        vol = mod.Volume(Conf(volume_dims=DIMS))
+        return (lambda: vol.agg_mean_var(sc.features, sc.intrs, sc.c2ws)), "reference"
+    from oracle import torch_oracle
+    return (lambda: torch_oracle.agg_mean_var(sc.features, sc.intrs, sc.c2ws, DIMS)), "port"
+
+
 def run_reference(args, rank, world):
-    """The reference's own CPU implementation of the path: the same ATen op sequence as
-    models/modules/volume.py on host tensors with every host thread (oracle/torch_oracle.py; the
-    reference is Python, so there is no oracle/_ref binary -- kind = "port")."""
+    """The reference's own CPU implementation of the path on the host cores, every host thread: the unmodified
+    Volume.agg_mean_var from baseline/_ref (kind "reference") or, when that copy is not staged, the ATen-op restatement
+    (oracle/torch_oracle.py, kind "port")."""
     if rank != 0:
         return
     from gens_b200.synthetic import make_scene
-    from oracle import torch_oracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sc = make_scene(HW[0], HW[1], args.nv, seed=0, with_images=False)
-    run = lambda: torch_oracle.agg_mean_var(sc.features, sc.intrs, sc.c2ws, DIMS)
+    run, kind = cpu_reference_build_fn(sc)
     with torch.no_grad():
         for _ in range(args.warmup):
             run()
@@ -413,8 +429,10 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"config2: {HW[0]}x{HW[1]}, {args.nv} views, volume dims {DIMS}, full 5-scale build",
                    "device": "host cpu"},
-        "cpu_baseline": {"value": val, "unit": "voxel*views/s", "cores": cores, "kind": "port",
-                         "sample": "full 5-scale build per step (ATen-op restatement of volume.py on host tensors)"},
+        "cpu_baseline": {"value": val, "unit": "voxel*views/s", "cores": cores, "kind": kind,
+                         "sample": "full 5-scale build per step (" + (
+                             "the unmodified reference's Volume.agg_mean_var from baseline/_ref on host tensors"
+                             if kind == "reference" else "ATen-op restatement of volume.py on host tensors") + ")"},
         "e2e": {"value": val, "unit": "voxel*views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "render": None if render is None else {
@@ -588,6 +606,110 @@ def bench_render(args, rank, world, dev, sc, host, vol_mod, timed):
     return res
 
 
+LOSS_W = dict(color_weight=1.0, sparse_scale_factor=100.0, sparse_weight=0.02, igr_weight=0.1, mfc_weight=1.0,
+              smooth_weight=0.0001, tv_weight=0.0001, pseudo_sdf_weight=1.0)  # confs/gens.conf:47-58
+
+
+def training_loss(preds, target, lncc):
+    """What the reference's runner computes from the hot path's outputs (models/losses/loss.py:23-84, conf weights);
+    `lncc` = the compute_LNCC implementation of the arm (K11 on the GPU arm, the ATen restatement on the CPU arm)."""
+    valid = preds["valid_mask"].float()
+    color = ((preds["color_fine"] - target).abs() * valid).sum() / (valid.sum() + 1e-5)
+    sparse = torch.exp(-preds["sparse_sdf"].abs() * LOSS_W["sparse_scale_factor"]).mean()
+    ncc_mask = valid * preds["mid_inside_sphere"]
+    mfc = 0.5 * ((lncc(preds["ref_gray_val"], preds["sampled_gray_val"]) * ncc_mask).sum(0) / (ncc_mask.sum(0) + 1e-8)).squeeze(-1)
+    return (color * LOSS_W["color_weight"] + preds["gradient_error"].mean() * LOSS_W["igr_weight"]
+            + sparse * LOSS_W["sparse_weight"] + mfc * LOSS_W["mfc_weight"] + preds["smooth_error"].mean() * LOSS_W["smooth_weight"]
+            + preds["tv_reg"].mean() * LOSS_W["tv_weight"] + preds["pseudo_sdf"].abs().mean() * LOSS_W["pseudo_sdf_weight"])
+
+
+def train_step_fn(surf, sc, vols, masks, feats, n_rays, lncc, dev):
+    """One config-3 training step of the ray half: forward("train") with pseudo points + loss + backward()."""
+    g = torch.Generator().manual_seed(17)
+    ro_all, rd_all = sc.rays(step=1)
+    sel = torch.randperm(ro_all.shape[0], generator=g)[:n_rays].to(ro_all.device)
+    ipts = {"imgs": sc.imgs, "intrs": sc.intrs, "c2ws": sc.c2ws, "rays_o": ro_all[sel].contiguous(),
+            "rays_d": rd_all[sel].contiguous(), "near": sc.near, "far": sc.far,
+            "pseudo_pts": (torch.rand(2048, 3, generator=g) * 1.0 - 0.5).to(dev)}
+    target = torch.rand(n_rays, 3, generator=g).to(dev)
+    params = [p for p in surf.parameters()] + list(vols) + list(feats)
+
+    def step():
+        for p in params:
+            p.grad = None
+        out = surf("train", ipts, vols, masks, feats, feats, cos_anneal_ratio=0.5, step=10)
+        loss = training_loss(out, target, lncc)
+        loss.backward()
+        return loss.detach()
+    return step
+
+
+def bench_train(args, rank, world, dev, timed):
+    """BASELINE config 3 (480x640, 5 views = 4 sources, 512-ray batches, forward + backward incl. the feature-metric
+    patches and the pseudo-point SDF query).  Two legs, each with its CPU arm on a bounded sample:
+      * ray half: ImplicitSurface.forward("train") + loss + backward() w.r.t. MLP parameters, the five volumes and the
+        five feature maps (the differentiable look-up / reprojection / LNCC kernels; dense layers on cuBLAS);
+      * volume half: Volume.agg_mean_var forward + backward to the feature maps (K1 + K1b).
+    Training is replicas-only across GPUs (the reference's DDP): every rank runs the same step, the line
+    reports rank 0's time x world as weak scaling."""
+    from gens_b200.losses import compute_LNCC
+    from gens_b200.synthetic import make_scene
+    from gens_b200.volume import Volume
+    nv, n_rays = 5, 512
+    host = make_scene(HW[0], HW[1], nv, seed=0, with_images=True)
+    sc = host.to(dev)
+    surf = build_surface(dev)
+    surf.train()
+    vols = [v.requires_grad_(True) for v in smooth_volumes(DIMS, dev)]
+    feats = [f.clone().requires_grad_(True) for f in sc.features]
+    vol_mod = Volume(volume_dims=DIMS)
+    with torch.no_grad():
+        _, masks = vol_mod.agg_mean_var(sc.features, sc.intrs, sc.c2ws)
+    step = train_step_fn(surf, sc, vols, masks, feats, n_rays, compute_LNCC, dev)
+    ms, _ = timed(step, 5, 3)
+    # volume half: forward + backward with a fixed upstream gradient
+    ups = None
+
+    def build_step():
+        nonlocal ups
+        for f in feats:
+            f.grad = None
+        v, _ = vol_mod.agg_mean_var(feats, sc.intrs, sc.c2ws)
+        if ups is None:
+            ups = [torch.randn_like(x) for x in v]
+        torch.autograd.backward(v, ups)
+    b_ms, _ = timed(build_step, 5, 3)
+    res = {"metric": "ray-samples/s (config 3: training step of the ray half, forward + backward)",
+           "value": world * n_rays * 128 / (ms * 1e-3), "unit": "ray-samples/s", "ms_per_step": ms, "rays": n_rays,
+           "views": nv, "steps": 5, "warmup": 3, "scaling": "weak (replicas, the reference's DDP)", "n_gpus": world,
+           "volume_build_fwd_bwd": {"ms_per_step": b_ms, "value": world * voxel_views(nv) / (b_ms * 1e-3),
+                                    "unit": "voxel*views/s (forward + backward to the feature maps)"},
+           "note": "dense SDF / colour layers run on cuBLAS fp32 under autograd; look-ups (K3 fwd/bwd/bwd2), "
+                   "reprojection (K6 fwd/bwd), LNCC (K11 fwd/bwd), up-sampling (K5) and K1/K1b are this repo's kernels"}
+    del step, build_step
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import torch_oracle
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cpu = torch.device("cpu")
+        c_rays, c_dims = 64, DIMS
+        csurf = build_surface(cpu, ops=torch_oracle.CpuOps)
+        csurf.train()
+        cvols = [v.requires_grad_(True) for v in smooth_volumes(c_dims, cpu)]
+        cfeats = [f.clone().requires_grad_(True) for f in host.features]
+        cmasks = [m.cpu() for m in masks]
+        cstep = train_step_fn(csurf, host, cvols, cmasks, cfeats, c_rays, torch_oracle.compute_lncc, cpu)
+        cstep()
+        t0 = time.perf_counter()
+        cstep()
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": c_rays * 128 / dt, "unit": "ray-samples/s", "cores": cores, "kind": "port",
+                               "ms": dt * 1e3, "sample": f"{c_rays} rays x 128 samples, forward + backward, same volumes "
+                               f"{c_dims} and 5 views (ATen-op restatement on host tensors, 1 step after 1 warm-up)"}
+    return res
+
+
 def bench_lattice(args, rank, world, dev, timed):
     """BASELINE config 5: the mesh-extraction SDF lattice u = -sdf on 512^3 points (reference implicit_surface.py:
     407-421: 512 sequential 64^3 blocks, each with a .cpu() sync) through ImplicitSurface.sdf_grid -- fused 5-scale
@@ -718,6 +840,7 @@ def run_ours(args, rank, world, local):
         if not args.no_render:
             render = bench_render(args, rank, world, dev, sc, host, vol_mod, timed)
         lattice = None if args.no_lattice else bench_lattice(args, rank, world, dev, timed)
+        train = None if args.no_train else bench_train(args, rank, world, dev, timed)
     clk = clocks.summary()
 
     fill = None
@@ -730,6 +853,13 @@ def run_ours(args, rank, world, local):
     verified, nvlink = None, None
     if world > 1:
         with torch.no_grad():
+            if args.exchange == "fused":
+                # poison the exchange buffers of every rank first: the timed builds left the very same values there,
+                # so a tile nobody writes (owner's peer store or local zero fill) must show up as NaN
+                for buf in _par.SlabExchange.get(DIMS, dev, None).bufs:
+                    buf.fill_(float("nan"))
+                torch.cuda.synchronize(dev)
+                barrier(world)
             sv, sm = sharded_build(vol_mod, sc.features, sc.intrs, sc.c2ws, rank, world)
             sv, sm = [v.clone() for v in sv], [m.clone() for m in sm]
             lv, lm = vol_mod.agg_mean_var(sc.features, sc.intrs, sc.c2ws)
@@ -737,7 +867,8 @@ def run_ours(args, rank, world, local):
             same = all(torch.equal(a, b) for a, b in zip(sv, lv)) and all(torch.equal(a, b) for a, b in zip(sm, lm))
             del sv, sm, lv, lm
         verified = {"slabs_bit_identical": all_ranks_true(same, world, dev), "checked_on": f"all {world} ranks",
-                    "against": "local 1-GPU Volume.agg_mean_var on every rank (torch.equal on all volumes and masks)"}
+                    "against": "local 1-GPU Volume.agg_mean_var on every rank (torch.equal on all volumes and masks; "
+                               "exchange buffers NaN-poisoned on every rank before the checked build)"}
         ingest, live_frac = exchange_ingest_bytes(sc, rank, world, dev)
         ingest = int(max_over_ranks(float(ingest), world, dev))
         link_peak = 770.0  # GB/s per direction per GPU: peer-copy rate measured on this pool (B200_PROFILING.md)
@@ -753,19 +884,20 @@ def run_ours(args, rank, world, local):
     # ---- CPU baseline (rank 0, N=1): bounded sample of the same workload --------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import torch_oracle
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
+        run_cpu, cpu_kind = cpu_reference_build_fn(host)
         with torch.no_grad():
-            torch_oracle.agg_mean_var(host.features, host.intrs, host.c2ws, DIMS)
+            run_cpu()
             best = 1e30
             for _ in range(2):
                 t0 = time.perf_counter()
-                torch_oracle.agg_mean_var(host.features, host.intrs, host.c2ws, DIMS)
+                run_cpu()
                 best = min(best, time.perf_counter() - t0)
-        cpu = {"value": voxel_views(nv) / best, "unit": "voxel*views/s", "cores": cores, "kind": "port",
-               "sample": "full 5-scale build, best of 2 after 1 warm-up (ATen-op restatement of volume.py, "
-                         "all host threads)", "ms": best * 1e3}
+        cpu = {"value": voxel_views(nv) / best, "unit": "voxel*views/s", "cores": cores, "kind": cpu_kind,
+               "sample": "full 5-scale build, best of 2 after 1 warm-up ("
+                         + ("the unmodified reference's Volume.agg_mean_var from baseline/_ref" if cpu_kind == "reference"
+                            else "ATen-op restatement of volume.py") + ", all host threads)", "ms": best * 1e3}
 
     ref_gpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -809,6 +941,7 @@ def run_ours(args, rank, world, local):
         "clocks": clk,
         "render": render,
         "lattice": lattice,
+        "train_step": train,
     }
     emit(line)
 
@@ -825,6 +958,7 @@ def main():
     ap.add_argument("--render-steps", type=int, default=2, help="full-image renders timed for the render metric")
     ap.add_argument("--render-chunk", type=int, default=RENDER_CHUNK)
     ap.add_argument("--no-lattice", action="store_true", help="skip the config-5 lattice leg")
+    ap.add_argument("--no-train", action="store_true", help="skip the config-3 training-step leg")
     ap.add_argument("--lattice-res", type=int, default=512)
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N > 1: slab exchange fused into K1's stores (NVLink peer memory) or NCCL all-gather + scatter")

@@ -304,6 +304,14 @@ def golden_train():
     feats = [f.clone().requires_grad_(True) for f in scene.features]
     ipts = {"imgs": scene.imgs, "intrs": scene.intrs, "c2ws": scene.c2ws, "rays_o": rays_o, "rays_d": rays_d,
             "near": scene.near, "far": scene.far, "pseudo_pts": pseudo}
+    captured = {}
+    real_core = surf.render_core
+
+    def spy(rays_o_, rays_d_, z_vals, *a, **k):
+        captured["z_vals"] = z_vals.detach().clone()
+        return real_core(rays_o_, rays_d_, z_vals, *a, **k)
+
+    surf.render_core = spy
     torch.manual_seed(123)
     res = surf("train", ipts, vols, masks, feats, feats, cos_anneal_ratio=0.7, step=3)
     losses = loss_fn(res, {"color": target}, step=3)
@@ -314,6 +322,7 @@ def golden_train():
         out["sd/" + k] = v.numpy()
     for i, m in enumerate(masks):
         out[f"mask{i}"] = m[0, 0].numpy().astype(np.uint8)
+    out["z_vals"] = captured["z_vals"].numpy()  # the 128 depths per ray the reference composited (after up-sampling)
     for k, v in res.items():
         out["out/" + k] = v.detach().numpy()
     for k, v in losses.items():

@@ -157,19 +157,24 @@ def test_forward_train_loss_backward_matches_reference(arms):
         assert abs(l_our[k] - l_ref[k]) <= 1e-3 * max(abs(l_ref[k]), 1e-3), (k, l_our[k], l_ref[k])
     # gradients of every parameter the reference trains
     assert set(g_ref) == set(g_our), set(g_ref) ^ set(g_our)
+    # error of a tensor's gradient relative to its own largest entry, but never finer than 1e-3 of the largest
+    # gradient entry of its group: parameters whose true gradient is zero (a bias feeding a normalisation layer, the
+    # colour network's scalar `s`) hold cancellation noise of that size in BOTH runs
+    groups = {"feature_network": [], "reg_network": [], "implicit_surface": []}
+    top = {gname: max(float(g_ref[n].abs().max()) for n in g_ref if n.startswith(gname)) for gname in groups}
     worst = {}
     for n in g_ref:
-        worst[n] = _rel(g_our[n], g_ref[n])
-    top = sorted(worst.items(), key=lambda kv: -kv[1])[:8]
-    print("train gradients, worst max |diff| / max |ref|:", [(n, f"{v:.2e}") for n, v in top])
-    groups = {"feature_network": [], "reg_network": [], "implicit_surface": []}
-    for n, v in worst.items():
-        for gname in groups:
-            if n.startswith(gname):
-                groups[gname].append(v)
+        gname = next(k for k in groups if n.startswith(k))
+        scale = max(float(g_ref[n].abs().max()), 1e-3 * top[gname])
+        worst[n] = float((g_our[n] - g_ref[n]).abs().max()) / scale
+        groups[gname].append(worst[n])
+    print("train gradients, worst:", [(n, f"{v:.2e}") for n, v in sorted(worst.items(), key=lambda kv: -kv[1])[:8]])
     for gname, vals in groups.items():
         assert vals, gname
-        print(f"{gname}: {len(vals)} tensors, median {float(np.median(vals)):.2e}, max {max(vals):.2e}")
+        print(f"{gname}: {len(vals)} tensors, largest |grad| {top[gname]:.2e}, median err {float(np.median(vals)):.2e}, "
+              f"max err {max(vals):.2e}")
+        # the importance samples of the patched arm come from the 3xTF32 kernel (placed <= 1e-4 away): gradients move
+        # by ~1e-3 of their scale; 5e-3 median / 5e-2 worst are the stated bounds
         assert float(np.median(vals)) <= 5e-3, (gname, float(np.median(vals)))
         assert max(vals) <= 5e-2, (gname, max(vals))
 

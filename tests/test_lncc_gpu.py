@@ -34,9 +34,13 @@ def test_lncc_forward_backward_match_oracle(cuda_lib, ns, b, patch, c):
     assert got.shape == (b, 1)
     # sums of 121 products in a different order than the CPU reduction: 1e-5 absolute on a [0, 2] score
     assert torch.allclose(got.cpu(), want.detach(), rtol=1e-4, atol=1e-5), float((got.cpu() - want).abs().max())
-    for name, a, e in (("ref", rg.grad.cpu(), rc.grad), ("src", sg.grad.cpu(), sc.grad)):
+    # ray 0 holds the constant source patch: its variance is 0 in exact arithmetic and fp32 cancellation noise of
+    # either sign in any implementation (cc = noise^2 / (noise + 1e-5)): the score is pinned above, the gradient of
+    # that ray is only required to be finite -- the reference's own autograd returns noise there as well
+    for name, a, e in (("ref", rg.grad.cpu()[:, 1:], rc.grad[:, 1:]), ("src", sg.grad.cpu()[:, 1:], sc.grad[:, 1:])):
         scale = float(e.abs().max())
         assert float((a - e).abs().max()) <= 2e-4 * scale + 1e-7, (name, float((a - e).abs().max()), scale)
+    assert bool(torch.isfinite(rg.grad).all()) and bool(torch.isfinite(sg.grad).all())
 
 
 def test_lncc_matches_reference_recorded_patches(cuda_lib, golden_dir):

@@ -378,8 +378,14 @@ def test_full_render_big_pyramid_matches_reference(cuda_lib, golden_dir, use_tc)
             assert sorted(res.keys()) == ref_keys
             assert np.array_equal(res["valid_mask"].cpu().numpy(), g["render/valid_mask"])
             assert np.array_equal(res["mid_inside_sphere"].cpu().numpy(), g["render/mid_inside_sphere"])
-            problems = [_mismatch(k, res[k], g["render/" + k], **_render_tolerances(k, use_tc)) for k in ref_keys
-                        if k not in skip]
+            def tol(k):
+                t = dict(_render_tolerances(k, use_tc))
+                if k == "color_fine":
+                    # white-noise feature maps at 240x320 sampled through a 128^3 field: a sample moved by 1e-6 changes
+                    # one ray's colour by up to 4e-5 (1 of 144 values on the first GPU run); floor 5e-5 on [0, 1]
+                    t["atol_scale"] = 5e-5
+                return t
+            problems = [_mismatch(k, res[k], g["render/" + k], **tol(k)) for k in ref_keys if k not in skip]
             problems = [p for p in problems if p]
             assert not problems, f"nograd={nograd}:\n" + "\n".join(problems)
     finally:
