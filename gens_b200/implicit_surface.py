@@ -78,10 +78,17 @@ class ImplicitSurface(nn.Module):
         self.fused_upsample = True   # K5 warp-per-ray kernels for up_sample / cat_z_vals (CUDA tensors)
 
     def _fold_sdf(self):
-        """Weight-normalised SDF layers folded once per render / lattice call."""
+        """Weight-normalised SDF layers folded (and packed for the tensor-core kernels) once per parameter version:
+        validate() calls render() per 256-ray chunk with unchanged weights."""
         if self.ops is _cuda_ops:
             from .sdf_analytic import FoldedSDF
-            return FoldedSDF(self.sdf_network)
+            key = tuple((p.data_ptr(), p._version) for p in self.sdf_network.parameters())
+            hit = getattr(self, "_folded_cache", None)
+            if hit is None or hit[0] != key or torch.is_grad_enabled():
+                hit = (key, FoldedSDF(self.sdf_network))
+                if not torch.is_grad_enabled():
+                    self._folded_cache = hit
+            return hit[1]
         return self.sdf_network.folded_weights()
 
     # ------------------------------------------------------------------ hierarchical sampling
@@ -165,7 +172,8 @@ class ImplicitSurface(nn.Module):
         """Unit SDF gradient at the zero-crossing points, in the reference camera frame (reference :300-302)."""
         b = pts_sdf0.shape[0]
         if analytic:
-            _, g_sdf0, _ = self.sdf_network.value_grad_smooth_nograd(pts_sdf0.reshape(-1, 3), volumes, False)
+            _, g_sdf0, _ = self.sdf_network.value_grad_smooth_nograd(pts_sdf0.reshape(-1, 3), volumes, False,
+                                                                     self._fold_sdf())
         else:
             g_sdf0, _ = self.sdf_network.gradient(pts_sdf0.reshape(-1, 3), volumes)
         g_sdf0 = g_sdf0.reshape(b, 1, 3)
@@ -235,11 +243,12 @@ class ImplicitSurface(nn.Module):
         if analytic:
             # inference: one hand-differentiated sweep (4 GEMM passes, no graph) instead of forward +
             # two nested autograd.grad calls
-            sdf_val, grad_all, smooth_all = self.sdf_network.value_grad_smooth_nograd(pts, volumes)
+            sdf_val, grad_all, smooth_all = self.sdf_network.value_grad_smooth_nograd(pts, volumes, True,
+                                                                                      self._fold_sdf())
         else:
             sdf_val = self.sdf_network(pts, volumes)[:, :1]
             grad_all, smooth_all = self.sdf_network.gradient(pts.clone(), volumes)
-        if analytic and self.fused_composite:
+        if analytic and self.fused_composite and n <= 160:  # K7 holds up to 160 samples per ray in registers
             return self._render_core_fused(rays_o, rays_d, z_vals, sample_dist, pts, voxel_mask, evaluated, sdf_val,
                                            grad_all, smooth_all, volumes, mask_volumes, features, match_features,
                                            imgs, intrs, c2ws, cos_anneal_ratio, step)

@@ -120,10 +120,12 @@ class SDFNetwork(nn.Module):
         return g, h
 
     # -- inference path ---------------------------------------------------------------------------
-    def value_grad_smooth_nograd(self, pts, volumes, need_smooth=True):
-        """(sdf, grad, smooth) without an autograd graph (CUDA only; see gens_b200/sdf_analytic.py)."""
+    def value_grad_smooth_nograd(self, pts, volumes, need_smooth=True, folded=None):
+        """(sdf, grad, smooth) without an autograd graph (CUDA only; see gens_b200/sdf_analytic.py).  `folded` = a
+        FoldedSDF of the current weights (ImplicitSurface keeps one per parameter version)."""
         from . import sdf_analytic
-        return sdf_analytic.value_grad_smooth(self, pts, volumes, None, need_smooth)
+        fw = folded if isinstance(folded, sdf_analytic.FoldedSDF) else None
+        return sdf_analytic.value_grad_smooth(self, pts, volumes, fw, need_smooth)
 
     def folded_weights(self):
         """Effective (weight, bias) per layer with the weight normalisation folded in."""

@@ -125,6 +125,10 @@ def fused_sharded_agg_mean_var(volume_module, features, intrs, c2ws, rank: int, 
     vols, masks = agg_mean_var(features, intrs, c2ws, dims, min_vis_view, slabs, volume_module.div_mode,
                                peer_outs=peer_outs)
     hdl.barrier(channel=0)  # every rank's stores into this buffer have landed (stream-ordered on all ranks)
+    # the exchange buffers are written through raw pointers (no _version bump): derived-data caches keyed on tensor
+    # versions (channels-last copies, the TV value) must not outlive a build into the same storage
+    from . import projector
+    projector.clear_caches()
     return vols, masks
 
 

@@ -65,6 +65,19 @@ class FoldedSDF:
             self.off.append(self.off[-1] + self.fo[l])  # off[l-1] = column of layer l in the feature part
         self._packed = None
         self._packed_rev = None
+        self._tc_ok = None
+
+    def tc_supported(self) -> bool:
+        """True when the tensor-core kernels take this network (layers up to 128 wide, encodings that fit the
+        resident operands); otherwise the cuBLAS fp32 chain of the same functions is used."""
+        if self._tc_ok is None:
+            try:
+                self.packed()
+                self.packed_rev()
+                self._tc_ok = True
+            except RuntimeError:
+                self._tc_ok = False
+        return self._tc_ok
 
     def packed_rev(self):
         """The transposed network for the tensor-core reverse sweep (built on first use)."""
@@ -110,7 +123,7 @@ def value_grad_smooth(net, pts: torch.Tensor, volumes, folded: Optional[FoldedSD
     pos, fe = new(2 * n, fw.pe_in), new(2 * n, fw.pe_feat)
     _c(L.gens_sdf_encode(P(pts), P(feats), P(dfeats), n, fw.scale, _U, fw.multires, fw.feat_multires, nf, P(pos),
                          P(fe), st), "gens_sdf_encode")
-    if USE_TC:
+    if USE_TC and fw.tc_supported():
         # whole MLP on the tensor cores: one persistent kernel forward (value + tangent), one in reverse
         from . import mlp_tc
         sdf, s1, t2 = mlp_tc.sdf_jvp(fw.packed(), pos, fe, n)
@@ -211,7 +224,7 @@ def value_only(net, pts: torch.Tensor, volumes, folded: Optional[FoldedSDF] = No
     pos, fe = new(n, fw.pe_in), new(n, fw.pe_feat)
     _c(L.gens_sdf_encode(P(pts), P(feats), None, n, fw.scale, _U, fw.multires, fw.feat_multires, nf, P(pos), P(fe), st),
        "gens_sdf_encode")
-    if USE_TC:
+    if USE_TC and fw.tc_supported():
         from . import mlp_tc
         return mlp_tc.sdf_values(fw.packed(), pos, fe)
     featpart = fe @ fw.wf_t
