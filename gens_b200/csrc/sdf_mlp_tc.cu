@@ -347,7 +347,10 @@ __device__ __forceinline__ void produce_weights(const Ctx& c, const float* __res
 // ===== MMA issuer: the whole warp walks the k-steps (uniform control flow and addresses), one elected lane
 // issues.  Per k-step: 2 x (Ah.Bh + Al.Bh + Ah.Bl) over 8 channels each.  WAIT_IN: a tile starts when the
 // epilogue warps have staged its encodings (forward kernels).
-template <bool WAIT_IN>
+// FOUR: also accumulate Al.Bl (the value kernel: its SDF decides where the hierarchical sampling puts the samples, and
+// the inverse CDF at inv_s up to 512 amplifies an SDF error of 1e-5 into sample depths moved by 1e-4; the fourth term
+// brings the products to fp32 accuracy for +1/3 of that kernel's MMA work).
+template <bool WAIT_IN, bool FOUR = false>
 __device__ __forceinline__ void issue_mmas(const Ctx& c, int n_ksteps, long long n_tiles, uint32_t w_ring) {
     const uint4* s_steps = reinterpret_cast<const uint4*>(c.smem + kOffSteps);
     const uint32_t elected = elect_one();
@@ -385,15 +388,30 @@ __device__ __forceinline__ void issue_mmas(const Ctx& c, int n_ksteps, long long
                     const uint64_t b_lo = ((uint64_t)desc_hi << 32) | (b_lo32 + b_lopart + j * b_step);
                     if (flags & 8u) {
                         const uint32_t a_hi = c.tmem + cur.x + j * 8, a_lo = c.tmem + cur.y + j * 8;
-                        mma_ts(d_tmem, a_hi, b_hi, idesc, acc_on);
-                        mma_ts(d_tmem, a_lo, b_hi, idesc, 1);
-                        mma_ts(d_tmem, a_hi, b_lo, idesc, 1);
+                        // smallest terms first: the accumulator adds with truncation
+                        if (FOUR) {
+                            mma_ts(d_tmem, a_lo, b_lo, idesc, acc_on);
+                            mma_ts(d_tmem, a_lo, b_hi, idesc, 1);
+                            mma_ts(d_tmem, a_hi, b_lo, idesc, 1);
+                            mma_ts(d_tmem, a_hi, b_hi, idesc, 1);
+                        } else {
+                            mma_ts(d_tmem, a_hi, b_hi, idesc, acc_on);
+                            mma_ts(d_tmem, a_lo, b_hi, idesc, 1);
+                            mma_ts(d_tmem, a_hi, b_lo, idesc, 1);
+                        }
                     } else {
                         const uint64_t a_hi = ((uint64_t)desc_hi << 32) | (cur.x + j * (2 * kChunkBytes >> 4));
                         const uint64_t a_lo = ((uint64_t)desc_hi << 32) | (cur.y + j * (2 * kChunkBytes >> 4));
-                        mma_ss(d_tmem, a_hi, b_hi, idesc, acc_on);
-                        mma_ss(d_tmem, a_lo, b_hi, idesc, 1);
-                        mma_ss(d_tmem, a_hi, b_lo, idesc, 1);
+                        if (FOUR) {
+                            mma_ss(d_tmem, a_lo, b_lo, idesc, acc_on);
+                            mma_ss(d_tmem, a_lo, b_hi, idesc, 1);
+                            mma_ss(d_tmem, a_hi, b_lo, idesc, 1);
+                            mma_ss(d_tmem, a_hi, b_hi, idesc, 1);
+                        } else {
+                            mma_ss(d_tmem, a_hi, b_hi, idesc, acc_on);
+                            mma_ss(d_tmem, a_lo, b_hi, idesc, 1);
+                            mma_ss(d_tmem, a_hi, b_lo, idesc, 1);
+                        }
                     }
                     acc_on = 1;
                 }
@@ -445,7 +463,7 @@ sdf_mlp_fwd_kernel(const float* __restrict__ pos, const float* __restrict__ fe, 
     if (warp == kProducerWarp) {
         if (lane == 0) produce_weights(c, wstream, n_ksteps, n_tiles, kOffW);
     } else if (warp == kMmaWarp) {
-        issue_mmas<true>(c, n_ksteps, n_tiles, kOffW);
+        issue_mmas<true, !JVP>(c, n_ksteps, n_tiles, kOffW);
     } else {
         // ===== input staging + epilogue (threads 0..511) ===================================================
         const float* s_bias = reinterpret_cast<const float*>(smem + kOffBias);

@@ -1093,7 +1093,7 @@ int launch_agg_fwd(const gens_volume_scale_t& sc, int nv, const float* w2c, cons
     // Tuning knob: 10 forces the packed kernel, 20 / 25 the row-group kernel with / without culling at any
     // D % 64 == 0, 11 the previous round's shipped configuration (shared-memory cameras, STG zero fill), 12 / 13
     // only one of the two changes.
-    const bool rg = variant == 20 || variant == 25 || ((variant == 0 || (variant >= 11 && variant <= 13) || (variant >= 30 && variant <= 35)) && D >= 256) ||
+    const bool rg = variant == 20 || variant == 25 || ((variant == 0 || (variant >= 11 && variant <= 13) || (variant >= 30 && variant <= 39)) && D >= 256) ||
                     (to_peers && variant != 10);
     if (rg && D % 64 == 0 && min_vis_view >= 0 && (!to_peers || (sc.a_base == 0 && variant != 25))) {
         const int cam_set = sc.cam_slot - 1;  // public ids are 1-based, 0 = none
@@ -1109,7 +1109,7 @@ int launch_agg_fwd(const gens_volume_scale_t& sc, int nv, const float* w2c, cons
         if (recip) GENS_RG(true, CULL, CC, ZB, PE); \
         else GENS_RG(false, CULL, CC, ZB, PE);      \
     } while (0)
-        if (!to_peers && constcam && variant >= 30 && variant <= 35 && recip) {
+        if (!to_peers && constcam && variant >= 30 && variant <= 39 && recip) {
             // tuning: walk x planes with the window fixed (L1 re-use across planes), ROWS planes per block, MINB blocks/SM
 #define GENS_RG_X(ROWS_, MINB_, WALKX_, GATHER_)                                                                     \
     volume_agg_rowgroup_kernel<true, ROWS_, true, true, true, false, WALKX_, MINB_, GATHER_>                         \
@@ -1123,7 +1123,11 @@ int launch_agg_fwd(const gens_volume_scale_t& sc, int nv, const float* w2c, cons
                 case 32: GENS_RG_X(16, 2, true, 1); break;
                 case 33: GENS_RG_X(32, 2, true, 1); break;
                 case 34: GENS_RG_X(16, 2, true, 0); break;   // + both voxels' gathers in flight
-                default: GENS_RG_X(8, 3, false, 0); break;   // 35: shipped walk, 3 blocks/SM, both gathers in flight
+                case 35: GENS_RG_X(8, 3, false, 0); break;   // shipped walk, 3 blocks/SM, both gathers in flight
+                case 36: GENS_RG_X(8, 5, false, 1); break;   // shipped walk squeezed to 5 blocks/SM (<= 48 registers)
+                case 37: GENS_RG_X(8, 6, false, 1); break;   // ... 6 blocks/SM (<= 40 registers)
+                case 38: GENS_RG_X(16, 5, true, 1); break;   // walk x, 5 blocks/SM
+                default: GENS_RG_X(8, 2, false, 0); break;   // 39: 2 blocks/SM, both gathers in flight
             }
 #undef GENS_RG_X
             return gens_launch_status();

