@@ -121,8 +121,14 @@ _SIGNATURES = {
     "gens_patch_warp": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp], _i),
     "gens_lncc_fwd": ([_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp], _i),
     "gens_lncc_bwd": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp], _i),
+    "gens_mc_classify": ([_vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp], _i),
+    "gens_mc_vertices": ([_vp, _i, _i, _i, _f, _vp, _vp, _vp, _ll, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                          _vp, _vp], _i),
+    "gens_mc_triangles": ([_vp, _i, _i, _i, _f, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _i, ctypes.c_char_p, _ll,
+                           _vp, _vp], _i),
     "gens_tv_reduce": ([_PP, _PP, _i, _i, _vp, _vp], _i),
     "gens_debug_set_variant": ([_i], _i),
+    "gens_debug_set_tc_terms": ([_i], _i),
     "gens_tf32_mma_peak": ([_i, _vp, _vp], _i),
     "gens_selftest_division": ([_i, ctypes.c_ulonglong, _vp, _vp], _i),
 }

@@ -448,7 +448,7 @@ __device__ __forceinline__ void stage_chunk(uint8_t* smem, int off_hi, int off_l
 // JVP = true: row 2i / 2i+1 = primal / tangent of point i; pos (2n,27) and fe (2n,100) hold the primal rows
 // [0,n) and the tangent rows [n,2n) (gens_sdf_encode); additionally stores, per hidden layer l and point p,
 // s1[l][p][c] = sp'(a) and t2[l][p][c] = sp''(a) da for the reverse sweep.
-template <bool JVP>
+template <bool JVP, bool FOUR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 sdf_mlp_fwd_kernel(const float* __restrict__ pos, const float* __restrict__ fe, long long n,
                    const float* __restrict__ wstream, const KStep* __restrict__ ksteps, int n_ksteps,
@@ -463,7 +463,7 @@ sdf_mlp_fwd_kernel(const float* __restrict__ pos, const float* __restrict__ fe, 
     if (warp == kProducerWarp) {
         if (lane == 0) produce_weights(c, wstream, n_ksteps, n_tiles, kOffW);
     } else if (warp == kMmaWarp) {
-        issue_mmas<true, !JVP>(c, n_ksteps, n_tiles, kOffW);
+        issue_mmas<true, FOUR>(c, n_ksteps, n_tiles, kOffW);
     } else {
         // ===== input staging + epilogue (threads 0..511) ===================================================
         const float* s_bias = reinterpret_cast<const float*>(smem + kOffBias);
@@ -723,6 +723,15 @@ int set_smem(K kernel) {
 }
 }  // namespace
 
+namespace {
+int g_tc_value_terms = 3;
+}
+extern "C" int gens_debug_set_tc_terms(int terms) {
+    if (terms != 3 && terms != 4) return GENS_E_BADARG;
+    g_tc_value_terms = terms;
+    return 0;
+}
+
 // Value pass of the SDF MLP on the tensor cores.  pos (n,27) / fe (n,100): the encodings produced by
 // gens_sdf_encode; wstream / ksteps / bias: the packed network (gens_b200/mlp_tc.py documents the format);
 // sdf_out (n).  n_sm = number of CTAs to launch (<= SM count; one persistent CTA per SM).
@@ -733,9 +742,16 @@ extern "C" int gens_sdf_mlp_value_tc(const float* pos, const float* fe, long lon
     if (n_ksteps <= 0 || n_ksteps > kMaxKSteps || n_layers <= 0 || n_layers > kMaxLayers || scale == 0.f)
         return GENS_E_UNSUPPORTED;
     if (n == 0) return 0;
-    if (int rc = set_smem(sdf_mlp_fwd_kernel<false>)) return rc;
     const long long tiles = (n + kTileM - 1) / kTileM;
     const int grid = (int)(tiles < n_sm ? tiles : n_sm);
+    if (g_tc_value_terms == 4) {  // measurement knob (gens_debug_set_tc_terms): fourth compensation term Al.Bl
+        if (int rc = set_smem(sdf_mlp_fwd_kernel<false, true>)) return rc;
+        sdf_mlp_fwd_kernel<false, true><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
+            pos, fe, n, wstream, reinterpret_cast<const KStep*>(ksteps), n_ksteps, bias, n_layers, scale, sdf_out,
+            nullptr, nullptr);
+        return gens_launch_status();
+    }
+    if (int rc = set_smem(sdf_mlp_fwd_kernel<false>)) return rc;
     sdf_mlp_fwd_kernel<false><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
         pos, fe, n, wstream, reinterpret_cast<const KStep*>(ksteps), n_ksteps, bias, n_layers, scale, sdf_out, nullptr,
         nullptr);

@@ -76,6 +76,7 @@ class ImplicitSurface(nn.Module):
         self.fused_blend = True      # K10 colour-blending network as one kernel (no-grad render_core tail)
         self.fused_composite = True  # K7 warp-per-ray compositing kernel for the no-grad render_core tail
         self.fused_upsample = True   # K5 warp-per-ray kernels for up_sample / cat_z_vals (CUDA tensors)
+        self.mesher = "device"       # K12 marching cubes on the device; "mcubes" = the reference's CPU package
 
     def _fold_sdf(self):
         """Weight-normalised SDF layers folded (and packed for the tensor-core kernels) once per parameter version:
@@ -397,10 +398,16 @@ class ImplicitSurface(nn.Module):
         return u
 
     def extract_geometry(self, volumes, bound_min, bound_max, resolution, threshold):
-        """Marching cubes on the SDF lattice (reference :407-427); needs the `mcubes` package."""
-        import mcubes
-        u = self.sdf_grid(volumes, bound_min, bound_max, resolution).cpu().numpy()
-        vertices, triangles = mcubes.marching_cubes(u, threshold)
+        """Marching cubes on the SDF lattice (reference :407-427).  The lattice never leaves the device: K12
+        (gens_b200.meshing) extracts the mesh there instead of `mcubes.marching_cubes` on a 537 MB host array; with
+        `self.mesher = "mcubes"` the reference's CPU call is used (needs the PyMCubes package)."""
+        u = self.sdf_grid(volumes, bound_min, bound_max, resolution)
+        if getattr(self, "mesher", "device") == "mcubes":
+            import mcubes
+            vertices, triangles = mcubes.marching_cubes(u.cpu().numpy(), threshold)
+        else:
+            from .meshing import marching_cubes
+            vertices, triangles = marching_cubes(u, threshold)
         b_max, b_min = bound_max.detach().cpu().numpy(), bound_min.detach().cpu().numpy()
         vertices = vertices / (resolution - 1.0) * (b_max - b_min)[None, :] + b_min[None, :]
         return vertices, triangles

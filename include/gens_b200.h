@@ -364,6 +364,29 @@ int gens_lncc_fwd(const float *ref, const float *src, int n_rays, int n_src, int
 int gens_lncc_bwd(const float *ref, const float *src, const float *g_score, const int *picked, int n_rays,
                   int n_src, int n_samples, int channels, float *g_ref, float *g_src, void *stream);
 
+/* ---- K12: marching cubes on the device-resident lattice ------------------------------------------
+ * Replaces `mcubes.marching_cubes(u, threshold)` at the end of extract_geometry (reference models/modules/
+ * implicit_surface.py:423; PyMCubes 0.1.4).  u (rx,ry,rz) fp32, x = slowest axis.  Corner / edge numbering and the
+ * derivation of the case table: gens_b200/mc_tables.py (tri_count (256) uint8, tri_edges (256,max_tris,3) int8).
+ *   classify : vmask[p] bit a = the surface crosses the edge from point p along +axis a (x,y,z); ntri[p] = number of
+ *              triangles of the cell whose minimum corner is p (0 on the far faces); both (rx*ry*rz) uint8
+ *   vertices : pts (n_pts) ascending linear ids with vmask != 0, vbase (n_pts) exclusive scan of popcount(vmask);
+ *              verts (n_verts,3) float64 = lattice index + off + t along the edge, t = (iso - f0) / (f1 - f0)
+ *   triangles: cells (n_cells) ascending ids with ntri != 0, tbase exclusive scan of ntri; edge_owner = HOST array
+ *              (12,4) int8 (di,dj,dk,axis) of the point that owns each cube edge; tris (n_tris,3) int64 vertex ids
+ *              (+ vert_offset) */
+int gens_mc_classify(const float *u, int rx, int ry, int rz, float iso, const uint8_t *tri_count, uint8_t *vmask,
+                     uint8_t *ntri, void *stream);
+int gens_mc_vertices(const float *u, int rx, int ry, int rz, float iso, const long long *pts, const long long *vbase,
+                     const uint8_t *vmask, long long n_pts, double off_x, double off_y, double off_z, double *verts,
+                     void *stream);
+int gens_mc_triangles(const float *u, int rx, int ry, int rz, float iso, const long long *cells, const long long *tbase,
+                      long long n_cells, const long long *pts, const long long *vbase, long long n_pts,
+                      const uint8_t *vmask, const uint8_t *tri_count, const int8_t *tri_edges, int max_tris,
+                      const int8_t *edge_owner, long long vert_offset, long long *tris, void *stream);
+
+/* Measurement knob: 3 (shipped) or 4 product terms (adds Alo.Blo) in the tensor-core SDF VALUE kernel. */
+int gens_debug_set_tc_terms(int terms);
 /* Measurement probe (bench.py): `iters` resident-operand tcgen05.mma.kind::tf32 128x256x8 instructions per CTA, one
  * CTA per SM; out[0] = CTAs launched, out[1] = one accumulator element.  Dense TF32 peak = out[0] * iters *
  * 2*128*256*8 flop / the CUDA-event time of the call (MEASURED_PEAKS.json has no TF32 figure). */
