@@ -539,12 +539,11 @@ __device__ __forceinline__ const Cam& cam_of(const Cam* s_cam, int cam_set, int 
 //            the own tensor only.  Tiles of the other ranks' slabs: dead ones are zero-filled locally as well (every
 //            rank reaches the same cull decision from the same cameras, so nobody ships zeros over NVLink), live
 //            ones are left to their owner.
-//   WALKX    the block keeps its (8 rows x 64 voxels) window and walks ROWS consecutive x planes instead of ROWS
-//            row groups of one plane: consecutive planes project one or two pixels apart, so a window's texels are
-//            re-used from L1 by the next plane IF the SM's resident windows fit there (hence MINB, resident blocks/SM)
-template <bool RECIP, int ROWS, bool CULL, bool CONSTCAM, bool ZBULK, bool PEERS, bool WALKX = false, int MINB = 4,
-          int GATHER = 1>
-__global__ void __launch_bounds__(256, MINB)
+// Measured and not kept (profiles/r02_k1_variant_sweep.txt): walking x planes with a fixed window (L1 re-use across
+// planes does not materialise: 187-225 us against 177), 5 / 6 resident blocks per SM at <= 48 / 40 registers (spills:
+// 263 / 306 us), 2-3 blocks with both voxels' gathers in flight (212 us and worse).
+template <bool RECIP, int ROWS, bool CULL, bool CONSTCAM, bool ZBULK, bool PEERS>
+__global__ void __launch_bounds__(256, 4)
 volume_agg_rowgroup_kernel(const Pair* __restrict__ feat, int nv, int H, int W, const float* __restrict__ w2c,
                            const float* __restrict__ k_stage, float k_row_scale, const float* __restrict__ grid, int D,
                            int a0, int a1, long long out_off, long long channel_stride, int min_vis_view, Extent e,
@@ -567,22 +566,23 @@ volume_agg_rowgroup_kernel(const Pair* __restrict__ feat, int nv, int H, int W, 
     else load_cams(s_cam, w2c, k_stage, k_row_scale, nv);  // two barriers inside
 
     const int cz0 = blockIdx.x * 64, c0 = cz0 + threadIdx.x;
-    // tile rr of this block: plane a_first + (WALKX ? rr : 0), rows b_first + (WALKX ? 0 : 8 rr) ...
-    const int a_first = PEERS ? (int)blockIdx.z : a0 + (int)blockIdx.z * (WALKX ? ROWS : 1);  // tensor dim 2 (world x)
-    const int b_first = (int)blockIdx.y * 8 * (WALKX ? 1 : ROWS);
+    // tile rr of this block: plane a_first, rows b_first + 8 rr ...
+    const int a_first = PEERS ? (int)blockIdx.z : a0 + (int)blockIdx.z;  // plane of tensor dim 2 (world x)
+    const int b_first = (int)blockIdx.y * 8 * ROWS;
     const bool own = !PEERS || (a_first >= a0 && a_first < a1);
+    const float X = __ldg(grid + a_first);
     if (CULL) {
         const int total = ROWS * nv * 4;  // one item = one corner of one (tile, view); 4 consecutive lanes = one (tile, view)
         for (int base = 0; base < total; base += 256) {
             const int i = base + tid;
             const bool active = i < total;
             const int corner = i & 3, v = active ? (i >> 2) % nv : 0, rg = active ? (i >> 2) / nv : 0;
-            const int a = a_first + (WALKX ? rg : 0), b0 = b_first + (WALKX ? 0 : 8 * rg);
+            const int b0 = b_first + 8 * rg;
             unsigned bits = 0;
-            if (active && b0 < D && a < (PEERS ? D : a1)) {
+            if (active && b0 < D) {
                 const Cam& cam = cam_of<CONSTCAM>(s_cam, cam_set, v);
                 if (cam.affine)
-                    bits = cull_planes(cam, __ldg(grid + a), __ldg(grid + b0 + (corner & 1) * 7),
+                    bits = cull_planes(cam, X, __ldg(grid + b0 + (corner & 1) * 7),
                                        __ldg(grid + cz0 + (corner >> 1) * 63), e);
             }
             bits &= __shfl_xor_sync(0xffffffffu, bits, 1);
@@ -601,18 +601,12 @@ volume_agg_rowgroup_kernel(const Pair* __restrict__ feat, int nv, int H, int W, 
                     ((long long)(PEERS ? a_first : a_first - a0) * D + (b_first + threadIdx.y)) * D + c0;
     float* const own_vol = PEERS ? peers.vol[peers.self] : volume;
     float* const own_msk = PEERS ? peers.msk[peers.self] : mask_volume;
-    const long long tile_step = WALKX ? (long long)D * D : 8LL * D;
+    const long long tile_step = 8LL * D;
     bool bulk_pending = false;
-    float X = __ldg(grid + a_first);
 #pragma unroll 1
     for (int rr = 0; rr < ROWS; ++rr, off += tile_step) {
-        const int b0 = b_first + (WALKX ? 0 : 8 * rr), b = b0 + threadIdx.y;
-        if (WALKX) {
-            if (a_first + rr >= a1) break;
-            X = __ldg(grid + a_first + rr);
-        } else if (b0 >= D) {
-            break;
-        }
+        const int b0 = b_first + 8 * rr, b = b0 + threadIdx.y;
+        if (b0 >= D) break;
         const unsigned live = s_live[rr];
         if (live == 0) {  // block-uniform: nothing of this tile is visible anywhere -> zeros (min_vis_view >= 0)
             if (ZBULK) {
@@ -650,8 +644,8 @@ volume_agg_rowgroup_kernel(const Pair* __restrict__ feat, int nv, int H, int W, 
             if (!((live >> v) & 1u)) continue;
             const Pair* map = feat + v * map_stride;
             const Cam& cam = cam_of<CONSTCAM>(s_cam, cam_set, v);
-            if (cam.affine) accumulate_view<1, RECIP, true, GATHER>(cam, map, pitch, X, Y, Z, e, acc);
-            else accumulate_view<1, RECIP, false, GATHER>(cam, map, pitch, X, Y, Z, e, acc);
+            if (cam.affine) accumulate_view<1, RECIP, true, 1>(cam, map, pitch, X, Y, Z, e, acc);
+            else accumulate_view<1, RECIP, false, 1>(cam, map, pitch, X, Y, Z, e, acc);
         }
         float res[2][9];
 #pragma unroll
@@ -1093,7 +1087,7 @@ int launch_agg_fwd(const gens_volume_scale_t& sc, int nv, const float* w2c, cons
     // Tuning knob: 10 forces the packed kernel, 20 / 25 the row-group kernel with / without culling at any
     // D % 64 == 0, 11 the previous round's shipped configuration (shared-memory cameras, STG zero fill), 12 / 13
     // only one of the two changes.
-    const bool rg = variant == 20 || variant == 25 || ((variant == 0 || (variant >= 11 && variant <= 13) || (variant >= 30 && variant <= 39)) && D >= 256) ||
+    const bool rg = variant == 20 || variant == 25 || ((variant == 0 || (variant >= 11 && variant <= 13)) && D >= 256) ||
                     (to_peers && variant != 10);
     if (rg && D % 64 == 0 && min_vis_view >= 0 && (!to_peers || (sc.a_base == 0 && variant != 25))) {
         const int cam_set = sc.cam_slot - 1;  // public ids are 1-based, 0 = none
@@ -1109,29 +1103,6 @@ int launch_agg_fwd(const gens_volume_scale_t& sc, int nv, const float* w2c, cons
         if (recip) GENS_RG(true, CULL, CC, ZB, PE); \
         else GENS_RG(false, CULL, CC, ZB, PE);      \
     } while (0)
-        if (!to_peers && constcam && variant >= 30 && variant <= 39 && recip) {
-            // tuning: walk x planes with the window fixed (L1 re-use across planes), ROWS planes per block, MINB blocks/SM
-#define GENS_RG_X(ROWS_, MINB_, WALKX_, GATHER_)                                                                     \
-    volume_agg_rowgroup_kernel<true, ROWS_, true, true, true, false, WALKX_, MINB_, GATHER_>                         \
-        <<<WALKX_ ? dim3(D / 64, D / 8, ceil_div_i(planes, ROWS_)) : dim3(D / 64, ceil_div_i(D, 8 * ROWS_), planes), \
-           block, 0, st>>>(                                                                                          \
-            feat, nv, sc.H, sc.W, w2c, intrs, sc.k_row_scale, sc.grid, D, sc.a0, sc.a1, out_off, sc.channel_stride,  \
-            min_vis_view, e, sc.volume, sc.mask_volume, cam_set, peers)
-            switch (variant) {
-                case 30: GENS_RG_X(16, 4, true, 1); break;
-                case 31: GENS_RG_X(16, 3, true, 1); break;
-                case 32: GENS_RG_X(16, 2, true, 1); break;
-                case 33: GENS_RG_X(32, 2, true, 1); break;
-                case 34: GENS_RG_X(16, 2, true, 0); break;   // + both voxels' gathers in flight
-                case 35: GENS_RG_X(8, 3, false, 0); break;   // shipped walk, 3 blocks/SM, both gathers in flight
-                case 36: GENS_RG_X(8, 5, false, 1); break;   // shipped walk squeezed to 5 blocks/SM (<= 48 registers)
-                case 37: GENS_RG_X(8, 6, false, 1); break;   // ... 6 blocks/SM (<= 40 registers)
-                case 38: GENS_RG_X(16, 5, true, 1); break;   // walk x, 5 blocks/SM
-                default: GENS_RG_X(8, 2, false, 0); break;   // 39: 2 blocks/SM, both gathers in flight
-            }
-#undef GENS_RG_X
-            return gens_launch_status();
-        }
         if (to_peers) {
             if (constcam) GENS_RG_R(true, true, true, true);
             else GENS_RG_R(true, false, true, true);
