@@ -34,3 +34,16 @@ def test_our_arm_refuses_to_run_without_a_gpu():
     r = subprocess.run([sys.executable, "bench.py", "--steps", "1", "--warmup", "0"], cwd=ROOT, capture_output=True,
                        text=True, timeout=300)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_committed_k1_traffic_capture_matches_the_kernel_sources():
+    """roofline.traffic comes from profiles/r02_k1_256_traffic.json (tools/summarize_ncu.py traffic <.ncu-rep>), which
+    records the hash of the kernel sources the capture was taken from: a capture that is stale against the tree fails
+    here (and bench.py would print traffic = null)."""
+    import json
+    sys.path.insert(0, ROOT)
+    import bench
+    assert os.path.exists(bench.K1_TRAFFIC_PROFILE), "no committed ncu traffic capture of K1"
+    rec = json.load(open(bench.K1_TRAFFIC_PROFILE))
+    assert rec["kernel_source_sha256_16"] == bench.k1_source_hash(), "K1 sources changed since the ncu capture: re-capture"
+    assert rec["dram_bytes_read"] > 0 and rec["dram_bytes_write"] > 0.5 * 256 ** 3 * 36
