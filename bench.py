@@ -916,9 +916,10 @@ def run_ours(args, rank, world, local):
                  "traffic": traffic, "traffic_source": traffic_src,
                  "kernel": "volume_agg_rowgroup_kernel @ 256^3", "ms": k1_ms,
                  "algorithmic_bytes": abytes, "peak_source": f"MEASURED_PEAKS.json ({peak_kind}, burst copy)",
-                 "limiter": "SM L1 data pipe (72 % busy avg / 79 % max under ncu: STG at 32 B/clk/SM + LDG.256 "
-                            "returns + camera LDS) on top of 108 us of arithmetic; the same store pattern alone "
-                            "runs at 6.5 TB/s (profiles/r01_k1_variant_sweep.txt, r01_ubench_planes.txt)"}
+                 "limiter": "gather latency at register-limited occupancy: long_scoreboard 6.0 of 12.8 cycles per issued "
+                            "instruction, 32 warps/SM at 62 registers, gathers miss L1 (12.5 % hits) and come from L2 (875 MB "
+                            "per launch); L1 data pipe 62 % busy, DRAM 40 %, issue slots 58 % (profiles/r02_k1_256_ncu_summary"
+                            ".txt, r02_k1_variant_sweep.txt)"}
     line = {
         "metric": "voxel*views/s (volume build)", "value": vv / (ms_step * 1e-3), "unit": "voxel*views/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,

@@ -570,6 +570,9 @@ sdf_mlp_fwd_kernel(const float* __restrict__ pos, const float* __restrict__ fe, 
 //     ga = sp' g_h ,  dga = sp''(a) da g_h + sp' dg_h            (epilogue, rows 2i / 2i+1 of a 64-point tile)
 //     [g_h ; dg_h]_{l-1} = [ga ; dga] Wx_l        -> accumulator 0 (overwritten per layer)
 //     [g_fe ; dg_fe]    += [ga ; dga] Wf_l        -> accumulator 1 (running sum over layers, l >= 1)
+// Per layer the x-part MMAs are issued and committed first (barrier 0), the feature-part MMAs second (barrier 1): the
+// epilogue of the next layer reads accumulator 0 and does its arithmetic while the feature part still runs, and only
+// waits for barrier 1 before it overwrites the A operand.
 // with g_h of the last hidden layer = w_out / scale (consts row 0) and the output layer's own feature part
 // (consts row 1) added to the primal rows of g_fe at the end.  The skip layer returns its position part in
 // columns [skip_col, skip_col + 27) of accumulator 0; together with layer 0's result it forms g_pos.
@@ -594,7 +597,7 @@ sdf_mlp_rev_kernel(const float* __restrict__ s1, const float* __restrict__ t2, l
         const int row = threadIdx.x & 127, cq = threadIdx.x >> 7;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const bool tangent = row & 1;
-        uint32_t acc_phase = 0;
+        uint32_t acc_phase = 0, afree_phase = 0;
         // s1 / t2 of the NEXT layer are fetched with cp.async into a thread-private shared-memory column while
         // the tensor core works on the current one (their DRAM latency used to sit on the layer-to-layer critical
         // path): slot q = blk * 8 + {0..3: s1 chunks, 4..7: t2 chunks}, [q][thread] float4 -> conflict-free.
@@ -667,6 +670,14 @@ sdf_mlp_rev_kernel(const float* __restrict__ s1, const float* __restrict__ t2, l
                         const float other = __shfl_xor_sync(0xffffffffu, mine, 1);  // the pair's other row
                         const float out = tangent ? fmaf(d2[j], other, d1[j] * mine) : d1[j] * mine;
                         split_tf32(out, hi[j], lo[j]);
+                    }
+                    if (!top && blk == 0) {
+                        // The layer above committed its x-part (barrier 0: accumulator 0 readable) BEFORE its
+                        // feature-part MMAs, which still read the A operand this thread is about to overwrite and ran
+                        // while the values above were loaded and computed; barrier 1 says they are done.
+                        mbar_wait(c.bar_acc(1), afree_phase);
+                        afree_phase ^= 1;
+                        tc_fence_after();
                     }
                     tmem_st16(c.tmem + lane_base + kColAhi + col0, hi);
                     tmem_st16(c.tmem + lane_base + kColAlo + col0, lo);

@@ -145,8 +145,11 @@ class PackedSDFReverse:
                         flags |= 1
                     if j == 0 and si == 0:
                         flags |= 4
-                    if si == len(segs) - 1 and j == nb - 1:
-                        flags |= 2
+                    if j == nb - 1:
+                        # x-part done -> barrier 0: the epilogue of the next layer may read accumulator 0 while the
+                        # feature-part MMAs below still run; feature part done -> barrier 1: the A operand in tensor
+                        # memory is no longer being read and may be overwritten
+                        flags |= 2 | (16 if si == 1 else 0)
                     steps.append([off, nbytes, A_H | (j << 8) | (acc << 16), flags])
                     off += nbytes
                 chunks.append(blk.reshape(-1))
@@ -219,7 +222,7 @@ def _replay(ksteps, stream, srcs, n_rows, on_commit):
             acc[col] = torch.zeros((n_rows, 128), dtype=torch.float64)
         acc[col][:, :n_pad] += srcs[kind][:, 16 * j: 16 * j + 16] @ w.t()
         if flags & 2:
-            on_commit(acc, col)
+            on_commit(acc, col, 1 if flags & 16 else 0)
 
 
 def _sp(y):
@@ -238,7 +241,7 @@ def emulate_grad(packed: PackedSDF, rev: PackedSDFReverse, pos: torch.Tensor, fe
     bias = packed.bias.double().cpu()
     state = {"layer": 0, "s1": [], "t2": [], "sdf": None}
 
-    def fwd_commit(acc, col):
+    def fwd_commit(acc, col, _barrier):
         l = state["layer"]
         y = acc[col]
         if l + 1 < packed.n_layers:
@@ -266,19 +269,23 @@ def emulate_grad(packed: PackedSDF, rev: PackedSDFReverse, pos: torch.Tensor, fe
     g_top[:n] = consts[0]
     rsrcs = {A_H: load_a(rev.n_hidden - 1, g_top)}
 
-    def rev_commit(acc, col):
-        l = rstate["layer"]          # the layer whose MMAs just finished
-        g = acc[ACC0]
-        if l == rev.skip_layer and l > 0:
-            rstate["g_pos"] += g[:, rev.skip_col: rev.skip_col + 27]
-        if l > 0:
-            rsrcs[A_H] = load_a(l - 1, g)
-        else:
-            rstate["g_pos"] += g[:, :27]
-            gfe = acc[ACC1][:, :100].clone()
-            gfe[:n] += consts[1, :100]
-            rstate["g_fe"] = gfe
-        rstate["layer"] = l - 1
+    def rev_commit(acc, col, barrier):
+        l = rstate["layer"]          # the layer whose MMAs are being committed
+        if barrier == 0:             # x-part done: the next A operand can be COMPUTED from accumulator 0 ...
+            g = acc[ACC0]
+            if l == rev.skip_layer and l > 0:
+                rstate["g_pos"] += g[:, rev.skip_col: rev.skip_col + 27]
+            if l > 0:
+                rstate["pending_a"] = load_a(l - 1, g)
+            else:                    # layer 0 has no feature part: the tile is finished
+                rstate["g_pos"] += g[:, :27]
+                gfe = acc[ACC1][:, :100].clone()
+                gfe[:n] += consts[1, :100]
+                rstate["g_fe"] = gfe
+                rstate["layer"] = l - 1
+        else:                        # ... but only WRITTEN once the feature-part MMAs have read the current one
+            rsrcs[A_H] = rstate.pop("pending_a")
+            rstate["layer"] = l - 1
 
     _replay(rev.ksteps.cpu().tolist(), rev.wstream.double().cpu(), rsrcs, rows, rev_commit)
     return state["sdf"], rstate["g_pos"].float(), rstate["g_fe"].float()
@@ -295,7 +302,7 @@ def emulate(packed: PackedSDF, pos: torch.Tensor, fe: torch.Tensor) -> torch.Ten
     bias = packed.bias.double().cpu()
     state = {"layer": 0, "sdf": None}
 
-    def commit(acc, col):
+    def commit(acc, col, _barrier):
         l = state["layer"]
         y = acc[col] + bias[l]
         if l + 1 < packed.n_layers:
