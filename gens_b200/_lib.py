@@ -12,7 +12,7 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libgens_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 DIV_TRUE, DIV_RECIP = 0, 1
 
 _lib = None
@@ -107,8 +107,8 @@ _SIGNATURES = {
     "gens_sdf_act_bwd": ([_vp, _i, _f, _vp, _vp, _ll, _i, _vp, _i, _vp], _i),
     "gens_sdf_decode": ([_vp, _vp, _vp, _vp, _vp, _ll, _f, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "gens_sdf_mlp_value_tc": ([_vp, _vp, _ll, _vp, _vp, _i, _vp, _i, _f, _i, _vp, _vp], _i),
-    "gens_sdf_mlp_jvp_tc": ([_vp, _vp, _ll, _vp, _vp, _i, _vp, _i, _f, _i, _vp, _vp, _vp, _vp], _i),
-    "gens_sdf_mlp_rev_tc": ([_vp, _vp, _ll, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp], _i),
+    "gens_sdf_mlp_jvp_tc": ([_vp, _vp, _ll, _vp, _vp, _i, _vp, _i, _f, _i, _vp, _vp, _vp], _i),
+    "gens_sdf_mlp_rev_tc": ([_vp, _ll, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp], _i),
     "gens_pack_nhwc4": ([_vp, _vp, _i, _i, _i, _i, _vp], _i),
     "gens_unpack_nhwc4": ([_vp, _vp, _i, _i, _i, _i, _vp], _i),
     "gens_lookup_feature_fwd": ([_vp, _ll, _i, _vp, _vp, _vp, _vp, _IP, _vp, _i, _vp, _vp, _vp, _vp], _i),
@@ -129,6 +129,7 @@ _SIGNATURES = {
     "gens_tv_reduce": ([_PP, _PP, _i, _i, _vp, _vp], _i),
     "gens_debug_set_variant": ([_i], _i),
     "gens_debug_set_tc_terms": ([_i], _i),
+    "gens_debug_tc_profile": ([_vp], _i),
     "gens_tf32_mma_peak": ([_i, _vp, _vp], _i),
     "gens_selftest_division": ([_i, ctypes.c_ulonglong, _vp, _vp], _i),
 }

@@ -56,16 +56,27 @@ constexpr int kOffW = kOffPlo + kPChunks * kChunkBytes;
 constexpr int kOffBias = kOffW + kWStages * kWSlotBytes;
 constexpr int kOffSteps = kOffBias + kMaxLayers * 128 * 4;  // per k-step issue records (uint4)
 constexpr int kOffBar = kOffSteps + kMaxKSteps * 16;
-constexpr int kNumBars = 2 * kWStages + 4;  // full[], empty[], acc[2], a_ready, in_ready
+constexpr int kNumBars = 2 * kWStages + 6;  // full[], empty[], acc[2], a_ready, in_ready, tape[2]
 constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
 // the reverse kernel keeps no encodings in shared memory: the ring starts at 0
 constexpr int kRevOffW = 0;
-// ... and stages the next layer's s1 / t2 there instead: 16 float4 per epilogue thread
+// ... and stages the s1 / t2 tapes there instead: two buffers x two tapes x 32 KB (64 points x 128 channels)
 constexpr int kRevOffStage = kWStages * kWSlotBytes;
-static_assert(kRevOffStage + 16 * kEpiThreads * 16 <= kOffBias, "reverse-kernel staging overlaps the bias block");
+// ... and, behind them, the skip layer's position cotangents of the tile in flight ([128 rows][27] floats)
+constexpr int kRevOffSkip = kRevOffStage + 4 * 32 * 64 * 16;
+static_assert(kRevOffSkip + kTileM * kNP * 4 <= kOffBias, "reverse-kernel staging overlaps the bias block");
+static_assert(kNF % 4 == 0, "g_fe rows are written with 16-byte stores");
 
 constexpr uint32_t kColAhi = 0, kColAlo = 128, kColAcc0 = 256, kColAcc1 = 384;
+
+// The tape between the JVP forward and the reverse kernel: per 64-point tile and hidden layer one contiguous 64 KB
+// block [which: sp'(a) | sp''(a) da][chunk of 4 channels: 32][slot: 64] float4, point pt of the tile in slot
+// (pt + chunk) & 63.  That is exactly the shared-memory image the reverse kernel's epilogue reads without bank conflicts
+// (16 consecutive points of one chunk are 256 contiguous bytes), so the reverse kernel fetches a layer's tapes with ONE
+// cp.async.bulk; the forward's stores are coalesced the same way.
+constexpr uint32_t kTapeBytes = 32u * 64u * 16u;  // one tape of one layer of one tile
+__device__ __forceinline__ uint32_t tape_slot(int pt, int chunk) { return (uint32_t)chunk * 1024u + (uint32_t)((pt + chunk) & 63) * 16u; }
 
 struct KStep {
     uint32_t w_off;    // byte offset of this k-step's [hi | lo] weight block in the stream (blocks are contiguous)
@@ -259,6 +270,7 @@ struct Ctx {
     __device__ __forceinline__ uint32_t bar_acc(int i) const { return bar0 + 8u * (2 * kWStages + i); }
     __device__ __forceinline__ uint32_t bar_a() const { return bar0 + 8u * (2 * kWStages + 2); }
     __device__ __forceinline__ uint32_t bar_in() const { return bar0 + 8u * (2 * kWStages + 3); }
+    __device__ __forceinline__ uint32_t bar_tape(int i) const { return bar0 + 8u * (2 * kWStages + 4 + i); }
 };
 
 // One-time setup shared by the kernels: bias / constant rows and the k-step issue records to shared memory,
@@ -298,6 +310,8 @@ __device__ __forceinline__ Ctx setup(uint8_t* smem, const KStep* __restrict__ ks
         mbar_init(c.bar_acc(1), 1);
         mbar_init(c.bar_a(), kEpiThreads);
         mbar_init(c.bar_in(), kEpiThreads);
+        mbar_init(c.bar_tape(0), 1);
+        mbar_init(c.bar_tape(1), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if ((threadIdx.x >> 5) == kProducerWarp) {
@@ -351,7 +365,9 @@ __device__ __forceinline__ void produce_weights(const Ctx& c, const float* __res
 // the inverse CDF at inv_s up to 512 amplifies an SDF error of 1e-5 into sample depths moved by 1e-4; the fourth term
 // brings the products to fp32 accuracy for +1/3 of that kernel's MMA work).
 template <bool WAIT_IN, bool FOUR = false>
-__device__ __forceinline__ void issue_mmas(const Ctx& c, int n_ksteps, long long n_tiles, uint32_t w_ring) {
+__device__ __forceinline__ void issue_mmas(const Ctx& c, int n_ksteps, long long n_tiles, uint32_t w_ring,
+                                           long long* prof = nullptr) {
+    long long t_wa = 0, t_wf = 0, t_is = 0, n_ks = 0;
     const uint4* s_steps = reinterpret_cast<const uint4*>(c.smem + kOffSteps);
     const uint32_t elected = elect_one();
     const uint32_t desc_hi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1 (bits 32-47)
@@ -371,12 +387,15 @@ __device__ __forceinline__ void issue_mmas(const Ctx& c, int n_ksteps, long long
             const uint32_t idesc = instr_desc(nn);
             const uint32_t d_tmem = c.tmem + (cur.w >> 16);
             if (flags & 1u) acc_on = 0;
+            const long long q0 = prof ? clock64() : 0;
             if (flags & 4u) {  // the epilogue's A operand must be in tensor memory
                 mbar_wait(c.bar_a(), a_phase);
                 a_phase ^= 1;
             }
+            const long long q1 = prof ? clock64() : 0;
             mbar_wait(c.bar_full(slot), phase);
             tc_fence_after();
+            const long long q2 = prof ? clock64() : 0;
             // B: [hi: 4 chunks][lo: 4 chunks], chunk = N rows x 16 B
             const uint32_t w_addr = c.s_base + w_ring + slot * kWSlotBytes;
             const uint32_t b_lo32 = ((w_addr & 0x3ffff) >> 4) | (nn << 16);  // LBO = 16 N bytes
@@ -420,11 +439,20 @@ __device__ __forceinline__ void issue_mmas(const Ctx& c, int n_ksteps, long long
             }
             acc_on = 1;
             __syncwarp();
+            if (prof) {
+                t_wa += q1 - q0;
+                t_wf += q2 - q1;
+                t_is += clock64() - q2;
+                ++n_ks;
+            }
             if (++slot == kWStages) {
                 slot = 0;
                 phase ^= 1;
             }
         }
+    }
+    if (prof && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+        prof[8] = t_wa; prof[9] = t_wf; prof[10] = t_is; prof[11] = n_ks;
     }
 }
 
@@ -447,13 +475,13 @@ __device__ __forceinline__ void stage_chunk(uint8_t* smem, int off_hi, int off_l
 // Forward kernels.  JVP = false: rows are points, pos (n,27), fe (n,100) -> sdf (n).
 // JVP = true: row 2i / 2i+1 = primal / tangent of point i; pos (2n,27) and fe (2n,100) hold the primal rows
 // [0,n) and the tangent rows [n,2n) (gens_sdf_encode); additionally stores, per hidden layer l and point p,
-// s1[l][p][c] = sp'(a) and t2[l][p][c] = sp''(a) da for the reverse sweep.
+// sp'(a) and sp''(a) da of every channel into the tape (layout at tape_slot) for the reverse sweep.
 template <bool JVP, bool FOUR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 sdf_mlp_fwd_kernel(const float* __restrict__ pos, const float* __restrict__ fe, long long n,
                    const float* __restrict__ wstream, const KStep* __restrict__ ksteps, int n_ksteps,
                    const float* __restrict__ bias, int n_layers, float scale, float* __restrict__ sdf_out,
-                   float* __restrict__ s1_out, float* __restrict__ t2_out) {
+                   float* __restrict__ tape_out) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const Ctx c = setup(smem, ksteps, n_ksteps, bias, n_layers);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -537,12 +565,15 @@ sdf_mlp_fwd_kernel(const float* __restrict__ pos, const float* __restrict__ fe, 
                                 split_tf32(tangent ? o_t[k] : got, hi[8 + k], lo[8 + k]);
                             }
                             if (live) {
-                                float4* o1 = reinterpret_cast<float4*>(s1_out + ((long long)layer * n + p) * 128 + cb);
-                                float4* o2 = reinterpret_cast<float4*>(t2_out + ((long long)layer * n + p) * 128 + cb);
+                                uint8_t* blk_base = reinterpret_cast<uint8_t*>(tape_out) +
+                                                    ((size_t)tile * (n_layers - 1) + layer) * (2u * kTapeBytes);
 #pragma unroll
                                 for (int q = 0; q < 2; ++q) {
-                                    __stcs(o1 + q, make_float4(s1v[4 * q], s1v[4 * q + 1], s1v[4 * q + 2], s1v[4 * q + 3]));
-                                    __stcs(o2 + q, make_float4(t2v[4 * q], t2v[4 * q + 1], t2v[4 * q + 2], t2v[4 * q + 3]));
+                                    const uint32_t at = tape_slot(row >> 1, cb / 4 + q);
+                                    __stcs(reinterpret_cast<float4*>(blk_base + at),
+                                           make_float4(s1v[4 * q], s1v[4 * q + 1], s1v[4 * q + 2], s1v[4 * q + 3]));
+                                    __stcs(reinterpret_cast<float4*>(blk_base + kTapeBytes + at),
+                                           make_float4(t2v[4 * q], t2v[4 * q + 1], t2v[4 * q + 2], t2v[4 * q + 3]));
                                 }
                             }
                         }
@@ -578,11 +609,12 @@ sdf_mlp_fwd_kernel(const float* __restrict__ pos, const float* __restrict__ fe, 
 // columns [skip_col, skip_col + 27) of accumulator 0; together with layer 0's result it forms g_pos.
 // Outputs (sdf_analytic's layout, primal rows [0,n), tangent rows [n,2n)): g_pos (2n,27), g_fe (2n,100).
 __global__ void __launch_bounds__(kThreads, 1)
-sdf_mlp_rev_kernel(const float* __restrict__ s1, const float* __restrict__ t2, long long n,
+sdf_mlp_rev_kernel(const float* __restrict__ tape, long long n,
                    const float* __restrict__ wstream, const KStep* __restrict__ ksteps, int n_ksteps,
                    const float* __restrict__ consts, int n_hidden, int skip_layer, int skip_col,
-                   float* __restrict__ g_pos, float* __restrict__ g_fe) {
+                   float* __restrict__ g_pos, float* __restrict__ g_fe, long long* __restrict__ prof) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    const long long k_start = prof ? clock64() : 0;
     const Ctx c = setup(smem, ksteps, n_ksteps, consts, 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int kPts = kTileM / 2;
@@ -591,33 +623,34 @@ sdf_mlp_rev_kernel(const float* __restrict__ s1, const float* __restrict__ t2, l
     if (warp == kProducerWarp) {
         if (lane == 0) produce_weights(c, wstream, n_ksteps, n_tiles, kRevOffW);
     } else if (warp == kMmaWarp) {
-        issue_mmas<false>(c, n_ksteps, n_tiles, kRevOffW);
+        issue_mmas<false>(c, n_ksteps, n_tiles, kRevOffW, prof);
     } else {
         const float* s_const = reinterpret_cast<const float*>(smem + kOffBias);
         const int row = threadIdx.x & 127, cq = threadIdx.x >> 7;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const bool tangent = row & 1;
         uint32_t acc_phase = 0, afree_phase = 0;
-        // s1 / t2 of the NEXT layer are fetched with cp.async into a thread-private shared-memory column while
-        // the tensor core works on the current one (their DRAM latency used to sit on the layer-to-layer critical
-        // path): slot q = blk * 8 + {0..3: s1 chunks, 4..7: t2 chunks}, [q][thread] float4 -> conflict-free.
-        const uint32_t stage = c.s_base + kRevOffStage + threadIdx.x * 16u;
-        auto prefetch = [&](long long pp, int layer) {
-            if (pp < n) {
-#pragma unroll
-                for (int blk = 0; blk < 2; ++blk) {
-                    const float* g1 = s1 + ((long long)layer * n + pp) * 128 + cq * 32 + blk * 16;
-                    const float* g2 = t2 + ((long long)layer * n + pp) * 128 + cq * 32 + blk * 16;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        cp_async16(stage + (uint32_t)(blk * 8 + q) * (kEpiThreads * 16u), g1 + 4 * q);
-                        if (tangent) cp_async16(stage + (uint32_t)(blk * 8 + 4 + q) * (kEpiThreads * 16u), g2 + 4 * q);
-                    }
-                }
+        float* s_skip = reinterpret_cast<float*>(smem + kRevOffSkip);
+        const bool timing = prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;  // measurement knob, see below
+        long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        // The tapes (sp', sp'' da) of the NEXT layer are fetched while the tensor core works on the current one: ONE
+        // cp.async.bulk of the layer's 64 KB block, issued by epilogue thread 0, completion on an mbarrier.  (Measured
+        // with gens_debug_tc_profile: per-thread cp.async of the own 16-byte pieces took 39 % of a layer's epilogue
+        // time just to issue, cooperative coalesced cp.async still 29 %.)  Two staging buffers alternate.  A buffer is
+        // overwritten two layers after it was read: by then every epilogue thread has arrived on bar_a of the layer in
+        // between, which thread 0 observes through that layer's MMA commit before it gets here.
+        const uint32_t stage0 = c.s_base + kRevOffStage;
+        uint32_t pf_buf = 0, use_buf = 0, tape_phase[2] = {0, 0};
+        auto prefetch = [&](long long tile_, int layer) {
+            if (threadIdx.x == 0) {
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(tape) +
+                                     ((size_t)tile_ * n_hidden + layer) * (2u * kTapeBytes);
+                mbar_arrive_expect_tx(c.bar_tape(pf_buf), 2u * kTapeBytes);
+                bulk_g2s(stage0 + pf_buf * (2u * kTapeBytes), src, 2u * kTapeBytes, c.bar_tape(pf_buf));
             }
-            cp_async_commit();
+            pf_buf ^= 1u;
         };
-        if ((long long)blockIdx.x < n_tiles) prefetch((long long)blockIdx.x * kPts + (row >> 1), n_hidden - 1);
+        if ((long long)blockIdx.x < n_tiles) prefetch((long long)blockIdx.x, n_hidden - 1);
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const long long p = tile * kPts + (row >> 1);
             const bool live = p < n;
@@ -627,11 +660,13 @@ sdf_mlp_rev_kernel(const float* __restrict__ s1, const float* __restrict__ t2, l
             for (int j = 0; j < 16; ++j) pos_part[j] = 0.0f;
             for (int layer = n_hidden - 1; layer >= 0; --layer) {
                 const bool top = layer == n_hidden - 1;
+                const long long e0 = timing ? clock64() : 0;
                 if (!top) {
                     mbar_wait(c.bar_acc(0), acc_phase);
                     acc_phase ^= 1;
                     tc_fence_after();
                 }
+                long long e1 = timing ? clock64() : 0, e2 = e1, e3 = e1, e4 = e1;
 #pragma unroll 1
                 for (int blk = 0; blk < 2; ++blk) {
                     const int col0 = cq * 32 + blk * 16;
@@ -644,24 +679,33 @@ sdf_mlp_rev_kernel(const float* __restrict__ s1, const float* __restrict__ t2, l
                     }
                     float d1[16], d2[16];
                     {
-                        if (blk == 0) cp_async_wait_all();  // this layer's s1 / t2 (issued one layer ago)
+                        if (blk == 0) {
+                            mbar_wait(c.bar_tape(use_buf), tape_phase[use_buf]);  // this layer's tapes (issued one layer ago)
+                            tape_phase[use_buf] ^= 1u;
+                            if (timing) e2 = clock64();
+                        }
+                        const uint32_t src = stage0 + use_buf * (2u * kTapeBytes);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float4 a = live ? lds128(stage + (uint32_t)(blk * 8 + q) * (kEpiThreads * 16u))
-                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const uint32_t at = tape_slot(row >> 1, cq * 8 + blk * 4 + q);
+                            const float4 a = live ? lds128(src + at) : make_float4(0.f, 0.f, 0.f, 0.f);
                             d1[4 * q] = a.x; d1[4 * q + 1] = a.y; d1[4 * q + 2] = a.z; d1[4 * q + 3] = a.w;
                             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (live && tangent) b = lds128(stage + (uint32_t)(blk * 8 + 4 + q) * (kEpiThreads * 16u));
+                            if (live && tangent) b = lds128(src + kTapeBytes + at);
                             d2[4 * q] = b.x; d2[4 * q + 1] = b.y; d2[4 * q + 2] = b.z; d2[4 * q + 3] = b.w;
                         }
                     }
                     if (!top) tmem_wait_ld();
-                    // the skip layer's x-part covers [h | pos]: keep the pos columns, they are not activations
+                    // the skip layer's x-part covers [h | pos]: keep the pos columns, they are not activations.  They
+                    // are owned by other threads than the ones that finish g_pos at the end of the tile, so they are
+                    // handed over through shared memory ([row][27] floats; a round trip through g_pos in global memory
+                    // put ~16 dependent loads per thread into the tile's tail: a third of the tile time).  Ordering:
+                    // this thread's bar_a arrival below, the MMA commits in between, the readers' bar_acc wait.
                     if (layer == skip_layer - 1 && col0 + 16 > skip_col) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const int cc = col0 + j - skip_col;
-                            if (cc >= 0 && cc < kNP && live) g_pos[out_row * kNP + cc] = __uint_as_float(v[j]);
+                            if (cc >= 0 && cc < kNP) s_skip[row * kNP + cc] = __uint_as_float(v[j]);
                         }
                     }
 #pragma unroll
@@ -671,6 +715,7 @@ sdf_mlp_rev_kernel(const float* __restrict__ s1, const float* __restrict__ t2, l
                         const float out = tangent ? fmaf(d2[j], other, d1[j] * mine) : d1[j] * mine;
                         split_tf32(out, hi[j], lo[j]);
                     }
+                    if (timing && blk == 0) e3 = clock64();
                     if (!top && blk == 0) {
                         // The layer above committed its x-part (barrier 0: accumulator 0 readable) BEFORE its
                         // feature-part MMAs, which still read the A operand this thread is about to overwrite and ran
@@ -679,6 +724,7 @@ sdf_mlp_rev_kernel(const float* __restrict__ s1, const float* __restrict__ t2, l
                         afree_phase ^= 1;
                         tc_fence_after();
                     }
+                    if (timing && blk == 0) e4 = clock64();
                     tmem_st16(c.tmem + lane_base + kColAhi + col0, hi);
                     tmem_st16(c.tmem + lane_base + kColAlo + col0, lo);
                 }
@@ -686,11 +732,23 @@ sdf_mlp_rev_kernel(const float* __restrict__ s1, const float* __restrict__ t2, l
                 tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(c.bar_a());
-                // the staged values are in registers / consumed: fetch the next layer's (or the next tile's top layer)
-                if (layer > 0) prefetch(p, layer - 1);
-                else if (tile + gridDim.x < n_tiles) prefetch((tile + gridDim.x) * kPts + (row >> 1), n_hidden - 1);
+                const long long e5 = timing ? clock64() : 0;
+                use_buf ^= 1u;
+                // fetch the next layer's tapes (or the next tile's top layer) into the other staging buffer
+                if (layer > 0) prefetch(tile, layer - 1);
+                else if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x, n_hidden - 1);
+                if (timing) {
+                    pt[0] += e1 - e0;            // wait for the x-part MMAs of the layer above
+                    pt[1] += e2 - e1;            // wait for this layer's s1 / t2 (cp.async)
+                    pt[2] += e3 - e2;            // accumulator load + arithmetic of the first 16 columns
+                    pt[3] += e4 - e3;            // wait for the feature-part MMAs (A operand free)
+                    pt[4] += e5 - e4;            // stores, second 16 columns, store fence, arrive
+                    pt[5] += clock64() - e5;     // prefetch issue
+                    pt[7] += 1;
+                }
             }
             // -- results: accumulator 0 = layer 0's position cotangents, accumulator 1 = feature cotangents
+            const long long tail0 = timing ? clock64() : 0;
             mbar_wait(c.bar_acc(0), acc_phase);
             acc_phase ^= 1;
             tc_fence_after();
@@ -703,22 +761,32 @@ sdf_mlp_rev_kernel(const float* __restrict__ s1, const float* __restrict__ t2, l
                     tmem_wait_ld();
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (col0 + j < kNP && live) {
-                            float* o = g_pos + out_row * kNP + col0 + j;
-                            *o = __uint_as_float(v[j]) + (skip_layer > 0 ? *o : 0.0f);
-                        }
+                        if (col0 + j < kNP && live)
+                            g_pos[out_row * kNP + col0 + j] =
+                                __uint_as_float(v[j]) + (skip_layer > 0 ? s_skip[row * kNP + col0 + j] : 0.0f);
                 }
                 if (col0 < kNF) {
                     tmem_ld16(c.tmem + lane_base + kColAcc1 + col0, v);
                     tmem_wait_ld();
+                    // rows are 400 bytes apart and col0 is a multiple of 16 floats: 16-byte stores (kNF % 4 == 0)
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (col0 + j < kNF && live)
-                            g_fe[out_row * kNF + col0 + j] =
-                                __uint_as_float(v[j]) + (tangent ? 0.0f : s_const[128 + col0 + j]);
+                    for (int j = 0; j < 16; j += 4)
+                        if (col0 + j < kNF && live) {
+                            float4 o;
+                            o.x = __uint_as_float(v[j]) + (tangent ? 0.0f : s_const[128 + col0 + j]);
+                            o.y = __uint_as_float(v[j + 1]) + (tangent ? 0.0f : s_const[128 + col0 + j + 1]);
+                            o.z = __uint_as_float(v[j + 2]) + (tangent ? 0.0f : s_const[128 + col0 + j + 2]);
+                            o.w = __uint_as_float(v[j + 3]) + (tangent ? 0.0f : s_const[128 + col0 + j + 3]);
+                            *reinterpret_cast<float4*>(g_fe + out_row * kNF + col0 + j) = o;
+                        }
                 }
             }
             tc_fence_before();  // accumulator reads done before the next tile's MMAs may overwrite them
+            if (timing) pt[6] += clock64() - tail0;
+        }
+        if (timing) {
+            for (int i = 0; i < 8; ++i) prof[i] = pt[i];
+            prof[12] = clock64() - k_start;
         }
     }
     teardown(c);
@@ -736,6 +804,15 @@ int set_smem(K kernel) {
 
 namespace {
 int g_tc_value_terms = 3;
+long long* g_tc_prof = nullptr;
+}
+// Measurement knob: a device buffer of 16 int64 that the next reverse-sweep launches fill with cycle counts of block 0
+// (epilogue thread 0: [0] wait x-part MMAs, [1] wait s1/t2, [2] load + arithmetic, [3] wait feature-part MMAs,
+// [4] stores + second half + arrive, [5] prefetch issue, [6] tile tails (last MMA wait + result stores), [7] layers; MMA issuer: [8] wait A operand, [9] wait weights,
+// [10] issue, [11] k-steps; [12] kernel cycles).  nullptr switches it off.
+extern "C" int gens_debug_tc_profile(long long* buf) {
+    g_tc_prof = buf;
+    return 0;
 }
 extern "C" int gens_debug_set_tc_terms(int terms) {
     if (terms != 3 && terms != 4) return GENS_E_BADARG;
@@ -759,22 +836,22 @@ extern "C" int gens_sdf_mlp_value_tc(const float* pos, const float* fe, long lon
         if (int rc = set_smem(sdf_mlp_fwd_kernel<false, true>)) return rc;
         sdf_mlp_fwd_kernel<false, true><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
             pos, fe, n, wstream, reinterpret_cast<const KStep*>(ksteps), n_ksteps, bias, n_layers, scale, sdf_out,
-            nullptr, nullptr);
+            nullptr);
         return gens_launch_status();
     }
     if (int rc = set_smem(sdf_mlp_fwd_kernel<false>)) return rc;
     sdf_mlp_fwd_kernel<false><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
-        pos, fe, n, wstream, reinterpret_cast<const KStep*>(ksteps), n_ksteps, bias, n_layers, scale, sdf_out, nullptr,
-        nullptr);
+        pos, fe, n, wstream, reinterpret_cast<const KStep*>(ksteps), n_ksteps, bias, n_layers, scale, sdf_out, nullptr);
     return gens_launch_status();
 }
 
 // Value + tangent pass: pos (2n,27) / fe (2n,100) with the tangent rows (directional derivative of the
-// encodings along u) in [n,2n); sdf_out (n); s1_out / t2_out (n_layers-1, n, 128) = sp'(a), sp''(a) da.
+// encodings along u) in [n,2n); sdf_out (n); tape_out: ceil(n/64) x (n_layers-1) blocks of 64 KB holding sp'(a) and
+// sp''(a) da of every hidden channel in the layout the reverse kernel stages verbatim (tape_slot above).
 extern "C" int gens_sdf_mlp_jvp_tc(const float* pos, const float* fe, long long n, const float* wstream,
                                    const void* ksteps, int n_ksteps, const float* bias, int n_layers, float scale,
-                                   int n_sm, float* sdf_out, float* s1_out, float* t2_out, void* stream) {
-    GENS_CHECK_ARG(pos && fe && wstream && ksteps && bias && sdf_out && s1_out && t2_out && n >= 0 && n_sm > 0);
+                                   int n_sm, float* sdf_out, float* tape_out, void* stream) {
+    GENS_CHECK_ARG(pos && fe && wstream && ksteps && bias && sdf_out && tape_out && n >= 0 && n_sm > 0);
     if (n_ksteps <= 0 || n_ksteps > kMaxKSteps || n_layers <= 0 || n_layers > kMaxLayers || scale == 0.f)
         return GENS_E_UNSUPPORTED;
     if (n == 0) return 0;
@@ -782,19 +859,18 @@ extern "C" int gens_sdf_mlp_jvp_tc(const float* pos, const float* fe, long long 
     const long long tiles = (n + kTileM / 2 - 1) / (kTileM / 2);
     const int grid = (int)(tiles < n_sm ? tiles : n_sm);
     sdf_mlp_fwd_kernel<true><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
-        pos, fe, n, wstream, reinterpret_cast<const KStep*>(ksteps), n_ksteps, bias, n_layers, scale, sdf_out, s1_out,
-        t2_out);
+        pos, fe, n, wstream, reinterpret_cast<const KStep*>(ksteps), n_ksteps, bias, n_layers, scale, sdf_out, tape_out);
     return gens_launch_status();
 }
 
-// Reverse sweep: s1 / t2 from gens_sdf_mlp_jvp_tc; wstream / ksteps = the transposed network
+// Reverse sweep: tape from gens_sdf_mlp_jvp_tc; wstream / ksteps = the transposed network
 // (mlp_tc.PackedSDFReverse); consts (2,128): row 0 = output-layer weights of the last hidden activations /
 // scale, row 1 = output-layer weights of the feature encoding / scale.  skip_layer / skip_col: the layer whose
 // input concatenates the position encoding and the column where it starts.  g_pos (2n,27), g_fe (2n,100).
-extern "C" int gens_sdf_mlp_rev_tc(const float* s1, const float* t2, long long n, const float* wstream,
+extern "C" int gens_sdf_mlp_rev_tc(const float* tape, long long n, const float* wstream,
                                    const void* ksteps, int n_ksteps, const float* consts, int n_hidden, int skip_layer,
                                    int skip_col, int n_sm, float* g_pos, float* g_fe, void* stream) {
-    GENS_CHECK_ARG(s1 && t2 && wstream && ksteps && consts && g_pos && g_fe && n >= 0 && n_sm > 0);
+    GENS_CHECK_ARG(tape && wstream && ksteps && consts && g_pos && g_fe && n >= 0 && n_sm > 0);
     if (n_ksteps <= 0 || n_ksteps > kMaxKSteps || n_hidden <= 0 || n_hidden >= kMaxLayers || skip_col < 0 ||
         skip_col + kNP > 128)
         return GENS_E_UNSUPPORTED;
@@ -803,7 +879,7 @@ extern "C" int gens_sdf_mlp_rev_tc(const float* s1, const float* t2, long long n
     const long long tiles = (n + kTileM / 2 - 1) / (kTileM / 2);
     const int grid = (int)(tiles < n_sm ? tiles : n_sm);
     sdf_mlp_rev_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
-        s1, t2, n, wstream, reinterpret_cast<const KStep*>(ksteps), n_ksteps, consts, n_hidden, skip_layer, skip_col,
-        g_pos, g_fe);
+        tape, n, wstream, reinterpret_cast<const KStep*>(ksteps), n_ksteps, consts, n_hidden, skip_layer, skip_col,
+        g_pos, g_fe, g_tc_prof);
     return gens_launch_status();
 }

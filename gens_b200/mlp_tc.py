@@ -178,31 +178,39 @@ def sdf_values(packed: PackedSDF, pos: torch.Tensor, fe: torch.Tensor) -> torch.
     return out
 
 
+TAPE_TILE_POINTS = 64        # points per tile of the JVP forward / reverse kernels
+TAPE_BLOCK_FLOATS = 2 * 32 * 64 * 4   # one (tile, layer) block: [sp' | sp'' da][chunk 32][slot 64] float4 = 64 KB
+
+
 def sdf_jvp(packed: PackedSDF, pos: torch.Tensor, fe: torch.Tensor, n: int):
-    """pos (2n,27) / fe (2n,100) with tangent rows in [n,2n) -> (sdf (n,1), s1, t2 (n_layers-1, n, 128))."""
+    """pos (2n,27) / fe (2n,100) with tangent rows in [n,2n) -> (sdf (n,1), tape).  The tape holds sp'(a) and
+    sp''(a) da of every hidden channel for the reverse sweep, as ceil(n/64) x (n_layers-1) blocks of 64 KB laid out
+    exactly as the reverse kernel stages them in shared memory (csrc/sdf_mlp_tc.cu: tape_slot)."""
     _lib.require_cuda(pos, fe)
     dev = pos.device
     sdf = torch.empty((n, 1), device=dev, dtype=torch.float32)
-    s1 = torch.empty((packed.n_layers - 1, n, 128), device=dev, dtype=torch.float32)
-    t2 = torch.empty((packed.n_layers - 1, n, 128), device=dev, dtype=torch.float32)
+    tiles = (n + TAPE_TILE_POINTS - 1) // TAPE_TILE_POINTS
+    tape = torch.empty((tiles, packed.n_layers - 1, TAPE_BLOCK_FLOATS), device=dev, dtype=torch.float32)
     if n == 0:
-        return sdf, s1, t2
+        return sdf, tape
     _lib.check(_lib.lib().gens_sdf_mlp_jvp_tc(
         _lib.ptr(pos), _lib.ptr(fe), n, _lib.ptr(packed.wstream), _lib.ptr(packed.ksteps), packed.n_ksteps,
-        _lib.ptr(packed.bias), packed.n_layers, packed.scale, packed.n_sm, _lib.ptr(sdf), _lib.ptr(s1), _lib.ptr(t2),
+        _lib.ptr(packed.bias), packed.n_layers, packed.scale, packed.n_sm, _lib.ptr(sdf), _lib.ptr(tape),
         _lib.stream_ptr(dev)), "gens_sdf_mlp_jvp_tc")
-    return sdf, s1, t2
+    return sdf, tape
 
 
-def sdf_reverse(rev: PackedSDFReverse, s1: torch.Tensor, t2: torch.Tensor, n: int):
+def sdf_reverse(rev: PackedSDFReverse, tape: torch.Tensor, n: int):
     """Reverse sweep -> (g_pos (2n,27), g_fe (2n,100)), primal rows first."""
-    dev = s1.device
+    dev = tape.device
     g_pos = torch.empty((2 * n, 27), device=dev, dtype=torch.float32)
     g_fe = torch.empty((2 * n, 100), device=dev, dtype=torch.float32)
     if n == 0:
         return g_pos, g_fe
+    if tape.shape[1] != rev.n_hidden:
+        raise RuntimeError("tape / reverse network mismatch")
     _lib.check(_lib.lib().gens_sdf_mlp_rev_tc(
-        _lib.ptr(s1), _lib.ptr(t2), n, _lib.ptr(rev.wstream), _lib.ptr(rev.ksteps), rev.n_ksteps, _lib.ptr(rev.consts),
+        _lib.ptr(tape), n, _lib.ptr(rev.wstream), _lib.ptr(rev.ksteps), rev.n_ksteps, _lib.ptr(rev.consts),
         rev.n_hidden, rev.skip_layer, rev.skip_col, rev.n_sm, _lib.ptr(g_pos), _lib.ptr(g_fe), _lib.stream_ptr(dev)),
         "gens_sdf_mlp_rev_tc")
     return g_pos, g_fe

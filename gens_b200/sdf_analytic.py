@@ -126,9 +126,9 @@ def value_grad_smooth(net, pts: torch.Tensor, volumes, folded: Optional[FoldedSD
     if USE_TC and fw.tc_supported():
         # whole MLP on the tensor cores: one persistent kernel forward (value + tangent), one in reverse
         from . import mlp_tc
-        sdf, s1, t2 = mlp_tc.sdf_jvp(fw.packed(), pos, fe, n)
-        g_pos, g_fe = mlp_tc.sdf_reverse(fw.packed_rev(), s1, t2, n)
-        del s1, t2
+        sdf, tape = mlp_tc.sdf_jvp(fw.packed(), pos, fe, n)
+        g_pos, g_fe = mlp_tc.sdf_reverse(fw.packed_rev(), tape, n)
+        del tape
         grad, smooth = new(n, 3), new(n, 3)
         g_f, dg_f = new(n, nf), new(n, nf)
         _c(L.gens_sdf_decode(P(pts), P(feats), P(dfeats), P(g_pos), P(g_fe), n, fw.scale, _U, fw.multires,

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GENS_ABI_VERSION 2
+#define GENS_ABI_VERSION 3
 
 #define GENS_E_BADARG (-1)      /* null pointer / non-positive size            */
 #define GENS_E_UNSUPPORTED (-2) /* shape outside what the kernels are built for */
@@ -274,17 +274,18 @@ int gens_sdf_mlp_value_tc(const float *pos, const float *fe, long long n, const 
                           int n_sm, float *sdf_out, void *stream);
 /* Value + tangent pass of the same network (forward half of SDFNetwork.gradient, sdf_network.py:131-153):
  * pos (2n,27) / fe (2n,100) carry the directional derivative of the encodings along u in rows [n,2n);
- * sdf_out (n); s1_out / t2_out (n_layers-1, n, 128) = softplus'(a) and softplus''(a)*da per hidden layer,
- * kept for the reverse sweep. */
+ * sdf_out (n); tape_out = softplus'(a) and softplus''(a)*da of every hidden channel, kept for the reverse sweep as
+ * ceil(n/64) x (n_layers-1) blocks of 64 KB: [sp' | sp'' da][chunk of 4 channels: 32][slot: 64] float4 with point pt
+ * of the tile in slot (pt + chunk) & 63 -- the shared-memory image the reverse kernel stages with one bulk copy. */
 int gens_sdf_mlp_jvp_tc(const float *pos, const float *fe, long long n, const float *wstream,
                         const void *ksteps, int n_ksteps, const float *bias, int n_layers, float scale,
-                        int n_sm, float *sdf_out, float *s1_out, float *t2_out, void *stream);
+                        int n_sm, float *sdf_out, float *tape_out, void *stream);
 /* Reverse sweep through value and tangent (the two nested autograd.grad calls of sdf_network.py:139-152):
- * s1 / t2 from gens_sdf_mlp_jvp_tc; wstream / ksteps = the transposed network (mlp_tc.PackedSDFReverse);
+ * tape from gens_sdf_mlp_jvp_tc; wstream / ksteps = the transposed network (mlp_tc.PackedSDFReverse);
  * consts (2,128): output-layer weights of the last hidden activations and of the feature encoding, / scale;
  * skip_layer / skip_col: the layer whose input concatenates the position encoding and its first column.
  * Writes the cotangents of the encodings g_pos (2n,27), g_fe (2n,100) for gens_sdf_decode. */
-int gens_sdf_mlp_rev_tc(const float *s1, const float *t2, long long n, const float *wstream,
+int gens_sdf_mlp_rev_tc(const float *tape, long long n, const float *wstream,
                         const void *ksteps, int n_ksteps, const float *consts, int n_hidden, int skip_layer,
                         int skip_col, int n_sm, float *g_pos, float *g_fe, void *stream);
 
@@ -385,6 +386,9 @@ int gens_mc_triangles(const float *u, int rx, int ry, int rz, float iso, const l
                       const uint8_t *vmask, const uint8_t *tri_count, const int8_t *tri_edges, int max_tris,
                       const int8_t *edge_owner, long long vert_offset, long long *tris, void *stream);
 
+/* Measurement knob: device buffer of 16 int64 filled by the next gens_sdf_mlp_rev_tc launches with per-phase cycle
+ * counts of block 0 (layout at the definition, csrc/sdf_mlp_tc.cu); NULL switches it off. */
+int gens_debug_tc_profile(long long *buf);
 /* Measurement knob: 3 (shipped) or 4 product terms (adds Alo.Blo) in the tensor-core SDF VALUE kernel. */
 int gens_debug_set_tc_terms(int terms);
 /* Measurement probe (bench.py): `iters` resident-operand tcgen05.mma.kind::tf32 128x256x8 instructions per CTA, one
