@@ -66,7 +66,7 @@ constexpr int kRevOffStage = kWStages * kWSlotBytes;
 // ... and, behind them, the skip layer's position cotangents of the tile in flight ([128 rows][27] floats)
 constexpr int kRevOffSkip = kRevOffStage + 4 * 32 * 64 * 16;
 static_assert(kRevOffSkip + kTileM * kNP * 4 <= kOffBias, "reverse-kernel staging overlaps the bias block");
-static_assert(kNF % 4 == 0, "g_fe rows are written with 16-byte stores");
+static_assert(kNF % 4 == 0, "feature-encoding rows are read / written with 16-byte accesses");
 
 constexpr uint32_t kColAhi = 0, kColAlo = 128, kColAcc0 = 256, kColAcc1 = 384;
 
@@ -456,21 +456,6 @@ __device__ __forceinline__ void issue_mmas(const Ctx& c, int n_ksteps, long long
     }
 }
 
-// 16 floats of one row of an encoding -> hi / lo chunks in the canonical layout
-__device__ __forceinline__ void stage_chunk(uint8_t* smem, int off_hi, int off_lo, int chunk, int row,
-                                            const float* __restrict__ src, int width, bool live) {
-    float v[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) v[e] = (live && 4 * chunk + e < width) ? __ldg(src + 4 * chunk + e) : 0.0f;
-    uint4 hi, lo;
-    split_tf32(v[0], hi.x, lo.x);
-    split_tf32(v[1], hi.y, lo.y);
-    split_tf32(v[2], hi.z, lo.z);
-    split_tf32(v[3], hi.w, lo.w);
-    *reinterpret_cast<uint4*>(smem + off_hi + chunk * kChunkBytes + row * 16) = hi;
-    *reinterpret_cast<uint4*>(smem + off_lo + chunk * kChunkBytes + row * 16) = lo;
-}
-
 // ------------------------------------------------------------------------------------------------------
 // Forward kernels.  JVP = false: rows are points, pos (n,27), fe (n,100) -> sdf (n).
 // JVP = true: row 2i / 2i+1 = primal / tangent of point i; pos (2n,27) and fe (2n,100) hold the primal rows
@@ -481,8 +466,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 sdf_mlp_fwd_kernel(const float* __restrict__ pos, const float* __restrict__ fe, long long n,
                    const float* __restrict__ wstream, const KStep* __restrict__ ksteps, int n_ksteps,
                    const float* __restrict__ bias, int n_layers, float scale, float* __restrict__ sdf_out,
-                   float* __restrict__ tape_out) {
+                   float* __restrict__ tape_out, long long* __restrict__ prof) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    const long long k_start = prof ? clock64() : 0;
     const Ctx c = setup(smem, ksteps, n_ksteps, bias, n_layers);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int kPts = JVP ? kTileM / 2 : kTileM;  // points per tile
@@ -491,7 +477,7 @@ sdf_mlp_fwd_kernel(const float* __restrict__ pos, const float* __restrict__ fe, 
     if (warp == kProducerWarp) {
         if (lane == 0) produce_weights(c, wstream, n_ksteps, n_tiles, kOffW);
     } else if (warp == kMmaWarp) {
-        issue_mmas<true, FOUR>(c, n_ksteps, n_tiles, kOffW);
+        issue_mmas<true, FOUR>(c, n_ksteps, n_tiles, kOffW, prof);
     } else {
         // ===== input staging + epilogue (threads 0..511) ===================================================
         const float* s_bias = reinterpret_cast<const float*>(smem + kOffBias);
@@ -499,25 +485,123 @@ sdf_mlp_fwd_kernel(const float* __restrict__ pos, const float* __restrict__ fe, 
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const bool tangent = JVP && (row & 1);
         uint32_t acc_phase[2] = {0, 0};
+        // measurement knob (gens_debug_tc_profile): cycles of block 0 / thread 0 per phase --
+        // [0] staging the encodings, [1] waiting for a layer's MMAs, [2] epilogue arithmetic + tape stores + A stores,
+        // [3] tiles, [7] layer epilogues
+        const bool timing = prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+        long long pt[4] = {0, 0, 0, 0}, n_epi = 0, pt_fence = 0;
+        // columns 27..31 of the position encoding are K padding: zero once, the staging below never touches them
+        for (int i2 = threadIdx.x; i2 < kTileM * (kPChunks * 4 - kNP); i2 += kEpiThreads) {
+            const int srow = i2 / (kPChunks * 4 - kNP), col = kNP + i2 % (kPChunks * 4 - kNP);
+            const int at = (col >> 2) * kChunkBytes + srow * 16 + (col & 3) * 4;
+            *reinterpret_cast<uint32_t*>(smem + kOffPhi + at) = 0u;
+            *reinterpret_cast<uint32_t*>(smem + kOffPlo + at) = 0u;
+        }
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const long long f0 = timing ? clock64() : 0;
             // -- encodings of this tile -> shared memory, split hi/lo (the previous tile's MMAs are done: this
             //    thread has already waited for its last accumulator)
             const long long p = JVP ? tile * kPts + (row >> 1) : tile * kPts + row;
             const bool live = p < n;
             const long long in_row = tangent ? n + p : p;
-            for (int ch = cq * (kFChunks / 4); ch < (cq + 1) * (kFChunks / 4); ++ch)
-                stage_chunk(smem, kOffFhi, kOffFlo, ch, row, fe + in_row * kNF, kNF, live);
-            for (int ch = cq * (kPChunks / 4); ch < (cq + 1) * (kPChunks / 4); ++ch)
-                stage_chunk(smem, kOffPhi, kOffPlo, ch, row, pos + in_row * kNP, kNP, live);
+            // Cooperative, sector-exact staging.  The tile's encodings are contiguous row-major blocks in global memory
+            // (JVP: a primal and a tangent block); who loads a value is independent of who owns the row later.  Measured
+            // (gens_debug_tc_profile): with every thread loading its own row's chunks, a warp request touched 32 rows
+            // 400 bytes apart -- half a sector used per 16-byte load, an eighth per scalar -- 7.7 k sector requests and
+            // 9-14 k cycles per tile with the tensor core idle.  Now a warp request covers 8 rows x 64 contiguous bytes
+            // of the feature encoding (16 full sectors; the 16-byte stores of one 8-row group are one conflict-free
+            // wavefront per chunk), and the position encoding is read as one contiguous float stream.
+            {
+                const int r8 = lane & 7, c4 = lane >> 3;
+                float4 fv[7];
+#pragma unroll
+                for (int it = 0; it < 7; ++it) {
+                    const int u = warp + 16 * it, rg = u / 7, cg = u - 7 * rg;
+                    const int srow = rg * 8 + r8, chunk = cg * 4 + c4;
+                    const long long pt_ = JVP ? tile * kPts + (srow >> 1) : tile * kPts + srow;
+                    const long long grow = (JVP && (srow & 1)) ? n + pt_ : pt_;
+                    fv[it] = (pt_ < n && 4 * chunk + 3 < kNF) ? __ldg(reinterpret_cast<const float4*>(fe + grow * kNF) + chunk)
+                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                constexpr int kPosFloats = kTileM * kNP;  // 3456 per tile
+                float pvv[7];
+#pragma unroll
+                for (int it = 0; it < 7; ++it) {
+                    const int idx = (int)threadIdx.x + 512 * it;
+                    float v = 0.0f;
+                    if (idx < kPosFloats) {
+                        if (JVP) {
+                            const int b = idx / (kPosFloats / 2), jj = idx - b * (kPosFloats / 2);
+                            const long long pt_ = tile * kPts + jj / kNP;
+                            if (pt_ < n) v = __ldg(pos + ((b ? n : 0) + tile * kPts) * kNP + jj);
+                        } else {
+                            if (tile * kPts + idx / kNP < n) v = __ldg(pos + tile * kPts * kNP + idx);
+                        }
+                    }
+                    pvv[it] = v;
+                }
+#pragma unroll
+                for (int it = 0; it < 7; ++it) {
+                    const int u = warp + 16 * it, rg = u / 7, cg = u - 7 * rg;
+                    const int srow = rg * 8 + r8, chunk = cg * 4 + c4;
+                    uint4 hi, lo;
+                    split_tf32(fv[it].x, hi.x, lo.x);
+                    split_tf32(fv[it].y, hi.y, lo.y);
+                    split_tf32(fv[it].z, hi.z, lo.z);
+                    split_tf32(fv[it].w, hi.w, lo.w);
+                    *reinterpret_cast<uint4*>(smem + kOffFhi + chunk * kChunkBytes + srow * 16) = hi;
+                    *reinterpret_cast<uint4*>(smem + kOffFlo + chunk * kChunkBytes + srow * 16) = lo;
+                }
+#pragma unroll
+                for (int it = 0; it < 7; ++it) {
+                    const int idx = (int)threadIdx.x + 512 * it;
+                    if (idx < kPosFloats) {
+                        int srow, col;
+                        if (JVP) {
+                            const int b = idx / (kPosFloats / 2), jj = idx - b * (kPosFloats / 2);
+                            srow = 2 * (jj / kNP) + b;
+                            col = jj % kNP;
+                        } else {
+                            srow = idx / kNP;
+                            col = idx % kNP;
+                        }
+                        uint32_t hi, lo;
+                        split_tf32(pvv[it], hi, lo);
+                        const int at = (col >> 2) * kChunkBytes + srow * 16 + (col & 3) * 4;
+                        *reinterpret_cast<uint32_t*>(smem + kOffPhi + at) = hi;
+                        *reinterpret_cast<uint32_t*>(smem + kOffPlo + at) = lo;
+                    }
+                }
+            }
+            const long long f0b = timing ? clock64() : 0;
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
             tc_fence_before();    // orders this thread's earlier tcgen05.ld of the accumulators
             mbar_arrive(c.bar_in());
+            if (timing) {
+                pt[0] += clock64() - f0;
+                pt_fence += clock64() - f0b;
+                pt[3] += 1;
+            }
 
             for (int layer = 0; layer < n_layers; ++layer) {
                 const int st = layer & 1;
+                if (layer == 1 && tile + gridDim.x < n_tiles) {
+                    // pull the NEXT tile's encodings towards L2 now: its staging prologue is a burst of loads from all
+                    // SMs at once during which the tensor core idles (11 k cycles per tile from HBM, measured)
+                    const long long np = JVP ? (tile + gridDim.x) * kPts + (row >> 1) : (tile + gridDim.x) * kPts + row;
+                    if (np < n) {
+                        const long long nr = tangent ? n + np : np;
+                        const float* f = fe + nr * kNF + 4 * cq * (kFChunks / 4);
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(f));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(f + 27));
+                        if (cq == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pos + nr * kNP));
+                    }
+                }
+                const long long f1 = timing ? clock64() : 0;
                 mbar_wait(c.bar_acc(st), acc_phase[st]);
                 acc_phase[st] ^= 1;
                 tc_fence_after();
+                const long long f2 = timing ? clock64() : 0;
                 const uint32_t acc = c.tmem + lane_base + (st ? kColAcc1 : kColAcc0);
                 if (layer + 1 < n_layers) {
                     const float* b = s_bias + layer * 128;
@@ -590,7 +674,16 @@ sdf_mlp_fwd_kernel(const float* __restrict__ pos, const float* __restrict__ fe, 
                         if (live && !tangent) sdf_out[p] = __fdiv_rn(__uint_as_float(v) + s_bias[layer * 128], scale);
                     }
                 }
+                if (timing) {
+                    pt[1] += f2 - f1;
+                    pt[2] += clock64() - f2;
+                    ++n_epi;
+                }
             }
+        }
+        if (timing) {
+            prof[0] = pt[0]; prof[1] = pt[1]; prof[2] = pt[2]; prof[3] = pt[3]; prof[4] = pt_fence; prof[7] = n_epi;
+            prof[12] = clock64() - k_start;
         }
     }
     teardown(c);
@@ -805,13 +898,16 @@ int set_smem(K kernel) {
 namespace {
 int g_tc_value_terms = 3;
 long long* g_tc_prof = nullptr;
+int g_tc_prof_target = 2;  // 0 value kernel, 1 JVP forward, 2 reverse
 }
-// Measurement knob: a device buffer of 16 int64 that the next reverse-sweep launches fill with cycle counts of block 0
+// Measurement knob: a device buffer of 16 int64 that the next launches of one kernel (target 0 value, 1 JVP forward,
+// 2 reverse; the forward kernels' layout is documented at their timers) fill with cycle counts of block 0 -- reverse:
 // (epilogue thread 0: [0] wait x-part MMAs, [1] wait s1/t2, [2] load + arithmetic, [3] wait feature-part MMAs,
 // [4] stores + second half + arrive, [5] prefetch issue, [6] tile tails (last MMA wait + result stores), [7] layers; MMA issuer: [8] wait A operand, [9] wait weights,
 // [10] issue, [11] k-steps; [12] kernel cycles).  nullptr switches it off.
-extern "C" int gens_debug_tc_profile(long long* buf) {
+extern "C" int gens_debug_tc_profile(long long* buf, int target) {
     g_tc_prof = buf;
+    g_tc_prof_target = target;
     return 0;
 }
 extern "C" int gens_debug_set_tc_terms(int terms) {
@@ -836,12 +932,13 @@ extern "C" int gens_sdf_mlp_value_tc(const float* pos, const float* fe, long lon
         if (int rc = set_smem(sdf_mlp_fwd_kernel<false, true>)) return rc;
         sdf_mlp_fwd_kernel<false, true><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
             pos, fe, n, wstream, reinterpret_cast<const KStep*>(ksteps), n_ksteps, bias, n_layers, scale, sdf_out,
-            nullptr);
+            nullptr, nullptr);
         return gens_launch_status();
     }
     if (int rc = set_smem(sdf_mlp_fwd_kernel<false>)) return rc;
     sdf_mlp_fwd_kernel<false><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
-        pos, fe, n, wstream, reinterpret_cast<const KStep*>(ksteps), n_ksteps, bias, n_layers, scale, sdf_out, nullptr);
+        pos, fe, n, wstream, reinterpret_cast<const KStep*>(ksteps), n_ksteps, bias, n_layers, scale, sdf_out, nullptr,
+        g_tc_prof_target == 0 ? g_tc_prof : nullptr);
     return gens_launch_status();
 }
 
@@ -859,7 +956,8 @@ extern "C" int gens_sdf_mlp_jvp_tc(const float* pos, const float* fe, long long 
     const long long tiles = (n + kTileM / 2 - 1) / (kTileM / 2);
     const int grid = (int)(tiles < n_sm ? tiles : n_sm);
     sdf_mlp_fwd_kernel<true><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
-        pos, fe, n, wstream, reinterpret_cast<const KStep*>(ksteps), n_ksteps, bias, n_layers, scale, sdf_out, tape_out);
+        pos, fe, n, wstream, reinterpret_cast<const KStep*>(ksteps), n_ksteps, bias, n_layers, scale, sdf_out, tape_out,
+        g_tc_prof_target == 1 ? g_tc_prof : nullptr);
     return gens_launch_status();
 }
 
@@ -880,6 +978,6 @@ extern "C" int gens_sdf_mlp_rev_tc(const float* tape, long long n, const float* 
     const int grid = (int)(tiles < n_sm ? tiles : n_sm);
     sdf_mlp_rev_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
         tape, n, wstream, reinterpret_cast<const KStep*>(ksteps), n_ksteps, consts, n_hidden, skip_layer, skip_col,
-        g_pos, g_fe, g_tc_prof);
+        g_pos, g_fe, g_tc_prof_target == 2 ? g_tc_prof : nullptr);
     return gens_launch_status();
 }

@@ -386,9 +386,9 @@ int gens_mc_triangles(const float *u, int rx, int ry, int rz, float iso, const l
                       const uint8_t *vmask, const uint8_t *tri_count, const int8_t *tri_edges, int max_tris,
                       const int8_t *edge_owner, long long vert_offset, long long *tris, void *stream);
 
-/* Measurement knob: device buffer of 16 int64 filled by the next gens_sdf_mlp_rev_tc launches with per-phase cycle
+/* Measurement knob: device buffer of 16 int64 filled by the next launches of one tensor-core SDF kernel with per-phase cycle
  * counts of block 0 (layout at the definition, csrc/sdf_mlp_tc.cu); NULL switches it off. */
-int gens_debug_tc_profile(long long *buf);
+int gens_debug_tc_profile(long long *buf, int target /* 0 value kernel, 1 JVP forward, 2 reverse */);
 /* Measurement knob: 3 (shipped) or 4 product terms (adds Alo.Blo) in the tensor-core SDF VALUE kernel. */
 int gens_debug_set_tc_terms(int terms);
 /* Measurement probe (bench.py): `iters` resident-operand tcgen05.mma.kind::tf32 128x256x8 instructions per CTA, one
