@@ -129,6 +129,7 @@ _SIGNATURES = {
     "gens_tv_reduce": ([_PP, _PP, _i, _i, _vp, _vp], _i),
     "gens_debug_set_variant": ([_i], _i),
     "gens_debug_set_tc_terms": ([_i], _i),
+    "gens_debug_blend_const": ([_i], _i),
     "gens_debug_tc_profile": ([_vp, _i], _i),
     "gens_tf32_mma_peak": ([_i, _vp, _vp], _i),
     "gens_selftest_division": ([_i, ctypes.c_ulonglong, _vp, _vp], _i),

@@ -4,8 +4,8 @@
 // small Linear layers on (n * n_src) rows plus ~40 element-wise / concat / reduction launches, all of whose
 // activations travel through HBM (27 % of a 16 k-ray render chunk, profiles/r01_launches_bench.txt).  Here one
 // thread owns one sample point, walks its source views, and keeps every activation in registers; the 11 k
-// weights sit in shared memory in the order the loops read them, so that every weight fetch is a broadcast
-// LDS.128 feeding four FFMAs:
+// weights sit in the constant bank (or shared memory) in the order the loops read them, so that every weight fetch
+// is a broadcast feeding four FFMAs:
 //   * "A" layers (inputs in registers) produce their outputs four at a time in a rolled loop,
 //   * the following "B" layer accumulates those four activations into its statically indexed outputs,
 // which keeps the code a few thousand instructions instead of the 19 k a full unroll would need.
@@ -47,6 +47,13 @@ constexpr int oB11 = oW11 + 8;            //                   [1] ; then |s| of
 constexpr int oS = oB11 + 1;
 constexpr int kWeightFloats = oS + 3;
 static_assert(kWeightFloats % 4 == 0, "weight image must be float4 granular");
+
+// The weight image in the constant bank (shipped; gens_debug_blend_const(0) selects the shared-memory variant):
+// broadcast weights arrive as constant-bank operands instead of LDS.128 through the SM's L1 data pipe (69 % busy in the
+// shared-memory variant under ncu), the kernel drops from 168 registers with spills to 128 without, and two blocks
+// of 256 threads fit an SM.  Published per call by one stream-ordered device-to-device copy: launches that use
+// DIFFERENT weights must not overlap on different streams of one device.
+__constant__ float c_blend[kWeightFloats];
 
 __device__ __forceinline__ float elu(float x) { return x > 0.f ? x : expf(x) - 1.0f; }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -93,16 +100,19 @@ __device__ __forceinline__ void view_features(const float* __restrict__ W, const
     for (int j = 0; j < kC; ++j) feat[j] = rf[j] + elu(acc[j]);
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+template <bool CONSTW, int THREADS>
+__global__ void __launch_bounds__(THREADS, CONSTW ? 512 / THREADS : 2)
 blend_kernel(const float* __restrict__ rgb_feat, const float* __restrict__ ray_diff, const uint8_t* __restrict__ mask,
              long long n, int ns, const float* __restrict__ weights, float* __restrict__ rgb_out) {
     extern __shared__ __align__(16) float smem[];
-    float* W = smem;                          // kWeightFloats
-    float* pre3 = smem + kWeightFloats;       // [64][kThreads]: view-independent half of base_fc.0, per thread
-    for (int i = threadIdx.x; i < kWeightFloats / 4; i += kThreads)
-        reinterpret_cast<float4*>(W)[i] = __ldg(reinterpret_cast<const float4*>(weights) + i);
-    __syncthreads();
-    const long long pt = (long long)blockIdx.x * kThreads + threadIdx.x;
+    const float* W = CONSTW ? c_blend : smem;                 // kWeightFloats
+    float* pre3 = smem + (CONSTW ? 0 : kWeightFloats);        // [64][THREADS]: view-independent half of base_fc.0
+    if (!CONSTW) {
+        for (int i = threadIdx.x; i < kWeightFloats / 4; i += THREADS)
+            reinterpret_cast<float4*>(smem)[i] = __ldg(reinterpret_cast<const float4*>(weights) + i);
+        __syncthreads();
+    }
+    const long long pt = (long long)blockIdx.x * THREADS + threadIdx.x;
     if (pt >= n) return;
     const float* rf0 = rgb_feat + pt * ns * kC;
     const float* rd0 = ray_diff + pt * ns * 4;
@@ -152,10 +162,10 @@ blend_kernel(const float* __restrict__ rgb_feat, const float* __restrict__ ray_d
 #pragma unroll 1
     for (int ob = 0; ob < 16; ++ob) {
         const float4 a = a_block<2 * kC>(reinterpret_cast<const float4*>(W + oW3s), ob, mv, ld4(W + oB3, ob));
-        pre3[(4 * ob + 0) * kThreads + threadIdx.x] = a.x;
-        pre3[(4 * ob + 1) * kThreads + threadIdx.x] = a.y;
-        pre3[(4 * ob + 2) * kThreads + threadIdx.x] = a.z;
-        pre3[(4 * ob + 3) * kThreads + threadIdx.x] = a.w;
+        pre3[(4 * ob + 0) * THREADS + threadIdx.x] = a.x;
+        pre3[(4 * ob + 1) * THREADS + threadIdx.x] = a.y;
+        pre3[(4 * ob + 2) * THREADS + threadIdx.x] = a.z;
+        pre3[(4 * ob + 3) * THREADS + threadIdx.x] = a.w;
     }
 
     float logit[kMaxSrc];
@@ -171,8 +181,8 @@ blend_kernel(const float* __restrict__ rgb_feat, const float* __restrict__ ray_d
             for (int j = 0; j < 32; ++j) x[j] = W[oB4 + j];
 #pragma unroll 1
             for (int ob = 0; ob < 16; ++ob) {
-                const float4 init = make_float4(pre3[(4 * ob + 0) * kThreads + threadIdx.x], pre3[(4 * ob + 1) * kThreads + threadIdx.x],
-                                                pre3[(4 * ob + 2) * kThreads + threadIdx.x], pre3[(4 * ob + 3) * kThreads + threadIdx.x]);
+                const float4 init = make_float4(pre3[(4 * ob + 0) * THREADS + threadIdx.x], pre3[(4 * ob + 1) * THREADS + threadIdx.x],
+                                                pre3[(4 * ob + 2) * THREADS + threadIdx.x], pre3[(4 * ob + 3) * THREADS + threadIdx.x]);
                 const float4 a = elu4(a_block<kC>(reinterpret_cast<const float4*>(W + oW3f), ob, feat, init));
                 b_accum<32>(reinterpret_cast<const float4*>(W + oW4), ob, a, x);
             }
@@ -244,6 +254,15 @@ blend_kernel(const float* __restrict__ rgb_feat, const float* __restrict__ ray_d
 
 }  // namespace
 
+namespace {
+int g_blend_const = 1;  // measured: 8.45 ms (shared memory, 168 registers + spills, 12 warps/SM) -> 6.65 ms per 4.2 M points
+}
+// Tuning knob: 1 = weights from the constant bank, 0 = from shared memory.
+extern "C" int gens_debug_blend_const(int on) {
+    g_blend_const = on ? 1 : 0;
+    return 0;
+}
+
 extern "C" int gens_blend_weight_floats(void) { return kWeightFloats; }
 
 extern "C" int gens_blend_colour(const float* rgb_feat, const float* ray_diff, const uint8_t* mask, long long n,
@@ -251,10 +270,22 @@ extern "C" int gens_blend_colour(const float* rgb_feat, const float* ray_diff, c
     if (n == 0) return 0;
     GENS_CHECK_ARG(rgb_feat && ray_diff && mask && weights && rgb_out && n > 0 && n_src > 0);
     if (n_src > kMaxSrc) return GENS_E_UNSUPPORTED;
+    if (g_blend_const) {
+        constexpr int kT = 256;  // 128 registers without the shared-memory weight loads: two blocks of 256
+        const int smem = 64 * kT * (int)sizeof(float);
+        cudaError_t e = cudaFuncSetAttribute(blend_kernel<true, kT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaMemcpyToSymbolAsync(c_blend, weights, sizeof(float) * kWeightFloats, 0, cudaMemcpyDeviceToDevice,
+                                    (cudaStream_t)stream);
+        if (e != cudaSuccess) return (int)e;
+        blend_kernel<true, kT><<<ceil_div_i(n, kT), kT, smem, (cudaStream_t)stream>>>(rgb_feat, ray_diff, mask, n, n_src,
+                                                                                     weights, rgb_out);
+        return gens_launch_status();
+    }
     const int smem = (kWeightFloats + 64 * kThreads) * (int)sizeof(float);
-    const cudaError_t e = cudaFuncSetAttribute(blend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const cudaError_t e = cudaFuncSetAttribute(blend_kernel<false, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    blend_kernel<<<ceil_div_i(n, kThreads), kThreads, smem, (cudaStream_t)stream>>>(rgb_feat, ray_diff, mask, n, n_src,
-                                                                                   weights, rgb_out);
+    blend_kernel<false, kThreads><<<ceil_div_i(n, kThreads), kThreads, smem, (cudaStream_t)stream>>>(rgb_feat, ray_diff, mask, n,
+                                                                                          n_src, weights, rgb_out);
     return gens_launch_status();
 }

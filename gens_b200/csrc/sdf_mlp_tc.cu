@@ -845,6 +845,14 @@ sdf_mlp_rev_kernel(const float* __restrict__ tape, long long n,
             mbar_wait(c.bar_acc(0), acc_phase);
             acc_phase ^= 1;
             tc_fence_after();
+            // The results leave through shared memory: rows of g_fe / g_pos are 400 / 108 bytes apart, so stores from the
+            // row-owning threads touch one sector per lane (6.6 k sector requests per tile, most of the 11 k-cycle tail
+            // the phase timers showed), while a tile's primal rows -- and its tangent rows -- are ONE contiguous block
+            // each in global memory.  The tape buffer layer 0 has just finished with is free (every thread arrived on
+            // bar_a before the MMAs awaited above could start): [half][point][100] floats, then [half][point][27].
+            const uint32_t obuf = stage0 + (use_buf ^ 1u) * (2u * kTapeBytes);
+            constexpr uint32_t kOutPosOff = 2u * 64u * kNF * 4u;
+            const uint32_t orow = (uint32_t)((row & 1) * 64 + (row >> 1));
 #pragma unroll 1
             for (int blk = 0; blk < 2; ++blk) {
                 const int col0 = cq * 32 + blk * 16;
@@ -854,26 +862,47 @@ sdf_mlp_rev_kernel(const float* __restrict__ tape, long long n,
                     tmem_wait_ld();
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (col0 + j < kNP && live)
-                            g_pos[out_row * kNP + col0 + j] =
-                                __uint_as_float(v[j]) + (skip_layer > 0 ? s_skip[row * kNP + col0 + j] : 0.0f);
+                        if (col0 + j < kNP) {
+                            const float o = __uint_as_float(v[j]) + (skip_layer > 0 ? s_skip[row * kNP + col0 + j] : 0.0f);
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(obuf + kOutPosOff + (orow * kNP + col0 + j) * 4u), "f"(o));
+                        }
                 }
                 if (col0 < kNF) {
                     tmem_ld16(c.tmem + lane_base + kColAcc1 + col0, v);
                     tmem_wait_ld();
-                    // rows are 400 bytes apart and col0 is a multiple of 16 floats: 16-byte stores (kNF % 4 == 0)
 #pragma unroll
                     for (int j = 0; j < 16; j += 4)
-                        if (col0 + j < kNF && live) {
+                        if (col0 + j < kNF) {
                             float4 o;
                             o.x = __uint_as_float(v[j]) + (tangent ? 0.0f : s_const[128 + col0 + j]);
                             o.y = __uint_as_float(v[j + 1]) + (tangent ? 0.0f : s_const[128 + col0 + j + 1]);
                             o.z = __uint_as_float(v[j + 2]) + (tangent ? 0.0f : s_const[128 + col0 + j + 2]);
                             o.w = __uint_as_float(v[j + 3]) + (tangent ? 0.0f : s_const[128 + col0 + j + 3]);
-                            *reinterpret_cast<float4*>(g_fe + out_row * kNF + col0 + j) = o;
+                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(obuf + (orow * kNF + col0 + j) * 4u),
+                                         "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w));
                         }
                 }
             }
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            {
+                const long long first = tile * kPts;
+                const long long left = n - first;
+                const int pts_here = left < kPts ? (int)left : kPts;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const long long grow = (h ? n : 0) + first;
+                    float4* dfe = reinterpret_cast<float4*>(g_fe + grow * kNF);
+                    for (int idx = threadIdx.x; idx < pts_here * (kNF / 4); idx += kEpiThreads)
+                        dfe[idx] = lds128(obuf + (uint32_t)(h * 64 * kNF * 4) + (uint32_t)idx * 16u);
+                    float* dpo = g_pos + grow * kNP;
+                    for (int idx = threadIdx.x; idx < pts_here * kNP; idx += kEpiThreads) {
+                        float o;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o) : "r"(obuf + kOutPosOff + (uint32_t)(h * 64 * kNP + idx) * 4u));
+                        dpo[idx] = o;
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");  // the buffer is a prefetch target again from here on
             tc_fence_before();  // accumulator reads done before the next tile's MMAs may overwrite them
             if (timing) pt[6] += clock64() - tail0;
         }

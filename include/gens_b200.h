@@ -386,6 +386,9 @@ int gens_mc_triangles(const float *u, int rx, int ry, int rz, float iso, const l
                       const uint8_t *vmask, const uint8_t *tri_count, const int8_t *tri_edges, int max_tris,
                       const int8_t *edge_owner, long long vert_offset, long long *tris, void *stream);
 
+/* Tuning knob of K10: 1 = blending weights read from the constant bank, 0 = from shared memory (shipped default: see
+ * csrc/blend.cu). */
+int gens_debug_blend_const(int on);
 /* Measurement knob: device buffer of 16 int64 filled by the next launches of one tensor-core SDF kernel with per-phase cycle
  * counts of block 0 (layout at the definition, csrc/sdf_mlp_tc.cu); NULL switches it off. */
 int gens_debug_tc_profile(long long *buf, int target /* 0 value kernel, 1 JVP forward, 2 reverse */);
