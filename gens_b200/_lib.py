@@ -180,10 +180,19 @@ def stream_ptr(device=None):
 
 
 def require_cuda(*tensors):
+    """Every tensor on the CURRENT CUDA device.  The C entries launch on the current device with the stream handed to
+    them: a tensor living elsewhere would otherwise surface as an invalid-resource-handle error from the launch (one
+    process drives one GPU here -- call torch.cuda.set_device / use `with torch.cuda.device(...)` first)."""
+    cur = None
     for t in tensors:
         if not t.is_cuda:
             raise RuntimeError("gens_b200 kernels need CUDA tensors (no CPU fallback); got a "
                                f"{t.device} tensor")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError(f"gens_b200: tensor on {t.device} but the current CUDA device is cuda:{cur}; "
+                               "make the tensors' device current (torch.cuda.set_device) before calling")
 
 
 def f32c(t: torch.Tensor) -> torch.Tensor:
