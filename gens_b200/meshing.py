@@ -84,14 +84,16 @@ def marching_cubes(u, isovalue: float):
 
 
 def sharded_marching_cubes(u_slab: torch.Tensor, isovalue: float, x0: int, rank: int, world: int, group=None,
-                           dst: Optional[int] = 0):
+                           dst: Optional[int] = 0, mesher=None):
     """Mesh of a lattice that is sharded by x-slabs (parallel.sharded_sdf_grid without the gather): every rank
     meshes the cells of its own slab -- `u_slab` holds its planes PLUS the first plane of the next rank's slab (the
     far face of its last cells; the last rank has none) -- and only the meshes travel: vertices / triangles are
     gathered on rank `dst` (or everywhere with dst=None) with the triangle indices re-based.  Vertices on a slab
     boundary plane are emitted by both neighbours (the mesh is geometrically watertight, not index-welded there)."""
     import torch.distributed as dist
-    v, t = marching_cubes_device(u_slab, isovalue, index_offset=(float(x0), 0.0, 0.0))
+    # `mesher(u, iso, index_offset=...) -> (vertices (n,3) f64, triangles (m,3) i64)`: the device kernels by default (a
+    # CPU mesher is injected by the gloo test of this gather logic)
+    v, t = (mesher or marching_cubes_device)(u_slab, isovalue, index_offset=(float(x0), 0.0, 0.0))
     if world == 1:
         return v, t
     counts = torch.tensor([v.shape[0], t.shape[0]], device=v.device, dtype=torch.int64)

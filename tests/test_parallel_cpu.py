@@ -66,6 +66,27 @@ def _worker(rank, world, port, golden_dir, out_q):
         ok &= (on_dst is None) if rank != 0 else torch.equal(on_dst, lattice)
         everywhere = parallel.sharded_sdf_grid(sdf_grid_fn, res, rank, world, dst=None)
         ok &= torch.equal(everywhere, lattice)
+        # sharded mesh extraction: every rank meshes its x-slab (+ one plane of overlap), only the meshes travel.  The
+        # CPU oracle's sequential mesher stands in for the CUDA kernels; the merged mesh must be the full lattice's.
+        from gens_b200 import meshing
+        from oracle import mc_oracle
+        gx = np.linspace(-1, 1, 17)
+        xx, yy, zz = np.meshgrid(gx, gx, gx, indexing="ij")
+        field = (np.sqrt(xx * xx + yy * yy + zz * zz) - 0.6).astype(np.float32)
+
+        def cpu_mesher(u, iso, index_offset=(0.0, 0.0, 0.0)):
+            v, t = mc_oracle.marching_cubes_numpy(u.numpy(), iso)
+            return torch.from_numpy(v + np.asarray(index_offset)[None, :]), torch.from_numpy(t)
+        x0, x1 = parallel.shard_range(17, rank, world)
+        slab = torch.from_numpy(field[x0:min(x1 + 1, 17)])
+        mv, mt = meshing.sharded_marching_cubes(slab, 0.0, x0, rank, world, dst=None, mesher=cpu_mesher)
+        fv, ft = mc_oracle.marching_cubes_numpy(field, 0.0)
+        # this CPU stand-in adds the slab offset AFTER the interpolation ((i_local + t) + x0, one ulp away from
+        # (i_global + t)); the CUDA mesher adds it to the integer index first and is exact (test_marching_cubes_gpu.py)
+        merged, whole = mc_oracle.canonical_triangles(mv.numpy(), mt.numpy()), mc_oracle.canonical_triangles(fv, ft)
+        ok &= merged.shape == whole.shape and bool(np.allclose(merged, whole, rtol=0.0, atol=1e-12))
+        only0 = meshing.sharded_marching_cubes(slab, 0.0, x0, rank, world, dst=0, mesher=cpu_mesher)
+        ok &= (only0[0] is None) if rank != 0 else (only0[1].shape[0] == ft.shape[0])
         out_q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
