@@ -207,8 +207,9 @@ class BlendingNetwork(nn.Module):
     # -- inference path: the whole network as one kernel (K10, csrc/blend.cu) -----------------------------
     def packed_weights(self) -> torch.Tensor:
         """The eleven Linear layers re-ordered into the shared-memory image of blend_kernel: "A" layers as
-        [out/4][in][4], the "B" layer that follows as [in/4][out][4], biases padded to float4 (offsets: the
-        constexpr table at the top of csrc/blend.cu).  Cached per parameter versions."""
+        [out/4][in][4], the "B" layer that follows as [in/4][ceil(out/2)][4 inputs][2 outputs] (an odd output count is
+        padded with a zero row), biases padded to float4 (offsets: the constexpr table at the top of csrc/blend.cu).
+        Cached per parameter versions."""
         params = list(self.parameters())
         key = tuple((p.data_ptr(), p._version) for p in params)
         if getattr(self, "_packed_key", None) == key:
@@ -219,9 +220,10 @@ class BlendingNetwork(nn.Module):
             out, inp = w.shape
             return w.reshape(out // 4, 4, inp).permute(0, 2, 1).reshape(-1)
 
-        def b_layout(w):                      # (out, in) -> [in/4][out][4]
+        def b_layout(w):                      # (out, in) -> [in/4][out/2][4][2]
+            w = F.pad(w, (0, 0, 0, w.shape[0] % 2))
             out, inp = w.shape
-            return w.reshape(out, inp // 4, 4).permute(1, 0, 2).reshape(-1)
+            return w.reshape(out // 2, 2, inp // 4, 4).permute(2, 0, 3, 1).reshape(-1)
 
         def pad4(v):
             v = v.reshape(-1)

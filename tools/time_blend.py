@@ -26,4 +26,4 @@ for ns in (2, 4):
             b.record(); torch.cuda.synchronize()
             print(f"ns={ns} const={knob}: {a.elapsed_time(b) / 3:.3f} ms per {n} points, max |diff| vs module "
                   f"{float((out[:65536] - ref).abs().max()):.2e}", flush=True)
-_lib.lib().gens_debug_blend_const(0)
+_lib.lib().gens_debug_blend_const(1)
