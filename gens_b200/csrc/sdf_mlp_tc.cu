@@ -760,10 +760,14 @@ sdf_mlp_rev_kernel(const float* __restrict__ tape, long long n,
                     tc_fence_after();
                 }
                 long long e1 = timing ? clock64() : 0, e2 = e1, e3 = e1, e4 = e1;
-#pragma unroll 1
+                // Both 16-column blocks are loaded and differentiated BEFORE the wait for the feature-part MMAs of the
+                // layer above (which still read the A operand), so that only the TF32 split and the tcgen05.st of the
+                // new A operand remain behind that wait (before: the second block's load and arithmetic as well).
+                float outv[2][16];
+#pragma unroll
                 for (int blk = 0; blk < 2; ++blk) {
                     const int col0 = cq * 32 + blk * 16;
-                    uint32_t v[16], hi[16], lo[16];
+                    uint32_t v[16];
                     if (top) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(tangent ? 0.0f : s_const[col0 + j]);
@@ -805,19 +809,25 @@ sdf_mlp_rev_kernel(const float* __restrict__ tape, long long n,
                     for (int j = 0; j < 16; ++j) {
                         const float mine = __uint_as_float(v[j]);                    // g_h (primal) / dg_h (tangent)
                         const float other = __shfl_xor_sync(0xffffffffu, mine, 1);  // the pair's other row
-                        const float out = tangent ? fmaf(d2[j], other, d1[j] * mine) : d1[j] * mine;
-                        split_tf32(out, hi[j], lo[j]);
+                        outv[blk][j] = tangent ? fmaf(d2[j], other, d1[j] * mine) : d1[j] * mine;
                     }
-                    if (timing && blk == 0) e3 = clock64();
-                    if (!top && blk == 0) {
-                        // The layer above committed its x-part (barrier 0: accumulator 0 readable) BEFORE its
-                        // feature-part MMAs, which still read the A operand this thread is about to overwrite and ran
-                        // while the values above were loaded and computed; barrier 1 says they are done.
-                        mbar_wait(c.bar_acc(1), afree_phase);
-                        afree_phase ^= 1;
-                        tc_fence_after();
-                    }
-                    if (timing && blk == 0) e4 = clock64();
+                }
+                if (timing) e3 = clock64();
+                if (!top) {
+                    // The layer above committed its x-part (barrier 0: accumulator 0 readable) BEFORE its
+                    // feature-part MMAs, which still read the A operand this thread is about to overwrite and ran
+                    // while the values above were loaded and computed; barrier 1 says they are done.
+                    mbar_wait(c.bar_acc(1), afree_phase);
+                    afree_phase ^= 1;
+                    tc_fence_after();
+                }
+                if (timing) e4 = clock64();
+#pragma unroll
+                for (int blk = 0; blk < 2; ++blk) {
+                    const int col0 = cq * 32 + blk * 16;
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) split_tf32(outv[blk][j], hi[j], lo[j]);
                     tmem_st16(c.tmem + lane_base + kColAhi + col0, hi);
                     tmem_st16(c.tmem + lane_base + kColAlo + col0, lo);
                 }
@@ -833,9 +843,9 @@ sdf_mlp_rev_kernel(const float* __restrict__ tape, long long n,
                 if (timing) {
                     pt[0] += e1 - e0;            // wait for the x-part MMAs of the layer above
                     pt[1] += e2 - e1;            // wait for this layer's s1 / t2 (cp.async)
-                    pt[2] += e3 - e2;            // accumulator load + arithmetic of the first 16 columns
+                    pt[2] += e3 - e2;            // accumulator load + arithmetic of both 16-column blocks
                     pt[3] += e4 - e3;            // wait for the feature-part MMAs (A operand free)
-                    pt[4] += e5 - e4;            // stores, second 16 columns, store fence, arrive
+                    pt[4] += e5 - e4;            // TF32 split, stores, store fence, arrive
                     pt[5] += clock64() - e5;     // prefetch issue
                     pt[7] += 1;
                 }
