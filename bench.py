@@ -688,6 +688,29 @@ def bench_train(args, rank, world, dev, timed):
                    "reprojection (K6 fwd/bwd), LNCC (K11 fwd/bwd), up-sampling (K5) and K1/K1b are this repo's kernels"}
     del step, build_step
     torch.cuda.empty_cache()
+    if rank == 0 and world == 1:
+        # SURVEY 8d "GPU reference baseline" for config 3: the UNMODIFIED reference's ImplicitSurface.forward("train")
+        # + the same loss (its own compute_LNCC) + backward() on this GPU: same weights, rays, volumes, feature maps.
+        ns = load_reference()
+        if ns is not None:
+            from gens_b200.config import gens_model_conf
+            ref_surf = ns.implicit_surface.ImplicitSurface(gens_model_conf()["implicit_surface"]).to(dev)
+            ref_surf.load_state_dict(surf.state_dict())
+            ref_surf.train()
+            rvols = [v.detach().clone().requires_grad_(True) for v in vols]
+            rfeats = [f.detach().clone().requires_grad_(True) for f in feats]
+            rstep = train_step_fn(ref_surf, sc, rvols, masks, rfeats, n_rays, ns.ncc.compute_LNCC, dev)
+            r_ms, _ = timed(rstep, 3, 3)
+            res["reference_ops_on_gpu"] = {
+                "value": n_rays * 128 / (r_ms * 1e-3), "unit": "ray-samples/s", "ms_per_step": r_ms, "kind": "reference",
+                "steps": 3, "warmup": 3,
+                "sample": "the unmodified reference (baseline/_ref: ImplicitSurface.forward('train'), its own "
+                          "gridsample_grad2 extension and compute_LNCC) + the same loss + backward(), same 512 rays, "
+                          "weights, volumes and feature maps on this GPU"}
+            del rstep, ref_surf, rvols, rfeats
+            import ref_runtime
+            ref_runtime.purge()
+            torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import torch_oracle
         cores = os.cpu_count() or 1
@@ -743,6 +766,111 @@ def bench_lattice(args, rank, world, dev, timed):
         out["verified"] = {"lattice_slabs_bit_identical": all_ranks_true(ok, world, dev),
                            "checked": "2 planes of every other rank's slab recomputed on rank 0"}
         del full
+    return out
+
+
+def bench_regularise(args, rank, world, dev, sc, vol_mod, timed):
+    """SURVEY 8f-4, the hand-off to the volume regulariser: the volume side of GenS.forward (models/gens.py:143-145:
+    agg_mean_var -> reg_network) from feature maps to the (1,4,D,D,D) volumes + masks the ray marcher samples, present
+    on every rank.  N = 1: K1 + the whole-volume network.  N > 1: parallel.sharded_build_and_regularise -- K1 slabs stay
+    on their rank, the network runs slab-parallel (halo planes + all-reduced InstanceNorm moments), only the 4-channel
+    results and the masks are gathered; checked on every rank against the local whole-volume pipeline.
+    Stride-1 layers at the fine scales and all InstanceNorms: K13 (csrc/conv3d.cu); stride-2 / transposed / deep layers:
+    cuDNN fp32 (library), TF32 off so that every arm is plain fp32.  N = 1 also times the reference's own network
+    (baseline/_ref when staged, else the same op sequence: cuDNN + ATen instance_norm) on K1's volumes."""
+    from gens_b200 import parallel
+    from gens_b200.config import gens_model_conf
+    from gens_b200.reg_network import RegNetwork
+    torch.manual_seed(0)
+    net = RegNetwork(gens_model_conf()["reg_network"]).to(dev).eval()
+    old_tf32, old_bench = torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True  # both arms: cuDNN picks its fastest algorithm per shape during warm-up
+
+    def whole():
+        with torch.no_grad():
+            v, m = vol_mod.agg_mean_var(sc.features, sc.intrs, sc.c2ws)
+            return net(v), m
+
+    def sharded():
+        return parallel.sharded_build_and_regularise(vol_mod, net, sc.features, sc.intrs, sc.c2ws, rank, world)
+    try:
+        ms_whole, _ = timed(whole, 3, 2)
+        out = {"metric": "voxel*views/s (build + regularise: the volume side of GenS.forward)",
+               "value": voxel_views(sc.intrs.shape[0]) / (ms_whole * 1e-3), "unit": "voxel*views/s", "ms_per_step": ms_whole,
+               "n_gpus": world, "steps": 3, "warmup": 2, "one_gpu_ms": ms_whole,
+               "note": "K1 builds the input; stride-1 convolutions with c_out <= 16 and every InstanceNorm = K13 "
+                       "(csrc/conv3d.cu), the other layers cuDNN fp32 (library calls, TF32 off)"}
+        if world == 1 and rank == 0:
+            import importlib.util
+            from gens_b200.reg_network import _LocalOps
+            path = os.path.join(ROOT, "baseline", "_ref", "GenS", "models", "modules", "reg_network.py")
+            kind = "port"
+            ref_net = None
+            if os.path.exists(path):
+                spec = importlib.util.spec_from_file_location("_bench_ref_reg_network", path)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                ref_net = mod.RegNetwork(gens_model_conf()["reg_network"]).to(dev).eval()
+                ref_net.load_state_dict(net.state_dict())
+                kind = "reference"
+            with torch.no_grad():
+                v32, _ = vol_mod.agg_mean_var(sc.features, sc.intrs, sc.c2ws)
+                run_ref = (lambda: ref_net(v32)) if ref_net is not None else (lambda: net._run(v32, _LocalOps))
+                ms_ref, _ = timed(run_ref, 3, 2)
+                ms_net, _ = timed(lambda: net(v32), 3, 2)
+                import copy
+                ref64 = copy.deepcopy(net).double()([v.double() for v in v32])
+
+                def err(outs):
+                    return max(float(((a.double() - b).abs() / (1e-5 * b.abs().max() + 1e-4 * b.abs())).max())
+                               for a, b in zip(outs, ref64))
+                e_ours, e_ref = err(net(v32)), err(run_ref())
+            out["network_only_ms"] = ms_net
+            out["reference_ops_on_gpu"] = {
+                "network_only_ms": ms_ref, "kind": kind,
+                "sample": ("the unmodified reference RegNetwork (baseline/_ref)" if kind == "reference" else
+                           "the reference's op sequence (cuDNN conv3d + ATen instance_norm)") + " on the same volumes and weights, fp32, this GPU",
+                "error_vs_float64": e_ref, "ours_error_vs_float64": e_ours,
+                "error_unit": "multiples of (1e-5 x max|ref| + 1e-4 x |ref|), worst output voxel of all scales"}
+            del v32, ref64, ref_net
+        if world > 1:
+            ms_sh, _ = timed(sharded, 3, 2)
+            # Whole volumes and slabs go through different cuDNN algorithms, so the two fp32 results differ by rounding
+            # that 17 convolution + InstanceNorm layers amplify.  Judge both against the SAME network evaluated in
+            # float64 on K1's (bit-identical) volumes: the slab pipeline must be as close to it as the whole-volume one.
+            import copy
+            with torch.no_grad():
+                (wv, wm), (sv, sm) = whole(), sharded()
+                v32, _ = vol_mod.agg_mean_var(sc.features, sc.intrs, sc.c2ws)
+                ref64 = copy.deepcopy(net).double()([v.double() for v in v32])
+                torch.cuda.synchronize(dev)
+
+                def err(outs):
+                    return max(float(((a.double() - b).abs() / (1e-5 * b.abs().max() + 1e-4 * b.abs())).max())
+                               for a, b in zip(outs, ref64))
+                err_whole, err_slab = err(wv), err(sv)
+                direct = max(float(((a - b).abs() / (1e-5 * b.abs().max() + 1e-4 * b.abs())).max()) for a, b in zip(sv, wv))
+                same_masks = all(torch.equal(a, b) for a, b in zip(sm, wm))
+                ok = same_masks and err_slab <= max(1.0, 1.5 * err_whole) and direct <= 10.0
+                del wv, wm, sv, sm, v32, ref64
+            gathered = sum(5 * d ** 3 * 4 for d in DIMS) * (world - 1) // world
+            out.update({"value": voxel_views(sc.intrs.shape[0]) / (ms_sh * 1e-3), "ms_per_step": ms_sh,
+                        "sharding": f"x-slabs over {world} ranks end to end: K1 slab -> slab-parallel U-Net (one halo plane "
+                                    "per layer and side, InstanceNorm moments all-reduced) -> gather of 4 + 1 channels",
+                        "gathered_bytes_per_gpu": gathered,
+                        "gathered_bytes_if_volumes_were_exchanged_first": sum(9 * d ** 3 * 4 for d in DIMS) * (world - 1) // world,
+                        "verified": {"as_accurate_as_the_whole_volume_pipeline": all_ranks_true(ok, world, dev),
+                                     "slab_error_vs_float64": max_over_ranks(err_slab, world, dev),
+                                     "whole_volume_error_vs_float64": max_over_ranks(err_whole, world, dev),
+                                     "slab_vs_whole_volume_fp32": max_over_ranks(direct, world, dev),
+                                     "unit": "multiples of (1e-5 x max|ref| + 1e-4 x |ref|), worst output voxel of all scales",
+                                     "rule": "masks torch.equal; slab error vs the float64 evaluation of the same network "
+                                             "<= max(1, 1.5 x the whole-volume fp32 pipeline's own error); checked on every rank"}})
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = old_tf32, old_bench
+    del net
+    torch.cuda.empty_cache()
     return out
 
 
@@ -841,6 +969,7 @@ def run_ours(args, rank, world, local):
             render = bench_render(args, rank, world, dev, sc, host, vol_mod, timed)
         lattice = None if args.no_lattice else bench_lattice(args, rank, world, dev, timed)
         train = None if args.no_train else bench_train(args, rank, world, dev, timed)
+        regularise = None if args.no_regularise else bench_regularise(args, rank, world, dev, sc, vol_mod, timed)
     clk = clocks.summary()
 
     fill = None
@@ -943,6 +1072,7 @@ def run_ours(args, rank, world, local):
         "render": render,
         "lattice": lattice,
         "train_step": train,
+        "regularise": regularise,
     }
     emit(line)
 
@@ -959,6 +1089,7 @@ def main():
     ap.add_argument("--render-steps", type=int, default=2, help="full-image renders timed for the render metric")
     ap.add_argument("--render-chunk", type=int, default=RENDER_CHUNK)
     ap.add_argument("--no-lattice", action="store_true", help="skip the config-5 lattice leg")
+    ap.add_argument("--no-regularise", action="store_true", help="skip the build + RegNetwork hand-off leg")
     ap.add_argument("--no-train", action="store_true", help="skip the config-3 training-step leg")
     ap.add_argument("--lattice-res", type=int, default=512)
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],

@@ -126,6 +126,8 @@ _SIGNATURES = {
                           _vp, _vp], _i),
     "gens_mc_triangles": ([_vp, _i, _i, _i, _f, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _i, ctypes.c_char_p, _ll,
                            _vp, _vp], _i),
+    "gens_conv3d_k3": ([_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp], _i),
+    "gens_instnorm_relu": ([_vp, _vp, _i, _ll, ctypes.c_double, _f, _vp, _vp], _i),
     "gens_tv_reduce": ([_PP, _PP, _i, _i, _vp, _vp], _i),
     "gens_debug_set_variant": ([_i], _i),
     "gens_debug_set_tc_terms": ([_i], _i),

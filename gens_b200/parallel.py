@@ -174,6 +174,42 @@ def sharded_agg_mean_var(volume_module, features, intrs, c2ws, rank: int, world:
     return full_v, full_m
 
 
+def gather_slab_volumes(slabs: Sequence[torch.Tensor], rank: int, world: int, group=None) -> List[torch.Tensor]:
+    """slabs[i] (1,C,D_i/P,D_i,D_i) on each rank -> (1,C,D_i,D_i,D_i) on every rank (in place on CUDA: the slab is
+    copied to its planes of the final tensor and one all-gather per channel fills in the rest)."""
+    out = []
+    for s in slabs:
+        d = s.shape[3]
+        if world == 1:
+            out.append(s)
+        elif s.is_cuda and d % world == 0:
+            a0, a1 = slab_bounds(d, rank, world)
+            full = torch.empty((1, s.shape[1], d, d, d), device=s.device, dtype=s.dtype)
+            full[:, :, a0:a1].copy_(s)
+            out.append(gather_slabs_inplace(full, d, rank, world, group))
+        else:
+            out.append(gather_slabs(s, d, world, group))
+    return out
+
+
+@torch.no_grad()
+def sharded_build_and_regularise(volume_module, reg_network, features, intrs, c2ws, rank: int, world: int,
+                                 min_vis_view: int = 1, group=None):
+    """The volume side of GenS.forward / init_volumes (reference models/gens.py:68-70, :143-145) on P GPUs without
+    ever assembling the 9-channel volumes: every rank builds its x-slabs (K1), the regulariser runs slab-parallel on
+    them (gens_b200/reg_network.py: one halo plane per layer and side, InstanceNorm statistics all-reduced), and only
+    the 4-channel results and the masks are gathered -- 384 MB instead of 690 MB per build for the config-2
+    pyramid, and 1/P of the regulariser's work per GPU.  Returns (volumes, mask_volumes) as
+    `reg_network(volume.agg_mean_var(...)[0])`, `...[1]` would on one GPU, on every rank.  Inference only."""
+    from .volume import agg_mean_var
+    dims = volume_module.volume_dims
+    slabs = [slab_bounds(d, rank, world) for d in dims]
+    vols, masks = agg_mean_var(features, intrs, c2ws, dims, min_vis_view, slabs, volume_module.div_mode)
+    reg = reg_network.forward_slabs(vols, rank, world, group)
+    del vols
+    return gather_slab_volumes(reg, rank, world, group), gather_slab_volumes(masks, rank, world, group)
+
+
 def gather_rays(local: torch.Tensor, n_total: int, rank: int, world: int, group=None) -> torch.Tensor:
     """Per-ray outputs (n_local, ...) of contiguous ray shards -> (n_total, ...) on every rank."""
     if world == 1:

@@ -1,0 +1,247 @@
+"""The volume regulariser that consumes K1's output, and its slab-parallel form.
+
+Reference: models/modules/reg_network.py:105-166 (`RegNetwork`): a 3-D U-Net over the five (1,8,D_i,D_i,D_i) mean/var
+volumes -- conv0, five stride-2 encoder stages (the next coarser volume is concatenated after each), five transposed-
+convolution decoder stages with skip additions, one 3x3x3 output convolution per scale -> five (1,4,D_i,D_i,D_i)
+volumes that the ray marcher samples.  Every convolution except the output ones is followed by InstanceNorm3d
+(no affine, eps 1e-5) and ReLU.  `RegNetwork` here keeps the reference's parameter names, so its state_dict loads.
+
+Why it is in this repo: on P GPUs the reference's data flow needs the full 9-channel volumes on every rank BEFORE this
+network (690 MB ingested per GPU, the floor of the fused slab exchange of gens_b200/parallel.py).  `forward_slabs` runs
+the SAME network on the x-slabs K1 leaves on each rank instead:
+  * a 3x3x3 convolution needs one neighbouring plane per side (stride 2: only the lower side; transposed stride 2: only
+    the upper side) -- one plane exchanged with each neighbour per layer (`_Ops.halo`, point-to-point);
+  * InstanceNorm needs the per-channel mean / variance of the WHOLE volume -- every rank reduces its slab and one
+    all-reduce of 2C numbers per layer combines them (parallel-variance formula, accumulated in float64);
+  * only the 4-channel results (and the 1-channel masks) are gathered afterwards: 384 MB instead of 690 MB per
+    build, and the network itself runs on 1/P of the voxels per GPU.
+Kernels: the stride-1 layers at the fine scales and every InstanceNorm run on K13 (csrc/conv3d.cu) -- in cuDNN / ATen
+those take 98 of the network's 112 ms on one B200; the stride-2 / transposed / deep narrow layers stay cuDNN (library
+calls, counted as such).  The slab path is inference only (like the other sharded paths): the reference trains with one
+scene per GPU (DDP replicas), and with autograd enabled `forward` is the reference's own op sequence.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import ctypes
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+EPS = 1e-5  # nn.InstanceNorm3d default, reg_network.py:16
+
+
+class _Unit(nn.Module):
+    """Holder of one normalised convolution; the weight lives in `.conv` as in the reference's Conv3d / Deconv3d
+    blocks (reg_network.py:7-50), bias-free because a normalisation follows."""
+
+    def __init__(self, c_in: int, c_out: int, stride: int = 1, transposed: bool = False):
+        super().__init__()
+        self.stride, self.transposed = stride, transposed
+        if transposed:
+            self.conv = nn.ConvTranspose3d(c_in, c_out, 3, stride=stride, padding=1, output_padding=stride - 1, bias=False)
+        else:
+            self.conv = nn.Conv3d(c_in, c_out, 3, stride=stride, padding=1, bias=False)
+
+
+class _LocalOps:
+    """Whole volumes on one device."""
+
+    @staticmethod
+    def unit(x: torch.Tensor, u: _Unit, skip: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if u.transposed:
+            y = F.conv_transpose3d(x, u.conv.weight, None, stride=u.stride, padding=1, output_padding=u.stride - 1)
+        else:
+            y = F.conv3d(x, u.conv.weight, None, stride=u.stride, padding=1)
+        y = F.relu_(F.instance_norm(y, eps=EPS))
+        return y if skip is None else y + skip
+
+    @staticmethod
+    def out(x: torch.Tensor, conv: nn.Conv3d) -> torch.Tensor:
+        return F.conv3d(x, conv.weight, conv.bias, stride=1, padding=1)
+
+
+class _Ops:
+    """Inference ops on x-slabs (planes of tensor dim 2) of every tensor on `world` ranks; rank r owns planes
+    [r d/P, (r+1) d/P).  world = 1: whole volumes.  On CUDA the stride-1 layers with c_in % 8 == 0 and c_out in
+    {4, 8, 16} run on K13 (csrc/conv3d.cu: direct FFMA2 convolution that also reduces the InstanceNorm moments, halo
+    planes read in place) and every normalisation on its in-place kernel; the rest (stride 2, transposed, the deep
+    narrow levels) is cuDNN with the moments taken by torch.var_mean."""
+
+    def __init__(self, rank: int = 0, world: int = 1, group=None):
+        self.rank, self.world, self.group = rank, world, group
+        self._packed = {}
+
+    def _peer(self, r: int) -> int:
+        return r if self.group is None else dist.get_global_rank(self.group, r)
+
+    def halo(self, x: torch.Tensor, lower: bool, upper: bool):
+        """The neighbours' boundary planes: (plane below the slab or None, plane above or None); None at the
+        volume's ends (= the convolution's zero padding)."""
+        r, p = self.rank, self.world
+        lo = torch.empty_like(x[:, :, :1]) if lower and r > 0 else None
+        hi = torch.empty_like(x[:, :, :1]) if upper and r + 1 < p else None
+        ops, keep = [], []
+        if lower and r + 1 < p:                     # my last plane is the lower halo of rank r+1
+            keep.append(x[:, :, -1:].contiguous())
+            ops.append(dist.P2POp(dist.isend, keep[-1], self._peer(r + 1), self.group))
+        if lo is not None:
+            ops.append(dist.P2POp(dist.irecv, lo, self._peer(r - 1), self.group))
+        if upper and r > 0:                         # my first plane is the upper halo of rank r-1
+            keep.append(x[:, :, :1].contiguous())
+            ops.append(dist.P2POp(dist.isend, keep[-1], self._peer(r - 1), self.group))
+        if hi is not None:
+            ops.append(dist.P2POp(dist.irecv, hi, self._peer(r + 1), self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return lo, hi
+
+    @staticmethod
+    def _padded(x, lo, hi, lower: bool, upper: bool):
+        parts = ([lo if lo is not None else torch.zeros_like(x[:, :, :1])] if lower else []) + [x] + \
+                ([hi if hi is not None else torch.zeros_like(x[:, :, :1])] if upper else [])
+        return torch.cat(parts, 2) if len(parts) > 1 else x
+
+    def _k13(self, x, conv) -> bool:
+        w = conv.weight
+        return (x.is_cuda and x.dtype == torch.float32 and isinstance(conv, nn.Conv3d) and conv.stride == (1, 1, 1)
+                and w.shape[1] % 8 == 0 and w.shape[0] in (4, 8, 16) and x.shape[0] == 1)
+
+    def _conv_k13(self, x, conv, lo, hi, want_stats: bool):
+        from . import _lib
+        w = conv.weight
+        key = (w.data_ptr(), w._version)
+        pk = self._packed.get(key)
+        if pk is None:  # (c_out, c_in, kd, kh, kw) -> [c_in][kh][kw][kd][c_out]
+            pk = self._packed[key] = w.detach().permute(1, 3, 4, 2, 0).contiguous().float()
+        x = _lib.f32c(x)
+        _, c_in, d, h, wd = x.shape
+        c_out = w.shape[0]
+        y = torch.empty((1, c_out, d, h, wd), device=x.device, dtype=torch.float32)
+        stats = torch.zeros(2 * c_out, device=x.device, dtype=torch.float64) if want_stats else None
+        null = ctypes.c_void_p(0)
+        _lib.check(_lib.lib().gens_conv3d_k3(
+            _lib.ptr(x), _lib.ptr(lo.contiguous()) if lo is not None else null,
+            _lib.ptr(hi.contiguous()) if hi is not None else null, _lib.ptr(pk),
+            _lib.ptr(conv.bias.detach()) if conv.bias is not None else null, c_in, c_out, d, h, wd, _lib.ptr(y),
+            _lib.ptr(stats) if want_stats else null, _lib.stream_ptr(x.device)), "gens_conv3d_k3")
+        return y, stats
+
+    def norm_relu_(self, y: torch.Tensor, stats: Optional[torch.Tensor], skip: Optional[torch.Tensor] = None):
+        """InstanceNorm over the WHOLE volume + ReLU (+ skip), in place.  stats = per-channel [sum | sum of squares] of
+        this rank's slab (float64); None: taken here.  Slabs are equal-sized, so the all-reduced sums over P x the local
+        count are the volume's moments."""
+        c = y.shape[1]
+        n_local = y[0, 0].numel()
+        if stats is None:
+            var, mean = torch.var_mean(y, dim=(0, 2, 3, 4), unbiased=False)
+            mean, var = mean.double(), var.double()
+            stats = torch.cat([mean, var + mean * mean]) * n_local
+        if self.world > 1:
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.group)
+        count = float(n_local * self.world)
+        if y.is_cuda and y.dtype == torch.float32 and y.is_contiguous() and n_local % 4 == 0 and \
+                (skip is None or (skip.is_contiguous() and skip.dtype == torch.float32)):
+            from . import _lib
+            _lib.check(_lib.lib().gens_instnorm_relu(
+                _lib.ptr(y), _lib.ptr(stats), c, n_local, count, EPS,
+                _lib.ptr(skip) if skip is not None else ctypes.c_void_p(0), _lib.stream_ptr(y.device)), "gens_instnorm_relu")
+            return y
+        g_mean = stats[:c] / count
+        rstd = torch.rsqrt((stats[c:] / count - g_mean * g_mean).clamp_min_(0.0) + EPS)
+        shape = (1, -1, 1, 1, 1)
+        y = y.sub_(g_mean.float().view(shape)).mul_(rstd.float().view(shape)).relu_()
+        return y.add_(skip) if skip is not None else y
+
+    def unit(self, x: torch.Tensor, u: _Unit, skip: Optional[torch.Tensor] = None) -> torch.Tensor:
+        d = x.shape[2]
+        w = u.conv.weight
+        stats = None
+        if u.transposed:                            # out plane 2i <- in i; out 2i+1 <- in i and i+1: upper halo only
+            lo, hi = self.halo(x, False, True) if self.world > 1 else (None, None)
+            y = F.conv_transpose3d(self._padded(x, None, hi, False, self.world > 1), w, None, stride=2, padding=1,
+                                   output_padding=1)[:, :, : 2 * d].contiguous()
+        elif u.stride == 2:                         # out plane o <- in 2o-1, 2o, 2o+1: lower halo only
+            if d % 2:
+                raise RuntimeError("slab-parallel RegNetwork: a stride-2 stage met a slab with an odd plane count")
+            lo, hi = self.halo(x, True, False) if self.world > 1 else (None, None)
+            y = F.conv3d(self._padded(x, lo, None, True, False), w, None, stride=2, padding=(0, 1, 1))
+        else:
+            lo, hi = self.halo(x, True, True) if self.world > 1 else (None, None)
+            if self._k13(x, u.conv):
+                y, stats = self._conv_k13(x, u.conv, lo, hi, True)
+            else:
+                y = F.conv3d(self._padded(x, lo, hi, True, True), w, None, stride=1, padding=(0, 1, 1))
+        return self.norm_relu_(y, stats, skip)
+
+    def out(self, x: torch.Tensor, conv: nn.Conv3d) -> torch.Tensor:
+        lo, hi = self.halo(x, True, True) if self.world > 1 else (None, None)
+        if self._k13(x, conv):
+            return self._conv_k13(x, conv, lo, hi, False)[0]
+        return F.conv3d(self._padded(x, lo, hi, True, True), conv.weight, conv.bias, stride=1, padding=(0, 1, 1))
+
+
+class RegNetwork(nn.Module):
+    """Same constructor, parameter names and forward as the reference's RegNetwork (reg_network.py:105-166)."""
+
+    def __init__(self, conf=None, d_voluem: Optional[Sequence[int]] = None, d_base: int = 8,
+                 d_out: Optional[Sequence[int]] = None):
+        super().__init__()
+        d_voluem = list(conf.get_list("d_voluem")) if conf is not None else list(d_voluem or [8] * 5)
+        d_base = conf.get_int("d_base") if conf is not None else d_base
+        d_out = list(conf.get_list("d_out")) if conf is not None else list(d_out or [4] * 5)
+        self.num_stage = n = len(d_out)
+        width = [d_base * 2 ** i for i in range(n)]          # encoder stage i
+        below = [d_base * 2 ** max(i - 1, 0) for i in range(n)]  # what decoder stage i returns to
+        self.conv0 = _Unit(d_voluem[0], d_base)
+        enc, dec, outs = [], [], []
+        c_in = d_base
+        for i in range(n):
+            enc.append(nn.Sequential(_Unit(c_in, width[i], stride=2), _Unit(width[i], width[i])))
+            if i + 1 < n:
+                c_in = width[i] + d_voluem[i + 1]
+            outs.append(nn.Conv3d(below[i], d_out[i], 3, 1, 1))
+            dec.append(_Unit(width[i], below[i], stride=2, transposed=True))
+        self.encoder_layers, self.decoder_layers, self.out_layers = nn.ModuleList(enc), nn.ModuleList(dec), nn.ModuleList(outs)
+
+    def _run(self, volumes: Sequence[torch.Tensor], ops) -> List[torch.Tensor]:
+        n = self.num_stage
+        if len(volumes) != n:
+            raise ValueError(f"RegNetwork: expected {n} volumes, got {len(volumes)}")
+        e = ops.unit(volumes[0], self.conv0)
+        skips = [e]
+        for i, stage in enumerate(self.encoder_layers):
+            e = ops.unit(ops.unit(e, stage[0]), stage[1])
+            skips.append(e)
+            if i + 1 < n:
+                e = torch.cat([e, volumes[i + 1]], dim=1)
+        fine = [None] * n
+        d = e
+        for i in range(n - 1, -1, -1):
+            d = ops.unit(d, self.decoder_layers[i], skips[i])
+            fine[i] = d
+        return [ops.out(fine[i], self.out_layers[i]) for i in range(n)]
+
+    def forward(self, volumes: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        """As the reference's forward.  With autograd enabled (training) or on host tensors: the reference's own op
+        sequence (cuDNN / ATen), bit-identical to it on the CPU; under no_grad on CUDA: the K13 path of `_Ops`."""
+        if volumes[0].is_cuda and not torch.is_grad_enabled():
+            return self._run(volumes, _Ops())
+        return self._run(volumes, _LocalOps)
+
+    @torch.no_grad()
+    def forward_slabs(self, slabs: Sequence[torch.Tensor], rank: int, world: int, group=None) -> List[torch.Tensor]:
+        """`slabs[i]` = planes [r D_i/P, (r+1) D_i/P) of volume i (tensor dim 2) -> the same planes of every output.
+        Needs D_i / 2 divisible by P at every scale (so that each stride-2 stage maps slabs onto slabs)."""
+        if world == 1:
+            return self._run(slabs, _Ops())
+        for v in slabs:  # every input scale feeds a stride-2 stage: its slab must hold an even number of planes
+            planes, full = v.shape[2], v.shape[3]
+            if planes * world != full or planes % 2:
+                raise RuntimeError(f"slab-parallel RegNetwork: a {full}^3 volume cannot be cut into {world} slabs "
+                                   "with an even number of planes each")
+        return self._run(slabs, _Ops(rank, world, group))

@@ -365,6 +365,21 @@ int gens_lncc_fwd(const float *ref, const float *src, int n_rays, int n_src, int
 int gens_lncc_bwd(const float *ref, const float *src, const float *g_score, const int *picked, int n_rays,
                   int n_src, int n_samples, int channels, float *g_ref, float *g_src, void *stream);
 
+/* ---- K13: 3x3x3 convolution with few channels + InstanceNorm, for the regulariser that consumes K1's volumes ----
+ * The stride-1 layers of RegNetwork (reference models/modules/reg_network.py:7-27 Conv3d block, :105-166 network) at
+ * the fine scales, where cuDNN's generic Nd kernel and ATen's batch-norm kernels take 98 of 112 ms (csrc/conv3d.cu).
+ * x (c_in, d, h, w) fp32 NCDHW of one sample, possibly an x-slab of d planes: lo_plane / hi_plane (c_in, h, w) are the
+ * planes just below / above the slab (NULL = zero padding).  w_packed = the torch weight (c_out, c_in, 3, 3, 3)
+ * permuted to [c_in][kh][kw][kd][c_out]; bias (c_out) or NULL.  c_in % 8 == 0, c_out in {4, 8, 16}.
+ * y (c_out, d, h, w).  stats (2 * c_out doubles, zeroed by the caller) or NULL: += per-channel sum and sum of squares of
+ * y (the InstanceNorm moments; a slab-parallel caller all-reduces them). */
+int gens_conv3d_k3(const float *x, const float *lo_plane, const float *hi_plane, const float *w_packed,
+                   const float *bias, int c_in, int c_out, int d, int h, int w, float *y, double *stats, void *stream);
+/* x (channels, per_channel) <- relu((x - mean_c) * rstd_c) [+ skip], mean / var from stats = [sum | sum of squares]
+ * over `count` values per channel (InstanceNorm3d without affine, biased variance, reg_network.py:16). */
+int gens_instnorm_relu(float *x, const double *stats, int channels, long long per_channel, double count, float eps,
+                       const float *skip, void *stream);
+
 /* ---- K12: marching cubes on the device-resident lattice ------------------------------------------
  * Replaces `mcubes.marching_cubes(u, threshold)` at the end of extract_geometry (reference models/modules/
  * implicit_surface.py:423; PyMCubes 0.1.4).  u (rx,ry,rz) fp32, x = slowest axis.  Corner / edge numbering and the

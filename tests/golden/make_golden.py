@@ -341,8 +341,29 @@ def golden_train():
           "volumes", [float(v.grad.norm()) for v in vols], "features", [float(f.grad.norm()) for f in feats if f.grad is not None])
 
 
+def golden_reg_network():
+    """reg_network.npz: outputs of the UNMODIFIED reference RegNetwork (models/modules/reg_network.py:105-166) on the
+    seeded volumes / parameters of tests/test_reg_network_cpu.py (its seeded_state / seeded_volumes rules, which do not
+    depend on construction order): strided samples of every output + its sum."""
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from test_reg_network_cpu import DIMS, seeded_state, seeded_volumes
+    mod = load_ref_module("models/modules/reg_network.py", "_golden_reg_network")
+    net = mod.RegNetwork(Conf({"d_voluem": [8] * 5, "d_out": [4] * 5, "d_base": 8}))
+    net.load_state_dict(seeded_state(net))
+    with torch.no_grad():
+        outs = net(seeded_volumes(DIMS))
+    stride = [4, 2, 1, 1, 1]
+    rec = {"stride": np.array(stride), "sum": np.array([float(o.double().sum()) for o in outs])}
+    for i, o in enumerate(outs):
+        rec[f"out{i}"] = o[0, :, ::stride[i], ::stride[i], ::stride[i]].numpy()
+    np.savez_compressed(os.path.join(HERE, "reg_network.npz"), **rec)
+    print("reg_network.npz:", {k: v.shape for k, v in rec.items()})
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["volume", "render"]
+    if "reg_network" in which:
+        golden_reg_network()
     if "train" in which:
         golden_train()
     if "render_big" in which:

@@ -1,0 +1,120 @@
+"""K13 (csrc/conv3d.cu) and the CUDA path of the volume regulariser (gens_b200/reg_network.py)."""
+import copy
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+def _k13(x, w, bias=None, lo=None, hi=None, stats=True):
+    from gens_b200 import _lib
+    c_out, c_in = w.shape[:2]
+    _, _, d, h, wd = x.shape
+    pk = w.permute(1, 3, 4, 2, 0).contiguous()
+    y = torch.full((1, c_out, d, h, wd), float("nan"), device=DEV)
+    st = torch.zeros(2 * c_out, device=DEV, dtype=torch.float64)
+    null = ctypes.c_void_p(0)
+    _lib.check(_lib.lib().gens_conv3d_k3(
+        _lib.ptr(x), _lib.ptr(lo) if lo is not None else null, _lib.ptr(hi) if hi is not None else null, _lib.ptr(pk),
+        _lib.ptr(bias) if bias is not None else null, c_in, c_out, d, h, wd, _lib.ptr(y),
+        _lib.ptr(st) if stats else null, _lib.stream_ptr(DEV)), "gens_conv3d_k3")
+    torch.cuda.synchronize()
+    return y, st
+
+
+@pytest.mark.parametrize("c_in,c_out,shape,bias", [
+    (8, 8, (16, 24, 64), False), (16, 16, (8, 16, 32), False), (8, 4, (12, 16, 96), True), (32, 4, (4, 8, 32), True),
+    (8, 8, (6, 12, 40), False), (8, 16, (5, 9, 33), True), (16, 8, (1, 1, 1), False)])
+def test_k13_conv_matches_float64_convolution(cuda_lib, c_in, c_out, shape, bias):
+    """Whole-volume case incl. partial tiles (sizes that are no multiple of the 4 x 8 x 32 tile), bias, moments."""
+    g = torch.Generator().manual_seed(c_in * 100 + c_out)
+    x = torch.randn(1, c_in, *shape, generator=g).to(DEV)
+    w = (torch.randn(c_out, c_in, 3, 3, 3, generator=g) / (27 * c_in) ** 0.5).to(DEV)
+    b = torch.randn(c_out, generator=g).to(DEV) if bias else None
+    want = F.conv3d(x.double(), w.double(), b.double() if bias else None, padding=1)
+    got, st = _k13(x, w, b)
+    assert not torch.isnan(got).any()
+    assert torch.all((got.double() - want).abs() <= 1e-6 * want.abs().max() + 1e-5 * want.abs())
+    sums = torch.cat([want.sum(dim=(0, 2, 3, 4)), (want * want).sum(dim=(0, 2, 3, 4))])
+    assert torch.all((st - sums).abs() <= 1e-5 * sums.abs() + 1e-4 * want[0, 0].numel() ** 0.5)
+    # without the moment buffer
+    got2, _ = _k13(x, w, b, stats=False)
+    assert torch.equal(got, got2)
+
+
+def test_k13_conv_on_a_slab_reads_its_halo_planes(cuda_lib):
+    g = torch.Generator().manual_seed(5)
+    full = torch.randn(1, 8, 24, 16, 64, generator=g).to(DEV)
+    w = (torch.randn(8, 8, 3, 3, 3, generator=g) / 15).to(DEV)
+    want = F.conv3d(full.double(), w.double(), None, padding=1)
+    for a0, a1 in ((0, 8), (8, 16), (16, 24), (4, 7)):
+        lo = full[0, :, a0 - 1].contiguous() if a0 > 0 else None
+        hi = full[0, :, a1].contiguous() if a1 < 24 else None
+        got, _ = _k13(full[:, :, a0:a1].contiguous(), w, None, lo, hi)
+        ref = want[:, :, a0:a1]
+        assert torch.all((got.double() - ref).abs() <= 1e-6 * ref.abs().max() + 1e-5 * ref.abs()), (a0, a1)
+    # an interior slab WITHOUT its halo planes must differ (the planes are really read)
+    got, _ = _k13(full[:, :, 8:16].contiguous(), w)
+    assert not torch.allclose(got.double()[:, :, 0], want[:, :, 8], atol=1e-4)
+
+
+def test_instnorm_relu_kernel(cuda_lib):
+    from gens_b200 import _lib
+    g = torch.Generator().manual_seed(9)
+    x = (torch.randn(1, 8, 8, 16, 32, generator=g) * 3 + 1).to(DEV)
+    skip = torch.randn(1, 8, 8, 16, 32, generator=g).to(DEV)
+    want = F.relu(F.instance_norm(x.double(), eps=1e-5)) + skip.double()
+    st = torch.cat([x.double().sum(dim=(0, 2, 3, 4)), (x.double() ** 2).sum(dim=(0, 2, 3, 4))])
+    y = x.clone()
+    n = x[0, 0].numel()
+    _lib.check(_lib.lib().gens_instnorm_relu(_lib.ptr(y), _lib.ptr(st), 8, n, float(n), 1e-5, _lib.ptr(skip),
+                                             _lib.stream_ptr(DEV)), "gens_instnorm_relu")
+    torch.cuda.synchronize()
+    assert torch.all((y.double() - want).abs() <= 1e-6 + 1e-5 * want.abs())
+
+
+def _err(outs, ref64):
+    return max(float(((a.double() - b).abs() / (1e-5 * b.abs().max() + 1e-4 * b.abs())).max()) for a, b in zip(outs, ref64))
+
+
+def test_regulariser_cuda_path_is_as_accurate_as_the_library_path(cuda_lib):
+    """RegNetwork.forward under no_grad on CUDA (K13 + in-place norm) against a float64 evaluation of the same network,
+    next to the reference's own op sequence in fp32 (cuDNN + ATen instance_norm, what forward runs with autograd on);
+    and, when the staged reference is present, against the reference module itself."""
+    from gens_b200.reg_network import RegNetwork
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(2)
+        net = RegNetwork().to(DEV).eval()
+        dims = [128, 64, 32, 16, 8]
+        vols = [torch.randn(1, 8, d, d, d, device=DEV) for d in dims]
+        with torch.no_grad():
+            ours = net(vols)
+            ref64 = copy.deepcopy(net).double()([v.double() for v in vols])
+        lib_path = net(vols)  # autograd enabled: the library op sequence
+        assert lib_path[0].requires_grad and not ours[0].requires_grad
+        e_ours, e_lib = _err(ours, ref64), _err([o.detach() for o in lib_path], ref64)
+        print(f"error vs float64 in units of (1e-5 max + 1e-4 |ref|): K13 path {e_ours:.3f}, library path {e_lib:.3f}")
+        assert e_ours <= max(1.0, 1.5 * e_lib)
+        import os, sys
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        path = os.path.join(root, "baseline", "_ref", "GenS", "models", "modules", "reg_network.py")
+        if os.path.exists(path):
+            import importlib.util
+            from gens_b200.config import gens_model_conf
+            spec = importlib.util.spec_from_file_location("_ref_reg_network_gpu", path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            ref = mod.RegNetwork(gens_model_conf()["reg_network"]).to(DEV).eval()
+            ref.load_state_dict(net.state_dict())
+            with torch.no_grad():
+                e_ref = _err(ref(vols), ref64)
+            print(f"the unmodified reference module on this GPU: {e_ref:.3f}")
+            assert e_ours <= max(1.0, 1.5 * e_ref)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old

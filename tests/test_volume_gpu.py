@@ -262,6 +262,24 @@ def test_fused_slab_exchange_two_gpus():
     assert r.stdout.count("bit-identical to the 1-GPU build: True") == 2, r.stdout[-2000:]
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs of one node")
+def test_slab_regulariser_handoff_two_gpus():
+    """K1 slabs -> slab-parallel RegNetwork -> gather of the 4-channel results, on 2 ranks at the config-2
+    sizes, against the whole-volume pipeline on every rank (bench.py's `regularise` leg carries the check)."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", "bench.py", "--gpus", "2", "--steps", "2",
+                        "--warmup", "3", "--no-render", "--no-lattice", "--no-train", "--no-cpu"],
+                       cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    reg = line["regularise"]
+    assert reg["verified"]["as_accurate_as_the_whole_volume_pipeline"] is True, reg
+    assert line["verified"]["slabs_bit_identical"] is True
+    assert reg["gathered_bytes_per_gpu"] * 9 == reg["gathered_bytes_if_volumes_were_exchanged_first"] * 5
+
+
 def _k1_variant(variant, feat_d, nv, h, w, w2c_d, k_d, grid_d, d, a0=0, a1=None, min_vis_view=1, const_cams=False):
     """One K1 launch under a tuning variant; const_cams stages the cameras in the constant bank first."""
     from gens_b200.volume import agg_scale_into, stage_camera_slots
