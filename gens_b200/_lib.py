@@ -127,11 +127,14 @@ _SIGNATURES = {
     "gens_mc_triangles": ([_vp, _i, _i, _i, _f, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _i, ctypes.c_char_p, _ll,
                            _vp, _vp], _i),
     "gens_conv3d_k3": ([_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp], _i),
+    "gens_conv3d_k3s2": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp], _i),
+    "gens_deconv3d_k3s2": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp], _i),
     "gens_instnorm_relu": ([_vp, _vp, _i, _ll, ctypes.c_double, _f, _vp, _vp], _i),
     "gens_tv_reduce": ([_PP, _PP, _i, _i, _vp, _vp], _i),
     "gens_debug_set_variant": ([_i], _i),
     "gens_debug_set_tc_terms": ([_i], _i),
     "gens_debug_blend_const": ([_i], _i),
+    "gens_debug_conv_td8": ([_i], _i),
     "gens_debug_tc_profile": ([_vp, _i], _i),
     "gens_tf32_mma_peak": ([_i, _vp, _vp], _i),
     "gens_selftest_division": ([_i, ctypes.c_ulonglong, _vp, _vp], _i),

@@ -157,19 +157,54 @@ class _Ops:
         y = y.sub_(g_mean.float().view(shape)).mul_(rstd.float().view(shape)).relu_()
         return y.add_(skip) if skip is not None else y
 
+    def _strided_k13(self, x, u: _Unit) -> bool:
+        w = u.conv.weight
+        if not (x.is_cuda and x.dtype == torch.float32 and x.shape[0] == 1):
+            return False
+        if u.transposed:   # weight (c_in, c_out, 3, 3, 3)
+            return w.shape[1] == 8 and w.shape[0] * 27 * 8 * 4 <= 96 * 1024
+        return w.shape[0] in (8, 16) and w.shape[1] * 27 * w.shape[0] * 4 <= 96 * 1024 and \
+            all(n % 2 == 0 for n in x.shape[2:])
+
+    def _conv_strided_k13(self, x, u: _Unit, halo):
+        from . import _lib
+        w = u.conv.weight
+        key = (w.data_ptr(), w._version)
+        pk = self._packed.get(key)
+        if pk is None:  # transposed: (c_in, c_out, kd, kh, kw) -> [c_in][kd][kh][kw][c_out]; else as the stride-1 layers
+            pk = w.detach().permute(0, 2, 3, 4, 1) if u.transposed else w.detach().permute(1, 3, 4, 2, 0)
+            pk = self._packed[key] = pk.contiguous().float()
+        x = _lib.f32c(x)
+        _, c_in, d, h, wd = x.shape
+        c_out = w.shape[1] if u.transposed else w.shape[0]
+        shape = (2 * d, 2 * h, 2 * wd) if u.transposed else (d // 2, h // 2, wd // 2)
+        y = torch.empty((1, c_out) + shape, device=x.device, dtype=torch.float32)
+        stats = torch.zeros(2 * c_out, device=x.device, dtype=torch.float64)
+        fn = _lib.lib().gens_deconv3d_k3s2 if u.transposed else _lib.lib().gens_conv3d_k3s2
+        _lib.check(fn(_lib.ptr(x), _lib.ptr(halo.contiguous()) if halo is not None else ctypes.c_void_p(0), _lib.ptr(pk),
+                      c_in, c_out, d, h, wd, _lib.ptr(y), _lib.ptr(stats), _lib.stream_ptr(x.device)),
+                   "gens_deconv3d_k3s2" if u.transposed else "gens_conv3d_k3s2")
+        return y, stats
+
     def unit(self, x: torch.Tensor, u: _Unit, skip: Optional[torch.Tensor] = None) -> torch.Tensor:
         d = x.shape[2]
         w = u.conv.weight
         stats = None
         if u.transposed:                            # out plane 2i <- in i; out 2i+1 <- in i and i+1: upper halo only
             lo, hi = self.halo(x, False, True) if self.world > 1 else (None, None)
-            y = F.conv_transpose3d(self._padded(x, None, hi, False, self.world > 1), w, None, stride=2, padding=1,
-                                   output_padding=1)[:, :, : 2 * d].contiguous()
+            if self._strided_k13(x, u):
+                y, stats = self._conv_strided_k13(x, u, hi)
+            else:
+                y = F.conv_transpose3d(self._padded(x, None, hi, False, self.world > 1), w, None, stride=2, padding=1,
+                                       output_padding=1)[:, :, : 2 * d].contiguous()
         elif u.stride == 2:                         # out plane o <- in 2o-1, 2o, 2o+1: lower halo only
             if d % 2:
                 raise RuntimeError("slab-parallel RegNetwork: a stride-2 stage met a slab with an odd plane count")
             lo, hi = self.halo(x, True, False) if self.world > 1 else (None, None)
-            y = F.conv3d(self._padded(x, lo, None, True, False), w, None, stride=2, padding=(0, 1, 1))
+            if self._strided_k13(x, u):
+                y, stats = self._conv_strided_k13(x, u, lo)
+            else:
+                y = F.conv3d(self._padded(x, lo, None, True, False), w, None, stride=2, padding=(0, 1, 1))
         else:
             lo, hi = self.halo(x, True, True) if self.world > 1 else (None, None)
             if self._k13(x, u.conv):

@@ -370,11 +370,20 @@ int gens_lncc_bwd(const float *ref, const float *src, const float *g_score, cons
  * the fine scales, where cuDNN's generic Nd kernel and ATen's batch-norm kernels take 98 of 112 ms (csrc/conv3d.cu).
  * x (c_in, d, h, w) fp32 NCDHW of one sample, possibly an x-slab of d planes: lo_plane / hi_plane (c_in, h, w) are the
  * planes just below / above the slab (NULL = zero padding).  w_packed = the torch weight (c_out, c_in, 3, 3, 3)
- * permuted to [c_in][kh][kw][kd][c_out]; bias (c_out) or NULL.  c_in % 8 == 0, c_out in {4, 8, 16}.
+ * permuted to [c_in][kh][kw][kd][c_out]; bias (c_out) or NULL.  c_in % 4 == 0, c_out in {4, 8, 16}.
  * y (c_out, d, h, w).  stats (2 * c_out doubles, zeroed by the caller) or NULL: += per-channel sum and sum of squares of
  * y (the InstanceNorm moments; a slab-parallel caller all-reduces them). */
 int gens_conv3d_k3(const float *x, const float *lo_plane, const float *hi_plane, const float *w_packed,
                    const float *bias, int c_in, int c_out, int d, int h, int w, float *y, double *stats, void *stream);
+/* The same convolution with stride 2 (first layer of every encoder stage): x (c_in, d, h, w) with d, h, w even ->
+ * y (c_out, d/2, h/2, w/2); only the plane BELOW an x-slab is needed.  c_out in {8, 16}; all weights must fit 96 KB. */
+int gens_conv3d_k3s2(const float *x, const float *lo_plane, const float *w_packed, int c_in, int c_out, int d, int h,
+                     int w, float *y, double *stats, void *stream);
+/* ConvTranspose3d(kernel 3, stride 2, padding 1, output_padding 1) (reg_network.py:30-50, every decoder stage):
+ * x (c_in, d, h, w) -> y (c_out, 2d, 2h, 2w); only the plane ABOVE an x-slab is needed.  w_packed = the torch weight
+ * (c_in, c_out, 3, 3, 3) permuted to [c_in][kd][kh][kw][c_out]; c_out = 8. */
+int gens_deconv3d_k3s2(const float *x, const float *hi_plane, const float *w_packed, int c_in, int c_out, int d, int h,
+                       int w, float *y, double *stats, void *stream);
 /* x (channels, per_channel) <- relu((x - mean_c) * rstd_c) [+ skip], mean / var from stats = [sum | sum of squares]
  * over `count` values per channel (InstanceNorm3d without affine, biased variance, reg_network.py:16). */
 int gens_instnorm_relu(float *x, const double *stats, int channels, long long per_channel, double count, float eps,
@@ -401,6 +410,8 @@ int gens_mc_triangles(const float *u, int rx, int ry, int rz, float iso, const l
                       const uint8_t *vmask, const uint8_t *tri_count, const int8_t *tri_edges, int max_tris,
                       const int8_t *edge_owner, long long vert_offset, long long *tris, void *stream);
 
+/* Measurement knob of K13: 8-voxel columns per thread for c_out = 8 too (default: 4). */
+int gens_debug_conv_td8(int on);
 /* Tuning knob of K10: 1 = blending weights read from the constant bank, 0 = from shared memory (shipped default: see
  * csrc/blend.cu). */
 int gens_debug_blend_const(int on);

@@ -62,6 +62,60 @@ def test_k13_conv_on_a_slab_reads_its_halo_planes(cuda_lib):
     assert not torch.allclose(got.double()[:, :, 0], want[:, :, 8], atol=1e-4)
 
 
+def _strided(x, w, transposed, halo=None):
+    from gens_b200 import _lib
+    _, c_in, d, h, wd = x.shape
+    if transposed:
+        c_out, pk, shape = w.shape[1], w.permute(0, 2, 3, 4, 1).contiguous(), (2 * d, 2 * h, 2 * wd)
+        fn = _lib.lib().gens_deconv3d_k3s2
+    else:
+        c_out, pk, shape = w.shape[0], w.permute(1, 3, 4, 2, 0).contiguous(), (d // 2, h // 2, wd // 2)
+        fn = _lib.lib().gens_conv3d_k3s2
+    y = torch.full((1, c_out) + shape, float("nan"), device=DEV)
+    st = torch.zeros(2 * c_out, device=DEV, dtype=torch.float64)
+    _lib.check(fn(_lib.ptr(x), _lib.ptr(halo) if halo is not None else ctypes.c_void_p(0), _lib.ptr(pk), c_in, c_out, d, h,
+                  wd, _lib.ptr(y), _lib.ptr(st), _lib.stream_ptr(DEV)), "strided K13")
+    torch.cuda.synchronize()
+    return y, st
+
+
+@pytest.mark.parametrize("transposed,c_in,c_out,shape", [
+    (False, 8, 8, (16, 24, 64)), (False, 16, 16, (8, 16, 32)), (False, 24, 8, (4, 6, 10)), (False, 8, 8, (2, 2, 2)),
+    (True, 8, 8, (8, 12, 32)), (True, 16, 8, (4, 8, 16)), (True, 8, 8, (3, 5, 7)), (True, 32, 8, (1, 1, 1))])
+def test_k13_strided_and_transposed_match_float64(cuda_lib, transposed, c_in, c_out, shape):
+    g = torch.Generator().manual_seed(c_in * 7 + c_out + int(transposed))
+    x = torch.randn(1, c_in, *shape, generator=g).to(DEV)
+    if transposed:
+        w = (torch.randn(c_in, c_out, 3, 3, 3, generator=g) / (8 * c_in) ** 0.5).to(DEV)
+        want = F.conv_transpose3d(x.double(), w.double(), None, stride=2, padding=1, output_padding=1)
+    else:
+        w = (torch.randn(c_out, c_in, 3, 3, 3, generator=g) / (27 * c_in) ** 0.5).to(DEV)
+        want = F.conv3d(x.double(), w.double(), None, stride=2, padding=1)
+    got, st = _strided(x, w, transposed)
+    assert got.shape == want.shape and not torch.isnan(got).any()
+    assert torch.all((got.double() - want).abs() <= 1e-6 * want.abs().max() + 1e-5 * want.abs())
+    sums = torch.cat([want.sum(dim=(0, 2, 3, 4)), (want * want).sum(dim=(0, 2, 3, 4))])
+    assert torch.all((st - sums).abs() <= 1e-5 * sums.abs() + 1e-4 * want[0, 0].numel() ** 0.5)
+
+
+def test_k13_strided_and_transposed_on_slabs(cuda_lib):
+    g = torch.Generator().manual_seed(6)
+    full = torch.randn(1, 8, 16, 12, 32, generator=g).to(DEV)
+    w = (torch.randn(8, 8, 3, 3, 3, generator=g) / 15).to(DEV)
+    down = F.conv3d(full.double(), w.double(), None, stride=2, padding=1)
+    up = F.conv_transpose3d(full.double(), w.double(), None, stride=2, padding=1, output_padding=1)
+    for a0, a1 in ((0, 8), (8, 16), (4, 10)):
+        slab = full[:, :, a0:a1].contiguous()
+        lo = full[0, :, a0 - 1].contiguous() if a0 > 0 else None
+        hi = full[0, :, a1].contiguous() if a1 < 16 else None
+        got, _ = _strided(slab, w, False, lo)
+        ref = down[:, :, a0 // 2: a1 // 2]
+        assert torch.all((got.double() - ref).abs() <= 1e-6 * ref.abs().max() + 1e-5 * ref.abs()), ("down", a0, a1)
+        got, _ = _strided(slab, w, True, hi)
+        ref = up[:, :, 2 * a0: 2 * a1]
+        assert torch.all((got.double() - ref).abs() <= 1e-6 * ref.abs().max() + 1e-5 * ref.abs()), ("up", a0, a1)
+
+
 def test_instnorm_relu_kernel(cuda_lib):
     from gens_b200 import _lib
     g = torch.Generator().manual_seed(9)

@@ -36,6 +36,10 @@ with torch.no_grad():
         st = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
         null = ctypes.c_void_p(0)
         f = lambda: _lib.lib().gens_conv3d_k3(_lib.ptr(xx), null, null, _lib.ptr(ww), null, cin, cout, 256, 256, 256, _lib.ptr(yy), _lib.ptr(st), _lib.stream_ptr(dev))
+        if cout == 8:
+            _lib.lib().gens_debug_conv_td8(1)
+            print(f"K13 conv 8->8 with 8-voxel columns: {t(f, 5):.3f} ms")
+            _lib.lib().gens_debug_conv_td8(0)
         ms = t(f, 5)
         print(f"K13 conv {cin}->{cout} @256^3: {ms:.3f} ms = {2 * 27 * cin * cout * 256 ** 3 / ms / 1e9:.1f} TFLOP/s fp32, {(cin + cout) * 256 ** 3 * 4 / ms / 1e6:.0f} GB/s algorithmic")
         del xx, yy
