@@ -773,8 +773,9 @@ def bench_regularise(args, rank, world, dev, sc, vol_mod, timed):
     """SURVEY 8f-4, the hand-off to the volume regulariser: the volume side of GenS.forward (models/gens.py:143-145:
     agg_mean_var -> reg_network) from feature maps to the (1,4,D,D,D) volumes + masks the ray marcher samples, present
     on every rank.  N = 1: K1 + the whole-volume network.  N > 1: parallel.sharded_build_and_regularise -- K1 slabs stay
-    on their rank, the network runs slab-parallel (halo planes + all-reduced InstanceNorm moments), only the 4-channel
-    results and the masks are gathered; checked on every rank against the local whole-volume pipeline.
+    on their rank, the network runs slab-parallel (halo planes + InstanceNorm moments of all ranks; NCCL messages, or
+    NVLink peer memory + CUDA graph: reg_network.PeerSlabRegulariser), only the 4-channel results and the masks are
+    gathered; checked on every rank against a float64 evaluation next to the local whole-volume pipeline.
     Stride-1 layers at the fine scales and all InstanceNorms: K13 (csrc/conv3d.cu); stride-2 / transposed / deep layers:
     cuDNN fp32 (library), TF32 off so that every arm is plain fp32.  N = 1 also times the reference's own network
     (baseline/_ref when staged, else the same op sequence: cuDNN + ATen instance_norm) on K1's volumes."""
@@ -836,6 +837,16 @@ def bench_regularise(args, rank, world, dev, sc, vol_mod, timed):
             del v32, ref64, ref_net
         if world > 1:
             ms_sh, _ = timed(sharded, 3, 2)
+            ms_graph = None
+            try:  # the same pipeline with every exchange through NVLink peer memory, replayed as one CUDA graph per rank
+                from gens_b200.reg_network import PeerSlabRegulariser
+                graphed = PeerSlabRegulariser(net, DIMS, rank, world, dev)
+                run_graphed = lambda: parallel.sharded_build_and_regularise(vol_mod, net, sc.features, sc.intrs, sc.c2ws,
+                                                                            rank, world, graphed=graphed)
+                ms_graph, _ = timed(run_graphed, 5, 3)
+            except Exception as exc:  # noqa: BLE001
+                sys.stderr.write(f"bench.py: peer-memory slab regulariser failed on rank {rank}: {exc}\n")
+                graphed = None
             # Whole volumes and slabs go through different cuDNN algorithms, so the two fp32 results differ by rounding
             # that 17 convolution + InstanceNorm layers amplify.  Judge both against the SAME network evaluated in
             # float64 on K1's (bit-identical) volumes: the slab pipeline must be as close to it as the whole-volume one.
@@ -850,12 +861,31 @@ def bench_regularise(args, rank, world, dev, sc, vol_mod, timed):
                     return max(float(((a.double() - b).abs() / (1e-5 * b.abs().max() + 1e-4 * b.abs())).max())
                                for a, b in zip(outs, ref64))
                 err_whole, err_slab = err(wv), err(sv)
+                graph_ok, err_graph, graph_vs_eager = None, None, None
+                if ms_graph is not None:  # the replayed graph's outputs, judged like the eager slab pipeline's
+                    gv, gm = run_graphed()
+                    torch.cuda.synchronize(dev)
+                    err_graph = err(gv)
+                    graph_vs_eager = max(float((a - b).abs().max() / b.abs().max()) for a, b in zip(gv, sv))
+                    graph_ok = all(torch.equal(a, b) for a, b in zip(gm, sm)) and err_graph <= max(1.0, 1.5 * err_whole)
+                    del gv, gm
                 direct = max(float(((a - b).abs() / (1e-5 * b.abs().max() + 1e-4 * b.abs())).max()) for a, b in zip(sv, wv))
                 same_masks = all(torch.equal(a, b) for a, b in zip(sm, wm))
                 ok = same_masks and err_slab <= max(1.0, 1.5 * err_whole) and direct <= 10.0
                 del wv, wm, sv, sm, v32, ref64
             gathered = sum(5 * d ** 3 * 4 for d in DIMS) * (world - 1) // world
-            out.update({"value": voxel_views(sc.intrs.shape[0]) / (ms_sh * 1e-3), "ms_per_step": ms_sh,
+            if graph_ok is not None:
+                graph_ok = all_ranks_true(graph_ok, world, dev)
+            best = ms_graph if (ms_graph is not None and graph_ok and ms_graph < ms_sh) else ms_sh
+            out.update({"value": voxel_views(sc.intrs.shape[0]) / (best * 1e-3), "ms_per_step": best,
+                        "nccl_eager_ms": ms_sh, "peer_memory_ms": ms_graph,
+                        "peer_memory": None if ms_graph is None else {
+                            "cuda_graph": graphed.graph is not None,
+                            "as_accurate_as_the_whole_volume_pipeline": graph_ok, "error_vs_float64": err_graph,
+                            "max_abs_diff_vs_eager_over_max": graph_vs_eager,
+                            "note": "layer outputs in a symmetric arena: halo planes and InstanceNorm moments are read from the "
+                                    "neighbours' memory over NVLink, one device barrier per step, results pulled from the "
+                                    "peers; no NCCL call.  Moments are summed with atomics: runs may differ in the last bits"},
                         "sharding": f"x-slabs over {world} ranks end to end: K1 slab -> slab-parallel U-Net (one halo plane "
                                     "per layer and side, InstanceNorm moments all-reduced) -> gather of 4 + 1 channels",
                         "gathered_bytes_per_gpu": gathered,

@@ -194,16 +194,23 @@ def gather_slab_volumes(slabs: Sequence[torch.Tensor], rank: int, world: int, gr
 
 @torch.no_grad()
 def sharded_build_and_regularise(volume_module, reg_network, features, intrs, c2ws, rank: int, world: int,
-                                 min_vis_view: int = 1, group=None):
+                                 min_vis_view: int = 1, group=None, graphed=None):
     """The volume side of GenS.forward / init_volumes (reference models/gens.py:68-70, :143-145) on P GPUs without
     ever assembling the 9-channel volumes: every rank builds its x-slabs (K1), the regulariser runs slab-parallel on
     them (gens_b200/reg_network.py: one halo plane per layer and side, InstanceNorm statistics all-reduced), and only
     the 4-channel results and the masks are gathered -- 384 MB instead of 690 MB per build for the config-2
     pyramid, and 1/P of the regulariser's work per GPU.  Returns (volumes, mask_volumes) as
-    `reg_network(volume.agg_mean_var(...)[0])`, `...[1]` would on one GPU, on every rank.  Inference only."""
+    `reg_network(volume.agg_mean_var(...)[0])`, `...[1]` would on one GPU, on every rank.  Inference only.
+    `graphed` = a reg_network.PeerSlabRegulariser built for this network and pyramid: halo planes, moments and
+    results travel through NVLink peer memory and the whole step replays as one CUDA graph (the returned tensors are then
+    its static outputs)."""
     from .volume import agg_mean_var
     dims = volume_module.volume_dims
     slabs = [slab_bounds(d, rank, world) for d in dims]
+    if graphed is not None:  # K1 writes into the graph's static inputs, one replay does the rest
+        agg_mean_var(features, intrs, c2ws, dims, min_vis_view, slabs, volume_module.div_mode,
+                     outs=list(zip(graphed.inputs, graphed.masks)))
+        return graphed()
     vols, masks = agg_mean_var(features, intrs, c2ws, dims, min_vis_view, slabs, volume_module.div_mode)
     reg = reg_network.forward_slabs(vols, rank, world, group)
     del vols

@@ -63,6 +63,10 @@ class _LocalOps:
     def out(x: torch.Tensor, conv: nn.Conv3d) -> torch.Tensor:
         return F.conv3d(x, conv.weight, conv.bias, stride=1, padding=1)
 
+    @staticmethod
+    def cat(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        return torch.cat([a, b], dim=1)
+
 
 class _Ops:
     """Inference ops on x-slabs (planes of tensor dim 2) of every tensor on `world` ranks; rank r owns planes
@@ -77,6 +81,27 @@ class _Ops:
 
     def _peer(self, r: int) -> int:
         return r if self.group is None else dist.get_global_rank(self.group, r)
+
+    # -- hooks the peer-memory variant overrides ----------------------------------------------------------------
+    def _new(self, shape, device) -> torch.Tensor:
+        """Storage of a layer's output."""
+        return torch.empty(shape, device=device, dtype=torch.float32)
+
+    def _own(self, y: torch.Tensor) -> torch.Tensor:
+        """A library-produced tensor as a layer output (the peer variant copies it to where neighbours can read it)."""
+        return y
+
+    def _combine(self, stats: torch.Tensor) -> torch.Tensor:
+        """The volume's moments from this rank's."""
+        if self.world > 1:
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.group)
+        return stats
+
+    def _publish(self) -> None:
+        """Called once a layer's output is final."""
+
+    def cat(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        return torch.cat([a, b], dim=1)
 
     def halo(self, x: torch.Tensor, lower: bool, upper: bool):
         """The neighbours' boundary planes: (plane below the slab or None, plane above or None); None at the
@@ -121,7 +146,7 @@ class _Ops:
         x = _lib.f32c(x)
         _, c_in, d, h, wd = x.shape
         c_out = w.shape[0]
-        y = torch.empty((1, c_out, d, h, wd), device=x.device, dtype=torch.float32)
+        y = self._new((1, c_out, d, h, wd), x.device)
         stats = torch.zeros(2 * c_out, device=x.device, dtype=torch.float64) if want_stats else None
         null = ctypes.c_void_p(0)
         _lib.check(_lib.lib().gens_conv3d_k3(
@@ -141,8 +166,7 @@ class _Ops:
             var, mean = torch.var_mean(y, dim=(0, 2, 3, 4), unbiased=False)
             mean, var = mean.double(), var.double()
             stats = torch.cat([mean, var + mean * mean]) * n_local
-        if self.world > 1:
-            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.group)
+        stats = self._combine(stats)
         count = float(n_local * self.world)
         if y.is_cuda and y.dtype == torch.float32 and y.is_contiguous() and n_local % 4 == 0 and \
                 (skip is None or (skip.is_contiguous() and skip.dtype == torch.float32)):
@@ -150,12 +174,15 @@ class _Ops:
             _lib.check(_lib.lib().gens_instnorm_relu(
                 _lib.ptr(y), _lib.ptr(stats), c, n_local, count, EPS,
                 _lib.ptr(skip) if skip is not None else ctypes.c_void_p(0), _lib.stream_ptr(y.device)), "gens_instnorm_relu")
+            self._publish()
             return y
         g_mean = stats[:c] / count
         rstd = torch.rsqrt((stats[c:] / count - g_mean * g_mean).clamp_min_(0.0) + EPS)
         shape = (1, -1, 1, 1, 1)
         y = y.sub_(g_mean.float().view(shape)).mul_(rstd.float().view(shape)).relu_()
-        return y.add_(skip) if skip is not None else y
+        y = y.add_(skip) if skip is not None else y
+        self._publish()
+        return y
 
     def _strided_k13(self, x, u: _Unit) -> bool:
         w = u.conv.weight
@@ -178,7 +205,7 @@ class _Ops:
         _, c_in, d, h, wd = x.shape
         c_out = w.shape[1] if u.transposed else w.shape[0]
         shape = (2 * d, 2 * h, 2 * wd) if u.transposed else (d // 2, h // 2, wd // 2)
-        y = torch.empty((1, c_out) + shape, device=x.device, dtype=torch.float32)
+        y = self._new((1, c_out) + shape, x.device)
         stats = torch.zeros(2 * c_out, device=x.device, dtype=torch.float64)
         fn = _lib.lib().gens_deconv3d_k3s2 if u.transposed else _lib.lib().gens_conv3d_k3s2
         _lib.check(fn(_lib.ptr(x), _lib.ptr(halo.contiguous()) if halo is not None else ctypes.c_void_p(0), _lib.ptr(pk),
@@ -195,8 +222,8 @@ class _Ops:
             if self._strided_k13(x, u):
                 y, stats = self._conv_strided_k13(x, u, hi)
             else:
-                y = F.conv_transpose3d(self._padded(x, None, hi, False, self.world > 1), w, None, stride=2, padding=1,
-                                       output_padding=1)[:, :, : 2 * d].contiguous()
+                y = self._own(F.conv_transpose3d(self._padded(x, None, hi, False, self.world > 1), w, None, stride=2,
+                                                 padding=1, output_padding=1)[:, :, : 2 * d].contiguous())
         elif u.stride == 2:                         # out plane o <- in 2o-1, 2o, 2o+1: lower halo only
             if d % 2:
                 raise RuntimeError("slab-parallel RegNetwork: a stride-2 stage met a slab with an odd plane count")
@@ -204,13 +231,13 @@ class _Ops:
             if self._strided_k13(x, u):
                 y, stats = self._conv_strided_k13(x, u, lo)
             else:
-                y = F.conv3d(self._padded(x, lo, None, True, False), w, None, stride=2, padding=(0, 1, 1))
+                y = self._own(F.conv3d(self._padded(x, lo, None, True, False), w, None, stride=2, padding=(0, 1, 1)))
         else:
             lo, hi = self.halo(x, True, True) if self.world > 1 else (None, None)
             if self._k13(x, u.conv):
                 y, stats = self._conv_k13(x, u.conv, lo, hi, True)
             else:
-                y = F.conv3d(self._padded(x, lo, hi, True, True), w, None, stride=1, padding=(0, 1, 1))
+                y = self._own(F.conv3d(self._padded(x, lo, hi, True, True), w, None, stride=1, padding=(0, 1, 1)))
         return self.norm_relu_(y, stats, skip)
 
     def out(self, x: torch.Tensor, conv: nn.Conv3d) -> torch.Tensor:
@@ -253,7 +280,7 @@ class RegNetwork(nn.Module):
             e = ops.unit(ops.unit(e, stage[0]), stage[1])
             skips.append(e)
             if i + 1 < n:
-                e = torch.cat([e, volumes[i + 1]], dim=1)
+                e = ops.cat(e, volumes[i + 1])
         fine = [None] * n
         d = e
         for i in range(n - 1, -1, -1):
@@ -280,3 +307,143 @@ class RegNetwork(nn.Module):
                 raise RuntimeError(f"slab-parallel RegNetwork: a {full}^3 volume cannot be cut into {world} slabs "
                                    "with an even number of planes each")
         return self._run(slabs, _Ops(rank, world, group))
+
+
+class _Arena:
+    """Bump allocator over ONE symmetric allocation (torch.distributed._symmetric_memory): every rank allocates the
+    same sequence, so a tensor lives at the same offset of every rank's buffer and `peer(r, t)` is rank r's copy of
+    `t`, readable over NVLink like local memory."""
+
+    def __init__(self, n_bytes: int, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.buf = symm_mem.empty(n_bytes // 4, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.base, self.used, self.size = self.buf.data_ptr(), 0, n_bytes
+
+    def alloc(self, shape, dtype=torch.float32) -> torch.Tensor:
+        n = 1
+        for v in shape:
+            n *= int(v)
+        item = torch.empty((), dtype=dtype).element_size()
+        off = (self.used + 255) // 256 * 256
+        if off + n * item > self.size:
+            raise RuntimeError("slab regulariser: symmetric arena exhausted")
+        self.used = off + n * item
+        return self.hdl.get_buffer(self.hdl.rank, tuple(int(v) for v in shape), dtype, off // item)
+
+    def peer(self, r: int, t: torch.Tensor) -> torch.Tensor:
+        """Rank r's copy of the (contiguous, arena-allocated) tensor or leading slice `t`."""
+        off = t.data_ptr() - self.base
+        assert 0 <= off < self.size and t.is_contiguous()
+        return self.hdl.get_buffer(r, tuple(t.shape), t.dtype, off // t.element_size())
+
+    def barrier(self):
+        self.hdl.barrier(channel=1)
+
+
+class _PeerOps(_Ops):
+    """The slab ops with every exchange done through peer memory instead of NCCL: layer outputs live in a symmetric
+    arena, a halo plane is the neighbour's tensor read in place over NVLink by the consuming kernel, the InstanceNorm
+    moments of all ranks are read from their arenas and summed locally, and one device-side barrier per step orders
+    producers and consumers.  No message, no copy, no host synchronisation: the whole forward is graph-capturable."""
+
+    def __init__(self, arena: _Arena, rank: int, world: int):
+        super().__init__(rank, world, None)
+        self.arena = arena
+
+    def _new(self, shape, device):
+        return self.arena.alloc(shape)
+
+    def _own(self, y):
+        out = self.arena.alloc(y.shape)
+        out.copy_(y)
+        return out
+
+    def cat(self, a, b):
+        out = self.arena.alloc((1, a.shape[1] + b.shape[1]) + tuple(a.shape[2:]))
+        torch.cat([a, b], dim=1, out=out)
+        self.arena.barrier()  # the concatenation is a layer input the neighbours read halos of
+        return out
+
+    def halo(self, x, lower: bool, upper: bool):
+        # x is final on every rank (barrier after the step that produced it); x[0, :, k] is not contiguous across
+        # channels, so the neighbour's WHOLE tensor is viewed and the plane sliced out of it
+        r, p = self.rank, self.world
+        lo = self.arena.peer(r - 1, x)[:, :, -1:] if lower and r > 0 else None
+        hi = self.arena.peer(r + 1, x)[:, :, :1] if upper and r + 1 < p else None
+        return lo, hi
+
+    def _combine(self, stats):
+        mine = self.arena.alloc(stats.shape, torch.float64)
+        mine.copy_(stats)
+        self.arena.barrier()  # every rank's moments are written (and everyone is done reading the input's halos)
+        total = self.arena.peer(0, mine).clone()
+        for r in range(1, self.world):
+            total += self.arena.peer(r, mine)
+        return total
+
+    def _publish(self):
+        self.arena.barrier()
+
+
+class PeerSlabRegulariser:
+    """K1's slabs -> slab-parallel RegNetwork -> full 4-channel volumes + masks on every rank, all exchanges through
+    NVLink peer memory (see _PeerOps), replayed as ONE CUDA graph per rank when capture succeeds.
+
+    Static buffers: `inputs[i]` / `masks[i]` are where K1 must write this rank's slabs (pass them as `outs=` to
+    agg_mean_var); `volumes` / `mask_volumes` are the assembled results, overwritten by the next call.  Every rank must
+    construct and call it collectively; a rank may not start call k + 1 before all ranks finished call k (the closing
+    barrier of a call gives that in stream order)."""
+
+    def __init__(self, net: "RegNetwork", dims: Sequence[int], rank: int, world: int, device, group=None,
+                 c_in: int = 8, use_graph: bool = True):
+        from . import parallel
+        self.net, self.rank, self.world, self.dims = net, rank, world, list(dims)
+        per_rank = sum(d ** 3 for d in dims) // world
+        self.arena = _Arena(int(per_rank * 4 * 64) + (64 << 20), device, group)   # ~60 channel-volumes of activations
+        self.inputs = [self.arena.alloc((1, c_in, d // world, d, d)) for d in dims]
+        self.masks = [self.arena.alloc((1, 1, d // world, d, d)) for d in dims]
+        self._mark = self.arena.used
+        c_out = [net.out_layers[i].weight.shape[0] for i in range(len(dims))]
+        self.volumes = [torch.empty((1, c, d, d, d), device=device) for c, d in zip(c_out, dims)]
+        self.mask_volumes = [torch.empty((1, 1, d, d, d), device=device) for d in dims]
+        self.graph = None
+        with torch.no_grad():
+            self._run()  # warm-up: cuDNN plans, packed weights
+            torch.cuda.synchronize(device)
+            if use_graph:
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._run()
+                    self.graph = g
+                except Exception as exc:  # noqa: BLE001 -- eager peer path keeps working
+                    import sys
+                    sys.stderr.write(f"gens_b200: CUDA-graph capture of the slab regulariser failed ({exc}); running eagerly\n")
+                    torch.cuda.synchronize(device)
+
+    def _run(self):
+        from .parallel import slab_bounds
+        self.arena.used = self._mark
+        ops = _PeerOps(self.arena, self.rank, self.world)
+        ops._packed = getattr(self, "_packed", {})
+        self._packed = ops._packed
+        self.arena.barrier()  # K1 of every rank has written its inputs
+        outs = self.net._run(self.inputs, ops)
+        outs = [o if o.data_ptr() >= self.arena.base and o.data_ptr() < self.arena.base + self.arena.size else ops._own(o)
+                for o in outs]
+        self.arena.barrier()  # every rank's results are final
+        for slabs, full in ((outs, self.volumes), (self.masks, self.mask_volumes)):
+            for s, f, d in zip(slabs, full, self.dims):
+                for r in range(self.world):  # pull every rank's slab (own included) into the full tensor
+                    a0, a1 = slab_bounds(d, r, self.world)
+                    f[:, :, a0:a1].copy_(self.arena.peer(r, s))
+        self.arena.barrier()  # nobody overwrites its arena (next call) while a peer still reads it
+
+    def __call__(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            with torch.no_grad():
+                self._run()
+        return self.volumes, self.mask_volumes

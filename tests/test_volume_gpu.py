@@ -265,7 +265,8 @@ def test_fused_slab_exchange_two_gpus():
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs of one node")
 def test_slab_regulariser_handoff_two_gpus():
     """K1 slabs -> slab-parallel RegNetwork -> gather of the 4-channel results, on 2 ranks at the config-2
-    sizes, against the whole-volume pipeline on every rank (bench.py's `regularise` leg carries the check)."""
+    sizes, against the whole-volume pipeline on every rank (bench.py's `regularise` leg carries the check), through
+    NCCL messages and through NVLink peer memory + CUDA graph (reg_network.PeerSlabRegulariser)."""
     import json, os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
@@ -276,6 +277,7 @@ def test_slab_regulariser_handoff_two_gpus():
     line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     reg = line["regularise"]
     assert reg["verified"]["as_accurate_as_the_whole_volume_pipeline"] is True, reg
+    assert reg["peer_memory"] is not None and reg["peer_memory"]["as_accurate_as_the_whole_volume_pipeline"] is True, reg
     assert line["verified"]["slabs_bit_identical"] is True
     assert reg["gathered_bytes_per_gpu"] * 9 == reg["gathered_bytes_if_volumes_were_exchanged_first"] * 5
 
