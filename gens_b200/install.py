@@ -9,7 +9,9 @@ What is replaced (and only this): `models.modules.volume.Volume`, `models.module
 ImplicitSurface` / `sample_pdf`, and the by-value imports of `lookup_volume`, `lookup_feature`,
 `surface_patch_warp` in `models.modules.{projector,sdf_network,implicit_surface}` (the reference imports
 them with `from .projector import ...`, so the importing modules' globals are patched too), plus
-`models.gens.Volume` / `models.gens.ImplicitSurface`, and `compute_LNCC` in `models.losses.{ncc,loss}`.  The reference's own `cuda_gridsample` JIT build is
+`models.gens.Volume` / `models.gens.ImplicitSurface`, `compute_LNCC` in `models.losses.{ncc,loss}`, and (regulariser=True)
+`RegNetwork` in `models.modules.reg_network` / `models.gens` -- same parameter names; with autograd enabled it runs the
+reference's own op sequence, under no_grad on CUDA the K13 kernels.  The reference's own `cuda_gridsample` JIT build is
 never triggered: a stub module is registered first, so no nvcc run happens at import time.
 """
 from __future__ import annotations
@@ -18,8 +20,8 @@ import sys
 import types
 
 
-def install(stub_grid_sample_ext: bool = True):
-    from . import implicit_surface, networks, projector, volume
+def install(stub_grid_sample_ext: bool = True, regulariser: bool = True):
+    from . import implicit_surface, networks, projector, reg_network, volume
 
     if stub_grid_sample_ext and "models.modules.grid_sample_cuda.cuda_gridsample" not in sys.modules:
         # the reference JIT-builds its extension at import (cuda_gridsample.py:5); our autograd triple
@@ -70,7 +72,11 @@ def install(stub_grid_sample_ext: bool = True):
         ref_loss.compute_LNCC = losses.compute_LNCC
     except ImportError:
         pass
+    if regulariser:
+        importlib.import_module("models.modules.reg_network").RegNetwork = reg_network.RegNetwork
     if "models.gens" in sys.modules:
         gens = sys.modules["models.gens"]
         gens.Volume, gens.ImplicitSurface = volume.Volume, implicit_surface.ImplicitSurface
+        if regulariser:
+            gens.RegNetwork = reg_network.RegNetwork
     return {"volume": ref_volume, "implicit_surface": ref_surface, "projector": ref_projector}

@@ -15,11 +15,16 @@ def test_install_patches_reference_modules():
     sys.modules.setdefault("mcubes", types.ModuleType("mcubes"))
     try:
         import gens_b200
+        from gens_b200.config import gens_model_conf
         mods = gens_b200.install()
         assert mods["volume"].Volume is gens_b200.Volume
         assert mods["implicit_surface"].ImplicitSurface is gens_b200.ImplicitSurface
         import models.modules.sdf_network as ref_sdf
         assert ref_sdf.lookup_volume is gens_b200.lookup_volume
+        import models.modules.reg_network as ref_reg
+        assert ref_reg.RegNetwork is gens_b200.RegNetwork
+        assert set(ref_reg.RegNetwork(gens_model_conf()["reg_network"]).state_dict()) >= {
+            "conv0.conv.weight", "encoder_layers.4.1.conv.weight", "decoder_layers.0.conv.weight", "out_layers.2.bias"}
         # the reference's own JIT build of gridsample_grad2 must not have been triggered
         assert "gridsample_grad2" not in sys.modules
         # constructor / method surface the callers rely on (gens.py:70, :143, :155)
