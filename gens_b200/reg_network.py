@@ -149,9 +149,13 @@ class _Ops:
         y = self._new((1, c_out, d, h, wd), x.device)
         stats = torch.zeros(2 * c_out, device=x.device, dtype=torch.float64) if want_stats else None
         null = ctypes.c_void_p(0)
+        # contiguous copies of the halo planes (peer-memory views are strided) must BOTH stay referenced until the launch:
+        # a temporary released between two argument evaluations hands its block to the next one
+        lo_c = lo.contiguous() if lo is not None else None
+        hi_c = hi.contiguous() if hi is not None else None
         _lib.check(_lib.lib().gens_conv3d_k3(
-            _lib.ptr(x), _lib.ptr(lo.contiguous()) if lo is not None else null,
-            _lib.ptr(hi.contiguous()) if hi is not None else null, _lib.ptr(pk),
+            _lib.ptr(x), _lib.ptr(lo_c) if lo_c is not None else null,
+            _lib.ptr(hi_c) if hi_c is not None else null, _lib.ptr(pk),
             _lib.ptr(conv.bias.detach()) if conv.bias is not None else null, c_in, c_out, d, h, wd, _lib.ptr(y),
             _lib.ptr(stats) if want_stats else null, _lib.stream_ptr(x.device)), "gens_conv3d_k3")
         return y, stats
@@ -208,7 +212,8 @@ class _Ops:
         y = self._new((1, c_out) + shape, x.device)
         stats = torch.zeros(2 * c_out, device=x.device, dtype=torch.float64)
         fn = _lib.lib().gens_deconv3d_k3s2 if u.transposed else _lib.lib().gens_conv3d_k3s2
-        _lib.check(fn(_lib.ptr(x), _lib.ptr(halo.contiguous()) if halo is not None else ctypes.c_void_p(0), _lib.ptr(pk),
+        halo_c = halo.contiguous() if halo is not None else None  # referenced until the launch
+        _lib.check(fn(_lib.ptr(x), _lib.ptr(halo_c) if halo_c is not None else ctypes.c_void_p(0), _lib.ptr(pk),
                       c_in, c_out, d, h, wd, _lib.ptr(y), _lib.ptr(stats), _lib.stream_ptr(x.device)),
                    "gens_deconv3d_k3s2" if u.transposed else "gens_conv3d_k3s2")
         return y, stats

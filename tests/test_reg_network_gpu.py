@@ -116,6 +116,32 @@ def test_k13_strided_and_transposed_on_slabs(cuda_lib):
         assert torch.all((got.double() - ref).abs() <= 1e-6 * ref.abs().max() + 1e-5 * ref.abs()), ("up", a0, a1)
 
 
+def test_slab_ops_accept_strided_halo_views(cuda_lib):
+    """A middle rank of the peer-memory path hands BOTH halo planes as strided views of the neighbours' tensors
+    (x[:, :, -1:] / x[:, :, :1]); their contiguous copies must both be alive at the launch (regression: the first copy
+    was released before the second was made, and the second took over its block)."""
+    import torch.nn as nn
+    from gens_b200.reg_network import _Ops, _Unit
+    g = torch.Generator().manual_seed(21)
+    full = torch.randn(1, 8, 24, 16, 64, generator=g).to(DEV)
+    ops = _Ops()
+    for unit, ref_fn in ((_Unit(8, 8), lambda w: F.conv3d(full.double(), w.double(), None, padding=1)),):
+        unit = unit.to(DEV)
+        want = ref_fn(unit.conv.weight)
+        a0, a1 = 8, 16
+        lo, hi = full[:, :, a0 - 1:a0], full[:, :, a1:a1 + 1]          # non-contiguous (channel stride = 24 planes)
+        assert not lo.is_contiguous() and not hi.is_contiguous()
+        got, _ = ops._conv_k13(full[:, :, a0:a1].contiguous(), unit.conv, lo, hi, True)
+        torch.cuda.synchronize()
+        ref = want[:, :, a0:a1]
+        assert torch.all((got.double() - ref).abs() <= 1e-6 * ref.abs().max() + 1e-5 * ref.abs())
+    out = nn.Conv3d(8, 4, 3, 1, 1).to(DEV)
+    want = F.conv3d(full.double(), out.weight.double(), out.bias.double(), padding=1)[:, :, 8:16]
+    got, _ = ops._conv_k13(full[:, :, 8:16].contiguous(), out, full[:, :, 7:8], full[:, :, 16:17], False)
+    torch.cuda.synchronize()
+    assert torch.all((got.double() - want).abs() <= 1e-6 * want.abs().max() + 1e-5 * want.abs())
+
+
 def test_instnorm_relu_kernel(cuda_lib):
     from gens_b200 import _lib
     g = torch.Generator().manual_seed(9)

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 if [ "$N" = "2" ]; then
   python -m pytest tests -m gpu -q -k "two_gpus" > gpurun_out/r2v_pytest2.log 2>&1; echo "pytest2 rc=$?"; tail -2 gpurun_out/r2v_pytest2.log
 fi
-if [ "$N" = "8" ]; then
+if [ "$N" = "8" ] && [ -z "$SKIP_CHECK" ]; then
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29571 tools/check_fused_slabs.py > gpurun_out/r2v_fused8.log 2>&1; echo "check rc=$?"
   grep -E "world 8" gpurun_out/r2v_fused8.log; grep -c "bit-identical to the 1-GPU build: True" gpurun_out/r2v_fused8.log
 fi
