@@ -382,10 +382,7 @@ class _PeerOps(_Ops):
         mine = self.arena.alloc(stats.shape, torch.float64)
         mine.copy_(stats)
         self.arena.barrier()  # every rank's moments are written (and everyone is done reading the input's halos)
-        total = self.arena.peer(0, mine).clone()
-        for r in range(1, self.world):
-            total += self.arena.peer(r, mine)
-        return total
+        return torch.stack([self.arena.peer(r, mine) for r in range(self.world)]).sum(0)  # two launches, not P
 
     def _publish(self):
         self.arena.barrier()
@@ -451,4 +448,8 @@ class PeerSlabRegulariser:
         else:
             with torch.no_grad():
                 self._run()
+        # a replay rewrites the static outputs without bumping their _version: derived-data caches keyed on tensor
+        # versions (channels-last copies of the volumes, the TV value) must not outlive it
+        from . import projector
+        projector.clear_caches()
         return self.volumes, self.mask_volumes
