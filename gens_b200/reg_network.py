@@ -15,10 +15,15 @@ the SAME network on the x-slabs K1 leaves on each rank instead:
     all-reduce of 2C numbers per layer combines them (parallel-variance formula, accumulated in float64);
   * only the 4-channel results (and the 1-channel masks) are gathered afterwards: 384 MB instead of 690 MB per
     build, and the network itself runs on 1/P of the voxels per GPU.
-Kernels: the stride-1 layers at the fine scales and every InstanceNorm run on K13 (csrc/conv3d.cu) -- in cuDNN / ATen
-those take 98 of the network's 112 ms on one B200; the stride-2 / transposed / deep narrow layers stay cuDNN (library
-calls, counted as such).  The slab path is inference only (like the other sharded paths): the reference trains with one
-scene per GPU (DDP replicas), and with autograd enabled `forward` is the reference's own op sequence.
+Two transports for those exchanges: NCCL messages (`_Ops`: point-to-point halo planes, a 2C-double all-reduce per
+layer, all-gathers of the results; also what the gloo tests run) and NVLink peer memory (`_PeerOps` /
+`PeerSlabRegulariser`: layer outputs in a symmetric arena, halos and moments read from the neighbours in place, device
+barriers, the whole step replayed as one CUDA graph per rank).
+Kernels: the layers with up to 16 output channels (stride 1, stride 2, transposed stride 2) and every InstanceNorm run
+on K13 (csrc/conv3d.cu) -- in cuDNN / ATen those take ~105 of the network's 112 ms on one B200; the deep narrow layers
+(32^3 and coarser) stay cuDNN (library calls, counted as such).  The slab path is inference only (like the other sharded
+paths): the reference trains with one scene per GPU (DDP replicas), and with autograd enabled `forward` is the
+reference's own op sequence.
 """
 from __future__ import annotations
 
@@ -70,10 +75,10 @@ class _LocalOps:
 
 class _Ops:
     """Inference ops on x-slabs (planes of tensor dim 2) of every tensor on `world` ranks; rank r owns planes
-    [r d/P, (r+1) d/P).  world = 1: whole volumes.  On CUDA the stride-1 layers with c_in % 8 == 0 and c_out in
-    {4, 8, 16} run on K13 (csrc/conv3d.cu: direct FFMA2 convolution that also reduces the InstanceNorm moments, halo
-    planes read in place) and every normalisation on its in-place kernel; the rest (stride 2, transposed, the deep
-    narrow levels) is cuDNN with the moments taken by torch.var_mean."""
+    [r d/P, (r+1) d/P).  world = 1: whole volumes.  On CUDA the layers with c_in % 8 == 0 and up to 16 output channels
+    run on K13 (csrc/conv3d.cu: direct FFMA2 convolutions -- stride 1, stride 2, transposed stride 2 -- that also reduce
+    the InstanceNorm moments and read the halo planes through their own pointers) and every normalisation on its
+    in-place kernel; the deep narrow levels are cuDNN with the moments taken by torch.var_mean."""
 
     def __init__(self, rank: int = 0, world: int = 1, group=None):
         self.rank, self.world, self.group = rank, world, group
