@@ -43,3 +43,18 @@ def test_install_patches_reference_modules():
         sys.path.remove(REF)
         for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
             del sys.modules[k]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+def test_install_can_leave_the_regulariser_alone():
+    sys.path.insert(0, REF)
+    sys.modules.setdefault("mcubes", types.ModuleType("mcubes"))
+    try:
+        import gens_b200
+        gens_b200.install(regulariser=False)
+        import models.modules.reg_network as ref_reg
+        assert ref_reg.RegNetwork is not gens_b200.RegNetwork and ref_reg.RegNetwork.__module__ == "models.modules.reg_network"
+    finally:
+        sys.path.remove(REF)
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]
