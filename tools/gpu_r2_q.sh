@@ -1,2 +1,3 @@
 #!/bin/bash
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q -x > gpurun_out/r2_final_pytest.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/r2_final_pytest.log
